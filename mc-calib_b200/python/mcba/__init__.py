@@ -1,0 +1,293 @@
+"""ctypes view of the libmcba C ABI (include/mcba.h) plus numpy-backed problem/parameter holders.
+
+This is host-side plumbing for tests and bench.py: it never computes anything itself and it does
+not fall back to the CPU oracle. `load_lib()` raises if the CUDA library is missing.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.abspath(os.path.join(_HERE, "..", "..", ".."))
+LIB_PATH = os.path.join(REPO, "mc-calib_b200", "csrc", "libmcba.so")
+ORACLE_PATH = os.path.join(REPO, "oracle", "liboracle.so")
+
+c_f32p = C.POINTER(C.c_float)
+c_f64p = C.POINTER(C.c_double)
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_u8p = C.POINTER(C.c_uint8)
+
+
+class mcba_problem(C.Structure):
+    _fields_ = [
+        ("stage", C.c_int32), ("n_cam", C.c_int32), ("n_pose", C.c_int32), ("n_board", C.c_int32),
+        ("n_pts", C.c_int32), ("n_obs", C.c_int64), ("n_bobs", C.c_int64),
+        ("u", c_f32p), ("v", c_f32p), ("pt_idx", c_i32p), ("bobs_ptr", c_i64p),
+        ("bobs_cam", c_i32p), ("bobs_pose", c_i32p), ("bobs_board", c_i32p),
+        ("pts_xyz", c_f32p), ("cam_model", c_i32p), ("cam_is_ref", c_u8p), ("board_is_ref", c_u8p),
+        ("cam_problem", c_i32p), ("n_problems", C.c_int32),
+    ]
+
+
+class mcba_params(C.Structure):
+    _fields_ = [("cam_pose", c_f64p), ("pose", c_f64p), ("board_pose", c_f64p), ("intrinsics", c_f64p)]
+
+
+class mcba_options(C.Structure):
+    _fields_ = [
+        ("max_num_iterations", C.c_int32), ("function_tolerance", C.c_double),
+        ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
+        ("initial_trust_region_radius", C.c_double), ("max_trust_region_radius", C.c_double),
+        ("min_trust_region_radius", C.c_double), ("min_relative_decrease", C.c_double),
+        ("min_lm_diagonal", C.c_double), ("max_lm_diagonal", C.c_double), ("huber_a", C.c_double),
+        ("jacobi_scaling", C.c_int32), ("max_num_consecutive_invalid_steps", C.c_int32),
+        ("verbose", C.c_int32), ("materialize_jacobian", C.c_int32),
+    ]
+
+
+class mcba_summary(C.Structure):
+    _fields_ = [
+        ("termination", C.c_int32), ("num_successful_steps", C.c_int32),
+        ("num_unsuccessful_steps", C.c_int32), ("num_iterations", C.c_int32),
+        ("initial_cost", C.c_double), ("final_cost", C.c_double), ("rms_px", C.c_double),
+        ("t_total_ms", C.c_double), ("t_jacobian_ms", C.c_double), ("t_schur_ms", C.c_double),
+        ("t_chol_ms", C.c_double), ("t_cost_ms", C.c_double), ("t_comm_ms", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class mcba_trace_row(C.Structure):
+    _fields_ = [
+        ("iteration", C.c_int32), ("step_is_valid", C.c_int32), ("step_is_successful", C.c_int32),
+        ("_pad", C.c_int32), ("cost", C.c_double), ("cost_change", C.c_double),
+        ("gradient_max_norm", C.c_double), ("step_norm", C.c_double),
+        ("relative_decrease", C.c_double), ("trust_region_radius", C.c_double),
+    ]
+
+
+def default_options(max_num_iterations=1000, **kw):
+    """Ceres 2.2.0 Solver::Options defaults + the reference's max_num_iterations (YAML number_iterations)."""
+    o = mcba_options(max_num_iterations, 1e-6, 1e-10, 1e-8, 1e4, 1e16, 1e-32, 1e-3, 1e-6, 1e32, 1.0, 1, 5, 0, 0)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+STAGE_K = {1: 15, 2: 12, 3: 12, 4: 18, 5: 27}
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t) if a is not None else t()
+
+
+class Problem:
+    """Owns the numpy arrays behind a mcba_problem (keeps them alive and contiguous)."""
+
+    def __init__(self, stage, u, v, pt_idx, bobs_ptr, bobs_cam, bobs_pose, bobs_board, pts_xyz,
+                 cam_model, n_pose, n_board, cam_is_ref=None, board_is_ref=None, cam_problem=None,
+                 n_problems=1):
+        self.stage = int(stage)
+        self.u = np.ascontiguousarray(u, np.float32)
+        self.v = np.ascontiguousarray(v, np.float32)
+        self.pt_idx = np.ascontiguousarray(pt_idx, np.int32)
+        self.bobs_ptr = np.ascontiguousarray(bobs_ptr, np.int64)
+        self.bobs_cam = np.ascontiguousarray(bobs_cam, np.int32)
+        self.bobs_pose = np.ascontiguousarray(bobs_pose, np.int32)
+        self.bobs_board = np.ascontiguousarray(bobs_board, np.int32)
+        self.pts_xyz = np.ascontiguousarray(pts_xyz, np.float32).reshape(-1, 3)
+        self.cam_model = np.ascontiguousarray(cam_model, np.int32)
+        self.n_cam = len(self.cam_model)
+        self.n_pose = int(n_pose)
+        self.n_board = int(n_board)
+        self.cam_is_ref = None if cam_is_ref is None else np.ascontiguousarray(cam_is_ref, np.uint8)
+        self.board_is_ref = None if board_is_ref is None else np.ascontiguousarray(board_is_ref, np.uint8)
+        self.cam_problem = None if cam_problem is None else np.ascontiguousarray(cam_problem, np.int32)
+        self.n_problems = int(n_problems)
+
+    @property
+    def n_obs(self):
+        return len(self.u)
+
+    @property
+    def n_bobs(self):
+        return len(self.bobs_cam)
+
+    def with_stage(self, stage):
+        p = Problem.__new__(Problem)
+        p.__dict__.update(self.__dict__)
+        p.stage = int(stage)
+        return p
+
+    def c(self):
+        s = mcba_problem()
+        s.stage, s.n_cam, s.n_pose, s.n_board = self.stage, self.n_cam, self.n_pose, self.n_board
+        s.n_pts, s.n_obs, s.n_bobs = len(self.pts_xyz), self.n_obs, self.n_bobs
+        s.u, s.v, s.pt_idx = _ptr(self.u, c_f32p), _ptr(self.v, c_f32p), _ptr(self.pt_idx, c_i32p)
+        s.bobs_ptr = _ptr(self.bobs_ptr, c_i64p)
+        s.bobs_cam, s.bobs_pose, s.bobs_board = (_ptr(self.bobs_cam, c_i32p), _ptr(self.bobs_pose, c_i32p),
+                                                 _ptr(self.bobs_board, c_i32p))
+        s.pts_xyz, s.cam_model = _ptr(self.pts_xyz, c_f32p), _ptr(self.cam_model, c_i32p)
+        s.cam_is_ref, s.board_is_ref = _ptr(self.cam_is_ref, c_u8p), _ptr(self.board_is_ref, c_u8p)
+        s.cam_problem, s.n_problems = _ptr(self.cam_problem, c_i32p), self.n_problems
+        return s
+
+
+class Params:
+    def __init__(self, cam_pose, pose, board_pose, intrinsics):
+        f = lambda a, w: np.ascontiguousarray(np.asarray(a, np.float64).reshape(-1, w)).copy()
+        self.cam_pose, self.pose = f(cam_pose, 6), f(pose, 6)
+        self.board_pose, self.intrinsics = f(board_pose, 6), f(intrinsics, 9)
+
+    def copy(self):
+        return Params(self.cam_pose, self.pose, self.board_pose, self.intrinsics)
+
+    def c(self):
+        return mcba_params(_ptr(self.cam_pose, c_f64p), _ptr(self.pose, c_f64p),
+                           _ptr(self.board_pose, c_f64p), _ptr(self.intrinsics, c_f64p))
+
+
+_lib = None
+
+
+def load_lib():
+    """Load libmcba.so (the CUDA product). Raises if it has not been built: there is no CPU fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python __graft_entry__.py` (build()) first; "
+                           "libmcba has no CPU fallback")
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, vpp = C.c_void_p, C.POINTER(C.c_void_p)
+    L.mcba_default_options.argtypes = [C.POINTER(mcba_options)]
+    L.mcba_default_options.restype = None
+    L.mcba_create.argtypes = [vpp, C.POINTER(mcba_problem), C.c_int]
+    L.mcba_set_stage.argtypes = [vp, C.c_int]
+    L.mcba_nccl_unique_id.argtypes = [vp]
+    L.mcba_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.mcba_solve.argtypes = [vp, C.POINTER(mcba_params), C.POINTER(mcba_options), C.POINTER(mcba_summary),
+                             C.POINTER(mcba_trace_row), C.c_int]
+    L.mcba_solve_batched.argtypes = [vp, C.POINTER(mcba_params), C.POINTER(mcba_options), C.POINTER(mcba_summary)]
+    L.mcba_solve_begin.argtypes = [vp, C.POINTER(mcba_params), C.POINTER(mcba_options)]
+    L.mcba_solve_step.argtypes = [vp]
+    L.mcba_solve_end.argtypes = [vp, C.POINTER(mcba_params), C.POINTER(mcba_summary)]
+    L.mcba_eval.argtypes = [vp, C.POINTER(mcba_params), C.POINTER(mcba_options), c_f64p, c_f64p, c_f64p]
+    L.mcba_jacobian_width.argtypes = [C.c_int]
+    L.mcba_reprojection_errors.argtypes = [vp, C.POINTER(mcba_params), c_f64p]
+    L.mcba_destroy.argtypes = [vp]
+    L.mcba_destroy.restype = None
+    L.mcba_last_error.argtypes = [vp]
+    L.mcba_last_error.restype = C.c_char_p
+    L.mcba_num_kernels.argtypes = []
+    L.mcba_kernel_name.argtypes = [C.c_int]
+    L.mcba_kernel_name.restype = C.c_char_p
+    L.mcba_kernel_stats.argtypes = [vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    L.mcba_reset_kernel_stats.argtypes = [vp]
+    _lib = L
+    return L
+
+
+class McbaError(RuntimeError):
+    pass
+
+
+class Handle:
+    """RAII wrapper of a libmcba handle; mirrors the call sequence of a reference refine* stage:
+    build the problem (mcba_create) then solve (mcba_solve)."""
+
+    def __init__(self, problem, device=0):
+        self.lib = load_lib()
+        self.problem = problem
+        self.h = C.c_void_p()
+        cp = problem.c()
+        rc = self.lib.mcba_create(C.byref(self.h), C.byref(cp), device)
+        if rc != 0:
+            msg = self.lib.mcba_last_error(self.h)
+            raise McbaError(f"mcba_create failed rc={rc}: {msg.decode() if msg else ''}")
+
+    def _check(self, rc, what):
+        if rc < 0:
+            msg = self.lib.mcba_last_error(self.h)
+            raise McbaError(f"{what} failed rc={rc}: {msg.decode() if msg else ''}")
+        return rc
+
+    def set_stage(self, stage):
+        self._check(self.lib.mcba_set_stage(self.h, stage), "mcba_set_stage")
+        self.problem = self.problem.with_stage(stage)
+
+    def comm_init(self, rank, n_ranks, uid_bytes):
+        buf = C.create_string_buffer(bytes(uid_bytes), 128)
+        self._check(self.lib.mcba_comm_init(self.h, rank, n_ranks, buf), "mcba_comm_init")
+
+    def solve(self, params, opt=None, trace_cap=2048):
+        opt = opt or default_options()
+        summ = mcba_summary()
+        trace = (mcba_trace_row * trace_cap)()
+        cp = params.c()
+        self._check(self.lib.mcba_solve(self.h, C.byref(cp), C.byref(opt), C.byref(summ), trace, trace_cap),
+                    "mcba_solve")
+        return summ, [trace[i] for i in range(min(trace_cap, summ.num_iterations))]
+
+    def solve_batched(self, params, opt=None):
+        opt = opt or default_options()
+        summ = (mcba_summary * self.problem.n_problems)()
+        cp = params.c()
+        self._check(self.lib.mcba_solve_batched(self.h, C.byref(cp), C.byref(opt), summ), "mcba_solve_batched")
+        return list(summ)
+
+    def solve_begin(self, params, opt):
+        cp = params.c()
+        self._check(self.lib.mcba_solve_begin(self.h, C.byref(cp), C.byref(opt)), "mcba_solve_begin")
+
+    def solve_step(self):
+        return self._check(self.lib.mcba_solve_step(self.h), "mcba_solve_step")
+
+    def solve_end(self, params):
+        summ = mcba_summary()
+        cp = params.c()
+        self._check(self.lib.mcba_solve_end(self.h, C.byref(cp), C.byref(summ)), "mcba_solve_end")
+        return summ
+
+    def eval(self, params, opt=None, want_jac=True):
+        opt = opt or default_options()
+        K = STAGE_K[self.problem.stage]
+        n = self.problem.n_obs
+        cost = C.c_double()
+        res = np.zeros((n, 2))
+        jac = np.zeros((n, 2, K)) if want_jac else None
+        cp = params.c()
+        self._check(self.lib.mcba_eval(self.h, C.byref(cp), C.byref(opt), C.byref(cost), _ptr(res, c_f64p),
+                                       _ptr(jac, c_f64p)), "mcba_eval")
+        return cost.value, res, jac
+
+    def reprojection_errors(self, params):
+        err = np.zeros(self.problem.n_obs)
+        cp = params.c()
+        self._check(self.lib.mcba_reprojection_errors(self.h, C.byref(cp), _ptr(err, c_f64p)),
+                    "mcba_reprojection_errors")
+        return err
+
+    def kernel_stats(self):
+        out = {}
+        for k in range(self.lib.mcba_num_kernels()):
+            n, ms = C.c_int64(), C.c_double()
+            self.lib.mcba_kernel_stats(self.h, k, C.byref(n), C.byref(ms))
+            out[self.lib.mcba_kernel_name(k).decode()] = (n.value, ms.value)
+        return out
+
+    def reset_kernel_stats(self):
+        self.lib.mcba_reset_kernel_stats(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.mcba_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
