@@ -161,6 +161,10 @@ const char *mcba_kernel_name(int k);
 int mcba_kernel_stats(void *handle, int k, int64_t *launches, double *total_ms);
 int mcba_reset_kernel_stats(void *handle);
 
+/* Test hook: copy an internal device buffer (normal-equation blocks, reduced system, scaling) to the host.
+ * Names: "FF" "gf" "S" "rhs" "zf" "ZtZ" "Hoo" "Wt" "Z" "brec" "scale_e" "scale_f" "diag_e" "diag_f". */
+int mcba_debug_fetch(void *handle, const char *name, double *out, int64_t cap, int64_t *n_out);
+
 #ifdef __cplusplus
 }
 #endif

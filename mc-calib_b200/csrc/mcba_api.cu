@@ -1,0 +1,847 @@
+// mcba_api.cu — libmcba: C ABI (include/mcba.h), host packer and the Levenberg-Marquardt driver.
+//
+// The driver restates ceres-solver 2.2.0's TrustRegionMinimizer + LevenbergMarquardtStrategy with the
+// options the reference uses (SPARSE_SCHUR, max_num_iterations, all else default;
+// /root/reference/McCalib/src/CameraGroup.cpp:463-468, Object3D.cpp:218-223, Camera.cpp:296-301):
+// SURVEY.md Appendix B lists the rules. All arithmetic of the path runs in the CUDA kernels of
+// mcba_kernels.cuh; the host only takes the accept/reject/terminate decisions from a handful of scalars.
+// There is no CPU fallback: every entry point fails with MCBA_ERR_CUDA when no sm_100 device is usable.
+#include "../../include/mcba.h"
+#include "mcba_kernels.cuh"
+
+#include <dlfcn.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+using namespace mcba;
+
+// ---- NCCL through dlopen (no link-time dependency; torch's bundled libnccl is reused when loaded) -------
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef void* nccl_comm_t;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(nccl_uid_t*) = nullptr;
+  int (*CommInitRank)(nccl_comm_t*, int, nccl_uid_t, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(nccl_comm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load() {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) return false;
+    GetUniqueId = (int (*)(nccl_uid_t*))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (int (*)(nccl_comm_t*, int, nccl_uid_t, int))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    AllGather = (int (*)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t))dlsym(lib, "ncclAllGather");
+    CommDestroy = (int (*)(nccl_comm_t))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && AllReduce && AllGather && CommDestroy;
+  }
+};
+static NcclApi g_nccl;
+constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;
+
+// ---- kernel families for timing -------------------------------------------------------------------------
+enum { KF_PREP = 0, KF_FUSED, KF_MATERIALIZE, KF_FROM_J, KF_COST, KF_EASSEMBLE, KF_PAIR, KF_EFACTOR, KF_SYRK,
+       KF_REDUCED, KF_CHOL, KF_BACKSUBST, KF_REDUCE, KF_NCCL, KF_COUNT };
+static const char* kKernelNames[KF_COUNT] = {
+    "prep_blocks", "resid_jac_fused", "resid_jac_materialize", "accumulate_from_jacobian", "cost_only",
+    "eblock_assemble", "pair_reduce", "eblock_factor", "schur_syrk", "build_reduced", "cholesky", "backsubst",
+    "reduce_misc", "nccl"};
+
+struct Handle {
+  std::string err;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  // problem (host copies of the small things)
+  int stage = 0, n_cam = 0, n_pose = 0, n_board = 0, n_pts = 0, nb = 0;
+  int64_t n_obs = 0, npad = 0;
+  std::vector<int32_t> h_bobs_cam, h_bobs_pose, h_bobs_board;
+  // static device data
+  float *d_u = nullptr, *d_v = nullptr; int32_t* d_pt = nullptr; double* d_pts = nullptr;
+  int4* d_bobs = nullptr; int* d_pose_bobs_ptr = nullptr;
+  int32_t* d_cam_model = nullptr; uint8_t *d_cam_is_ref = nullptr, *d_board_is_ref = nullptr;
+  // stage-dependent
+  int Wc = 0, Wb = 0, n_f = 0, ldz = 0, n_pair = 0, n_chunks = 0, NT = 0, NE = 0, K = 0;
+  int* d_pair_bobs = nullptr; PairChunk* d_chunks = nullptr; int* d_pair_chunk_ptr = nullptr;
+  double *d_brec = nullptr, *d_cost_bobs = nullptr, *d_Hoo = nullptr, *d_Wt = nullptr, *d_Z = nullptr, *d_L = nullptr;
+  double *d_scale_e = nullptr, *d_diag_e = nullptr, *d_scale_f = nullptr, *d_diag_f = nullptr;
+  double *d_FF = nullptr, *d_gf = nullptr, *d_S = nullptr, *d_rhs = nullptr, *d_zf = nullptr, *d_ZtZ = nullptr;
+  double *d_syrk_partial = nullptr, *d_pair_partial = nullptr, *d_pair_rec = nullptr, *d_part_e = nullptr;
+  double *d_red_scratch = nullptr, *d_scalars = nullptr, *d_gather = nullptr;
+  int* d_fail = nullptr;
+  double *d_jmat = nullptr, *d_resmat = nullptr;   // lazily allocated
+  int syrk_nt = 0, syrk_tiles = 0, syrk_nsplit = 0; int64_t syrk_rows_per_split = 0;
+  // parameters: two copies (current / candidate), swapped on acceptance
+  double *d_cam_pose[2] = {nullptr, nullptr}, *d_pose[2] = {nullptr, nullptr}, *d_board[2] = {nullptr, nullptr},
+         *d_intr[2] = {nullptr, nullptr};
+  double *d_prep_cam = nullptr, *d_prep_pose = nullptr, *d_prep_board = nullptr;
+  int cur = 0;
+  // comm
+  int rank = 0, n_ranks = 1; nccl_comm_t comm = nullptr;
+  // LM state
+  mcba_options opt;
+  bool solving = false, done = false;
+  double radius = 0, decrease_factor = 2, x_cost = 0, x_norm = 0, grad_max = 0, minimum_cost = 0, cand_cost = 0;
+  bool reuse_diagonal = false, at_least_one_success = false, have_scale = false;
+  int num_consecutive_invalid = 0, termination = MCBA_NO_CONVERGENCE;
+  mcba_trace_row it;
+  mcba_summary summ;
+  std::vector<mcba_trace_row> trace;
+  int64_t n_obs_global = 0;
+  // timing
+  struct Pending { int fam; cudaEvent_t a, b; };
+  std::vector<Pending> pending; std::vector<cudaEvent_t> free_events;
+  int64_t kf_launches[KF_COUNT] = {0}; double kf_ms[KF_COUNT] = {0};
+};
+
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { H->err = std::string(#x) + ": " + cudaGetErrorString(e_); return MCBA_ERR_CUDA; } } while (0)
+#define CHECK_LAUNCH() CU(cudaGetLastError())
+
+static cudaEvent_t get_event(Handle* H) {
+  if (!H->free_events.empty()) { cudaEvent_t e = H->free_events.back(); H->free_events.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+static void flush_timers(Handle* H) {
+  if (H->pending.empty()) return;
+  cudaStreamSynchronize(H->stream);
+  for (auto& p : H->pending) {
+    float ms = 0; cudaEventElapsedTime(&ms, p.a, p.b);
+    H->kf_ms[p.fam] += ms; H->kf_launches[p.fam] += 1;
+    H->free_events.push_back(p.a); H->free_events.push_back(p.b);
+  }
+  H->pending.clear();
+}
+struct Timed {   // RAII: brackets the launches of one kernel family with CUDA events on the library stream
+  Handle* H; int fam; cudaEvent_t a;
+  Timed(Handle* h, int f) : H(h), fam(f) { a = get_event(H); cudaEventRecord(a, H->stream); }
+  ~Timed() { cudaEvent_t b = get_event(H); cudaEventRecord(b, H->stream); H->pending.push_back({fam, a, b}); if (H->pending.size() > 4096) flush_timers(H); }
+};
+
+template <typename T> static int dalloc(Handle* H, T** p, size_t n) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (n == 0) n = 1;
+  CU(cudaMalloc((void**)p, n * sizeof(T)));
+  return 0;
+}
+template <typename T> static void dfree(T** p) { if (*p) { cudaFree(*p); *p = nullptr; } }
+
+struct StageDims { bool cam, intr, board; int K, NT, NE, WF; };
+static StageDims stage_dims(int stage) {
+  switch (stage) {
+    case 1: return {false, true, false, Cols<1>::K, Cols<1>::NT, PairRec<1>::NE, Cols<1>::WF};
+    case 2: return {false, false, true, Cols<2>::K, Cols<2>::NT, PairRec<2>::NE, Cols<2>::WF};
+    case 3: return {true, false, false, Cols<3>::K, Cols<3>::NT, PairRec<3>::NE, Cols<3>::WF};
+    case 4: return {true, false, true, Cols<4>::K, Cols<4>::NT, PairRec<4>::NE, Cols<4>::WF};
+    case 5: return {true, true, true, Cols<5>::K, Cols<5>::NT, PairRec<5>::NE, Cols<5>::WF};
+  }
+  return {false, false, false, 0, 0, 0, 0};
+}
+
+#define DISPATCH_STAGE(stage, ...)                    \
+  switch (stage) {                                    \
+    case 1: { constexpr int ST = 1; __VA_ARGS__; } break; \
+    case 2: { constexpr int ST = 2; __VA_ARGS__; } break; \
+    case 3: { constexpr int ST = 3; __VA_ARGS__; } break; \
+    case 4: { constexpr int ST = 4; __VA_ARGS__; } break; \
+    case 5: { constexpr int ST = 5; __VA_ARGS__; } break; \
+  }
+
+static int setup_stage(Handle* H, int stage) {
+  const StageDims sd = stage_dims(stage);
+  if (sd.K == 0) { H->err = "stage must be 1..5"; return MCBA_ERR_INVALID; }
+  if (sd.board && H->n_board <= 0) { H->err = "stage needs board blocks but n_board == 0"; return MCBA_ERR_INVALID; }
+  H->stage = stage; H->K = sd.K; H->NT = sd.NT; H->NE = sd.NE;
+  H->Wc = (sd.cam ? 6 : 0) + (sd.intr ? 9 : 0);
+  H->Wb = sd.board ? 6 : 0;
+  H->n_f = H->n_cam * H->Wc + (sd.board ? H->n_board * H->Wb : 0);
+  H->ldz = ((H->n_f + 1 + 7) / 8) * 8;
+  // pair lists: pair = cam * nbp + board (board = 0 when the stage has no board block)
+  const int nbp = sd.board ? H->n_board : 1;
+  H->n_pair = H->n_cam * nbp;
+  std::vector<int> cnt(H->n_pair + 1, 0);
+  for (int b = 0; b < H->nb; ++b) cnt[H->h_bobs_cam[b] * nbp + (sd.board ? H->h_bobs_board[b] : 0) + 1]++;
+  for (int p = 0; p < H->n_pair; ++p) cnt[p + 1] += cnt[p];
+  std::vector<int> pair_bobs(std::max(1, H->nb)), fill(cnt.begin(), cnt.end() - 1);
+  for (int b = 0; b < H->nb; ++b) pair_bobs[fill[H->h_bobs_cam[b] * nbp + (sd.board ? H->h_bobs_board[b] : 0)]++] = b;
+  constexpr int CHUNK = 64;
+  std::vector<PairChunk> chunks; std::vector<int> pcp(H->n_pair + 1, 0);
+  for (int p = 0; p < H->n_pair; ++p) {
+    pcp[p] = (int)chunks.size();
+    for (int s = cnt[p]; s < cnt[p + 1]; s += CHUNK) chunks.push_back({p, s, std::min(cnt[p + 1], s + CHUNK), s == cnt[p]});
+  }
+  pcp[H->n_pair] = (int)chunks.size();
+  H->n_chunks = (int)chunks.size();
+  if (dalloc(H, &H->d_pair_bobs, pair_bobs.size())) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_chunks, chunks.size())) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_pair_chunk_ptr, pcp.size())) return MCBA_ERR_CUDA;
+  CU(cudaMemcpy(H->d_pair_bobs, pair_bobs.data(), pair_bobs.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (!chunks.empty()) CU(cudaMemcpy(H->d_chunks, chunks.data(), chunks.size() * sizeof(PairChunk), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(H->d_pair_chunk_ptr, pcp.data(), pcp.size() * sizeof(int), cudaMemcpyHostToDevice));
+  const size_t np = H->n_pose, nf = H->n_f, ldz = H->ldz;
+  if (dalloc(H, &H->d_brec, (size_t)H->nb * H->NT * 64)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_cost_bobs, (size_t)H->nb)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_Hoo, np * 36) || dalloc(H, &H->d_L, np * 36)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_Wt, np * 6 * ldz) || dalloc(H, &H->d_Z, np * 6 * ldz)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_scale_e, np * 6) || dalloc(H, &H->d_diag_e, np * 6)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_scale_f, nf) || dalloc(H, &H->d_diag_f, nf)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_FF, nf * nf) || dalloc(H, &H->d_gf, nf) || dalloc(H, &H->d_S, nf * nf)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_rhs, nf) || dalloc(H, &H->d_zf, nf) || dalloc(H, &H->d_ZtZ, ldz * ldz)) return MCBA_ERR_CUDA;
+  H->syrk_nt = (H->ldz + SY_T - 1) / SY_T;
+  H->syrk_tiles = H->syrk_nt * (H->syrk_nt + 1) / 2;
+  const int64_t n_rows = 6 * (int64_t)H->n_pose;
+  int nsplit = (4 * 148 + H->syrk_tiles - 1) / H->syrk_tiles;
+  nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(nsplit, (n_rows + 63) / 64));
+  H->syrk_rows_per_split = (((n_rows + nsplit - 1) / nsplit + SY_K - 1) / SY_K) * SY_K;
+  if (H->syrk_rows_per_split == 0) H->syrk_rows_per_split = SY_K;
+  H->syrk_nsplit = (int)std::max<int64_t>(1, (n_rows + H->syrk_rows_per_split - 1) / H->syrk_rows_per_split);
+  if (dalloc(H, &H->d_syrk_partial, (size_t)H->syrk_nsplit * H->syrk_tiles * SY_T * SY_T)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_pair_partial, (size_t)H->n_chunks * H->NE)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_pair_rec, (size_t)H->n_pair * H->NE)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_part_e, np * 4)) return MCBA_ERR_CUDA;
+  dfree(&H->d_jmat); dfree(&H->d_resmat);
+  H->have_scale = false;
+  // opt in to > 48 KB dynamic shared memory
+  DISPATCH_STAGE(stage, {
+    const int sm = OBS_WARPS * (CTX_SIZE + Cols<ST>::NBLK * 8 * TS) * 8;
+    CU(cudaFuncSetAttribute(k_observations<ST, MODE_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    CU(cudaFuncSetAttribute(k_observations<ST, MODE_FROM_J>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    CU(cudaFuncSetAttribute(k_eblock_assemble<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * H->ldz * 8));
+  });
+  return MCBA_OK;
+}
+
+// out_dev[m] = column-wise sum (cols < m_sum) / max (others) of in[n][m]; deterministic two-stage
+static int reduce_rows(Handle* H, const double* in, int64_t n, int m, int m_sum, double* out_dev) {
+  Timed t(H, KF_REDUCE);
+  int nblk = (int)std::min<int64_t>(512, std::max<int64_t>(1, (n + 2047) / 2048));
+  const int64_t rpb = (n + nblk - 1) / std::max(1, nblk);
+  if (nblk == 1) {
+    k_reduce_rows<<<1, RED_T, 0, H->stream>>>(in, n, m, m_sum, std::max<int64_t>(n, 1), out_dev);
+  } else {
+    k_reduce_rows<<<nblk, RED_T, 0, H->stream>>>(in, n, m, m_sum, rpb, H->d_red_scratch);
+    k_reduce_rows<<<1, RED_T, 0, H->stream>>>(H->d_red_scratch, nblk, m, m_sum, nblk, out_dev);
+  }
+  CHECK_LAUNCH();
+  return MCBA_OK;
+}
+
+static ObsArgs obs_args(Handle* H, int which, double huber_a) {
+  ObsArgs a;
+  a.u = H->d_u; a.v = H->d_v; a.pt = H->d_pt; a.pts = H->d_pts; a.bobs = H->d_bobs;
+  a.prep_cam = H->d_prep_cam; a.prep_pose = H->d_prep_pose; a.prep_board = H->d_prep_board; a.intr = H->d_intr[which];
+  a.cam_model = H->d_cam_model; a.cam_is_ref = H->d_cam_is_ref; a.board_is_ref = H->d_board_is_ref;
+  a.huber_a = huber_a; a.nb = H->nb; a.brec = H->d_brec; a.cost_bobs = H->d_cost_bobs;
+  a.jmat = H->d_jmat; a.resmat = H->d_resmat; a.npad = H->npad;
+  return a;
+}
+
+static int launch_prep(Handle* H, int which) {
+  Timed t(H, KF_PREP);
+  const int n = H->n_pose + H->n_cam + H->n_board;
+  k_prep_blocks<<<(n + 127) / 128, 128, 0, H->stream>>>(H->d_cam_pose[which], H->n_cam, H->d_pose[which], H->n_pose,
+                                                        H->d_board[which], H->n_board, H->d_prep_cam, H->d_prep_pose,
+                                                        H->d_prep_board);
+  CHECK_LAUNCH();
+  return MCBA_OK;
+}
+
+static int grid_for(int nb, int ctas_per_sm) { return std::max(1, std::min((nb + OBS_WARPS - 1) / OBS_WARPS, 148 * ctas_per_sm)); }
+
+template <int MODE> static int launch_obs(Handle* H, int which, double huber_a) {
+  if (H->nb == 0) return MCBA_OK;
+  const int fam = MODE == MODE_FUSED ? KF_FUSED : MODE == MODE_MATERIALIZE ? KF_MATERIALIZE : MODE == MODE_FROM_J ? KF_FROM_J : KF_COST;
+  Timed t(H, fam);
+  ObsArgs a = obs_args(H, which, huber_a);
+  DISPATCH_STAGE(H->stage, {
+    constexpr bool ACC = (MODE == MODE_FUSED || MODE == MODE_FROM_J);
+    const int sm = OBS_WARPS * (CTX_SIZE + (ACC ? Cols<ST>::NBLK * 8 * TS : 0)) * 8;
+    const int grid = grid_for(H->nb, ACC ? std::max(1, (227 * 1024) / (sm + 1024)) : 8);
+    k_observations<ST, MODE><<<grid, OBS_WARPS * 32, sm, H->stream>>>(a);
+  });
+  CHECK_LAUNCH();
+  return MCBA_OK;
+}
+
+static int ensure_jmat(Handle* H) {
+  if (H->d_jmat) return MCBA_OK;
+  if (dalloc(H, &H->d_jmat, (size_t)2 * H->K * H->npad) || dalloc(H, &H->d_resmat, (size_t)2 * H->npad)) return MCBA_ERR_CUDA;
+  return MCBA_OK;
+}
+
+// gather [m] doubles from every rank (rank-major) to the host; world 1: plain D2H
+static int gather_scalars(Handle* H, const double* d_local, int m, std::vector<double>& host) {
+  host.assign((size_t)m * H->n_ranks, 0.0);
+  if (H->n_ranks == 1) {
+    CU(cudaMemcpyAsync(host.data(), d_local, m * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+  } else {
+    { Timed t(H, KF_NCCL);
+      const int rc = g_nccl.AllGather(d_local, H->d_gather, m, NCCL_DOUBLE, H->comm, H->stream);
+      if (rc != 0) { H->err = std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"); return MCBA_ERR_NCCL; } }
+    CU(cudaMemcpyAsync(host.data(), H->d_gather, (size_t)m * H->n_ranks * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+  }
+  CU(cudaStreamSynchronize(H->stream));
+  return MCBA_OK;
+}
+static int allreduce_sum(Handle* H, double* d_buf, size_t n) {
+  if (H->n_ranks == 1) return MCBA_OK;
+  Timed t(H, KF_NCCL);
+  const int rc = g_nccl.AllReduce(d_buf, d_buf, n, NCCL_DOUBLE, NCCL_SUM, H->comm, H->stream);
+  if (rc != 0) { H->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"); return MCBA_ERR_NCCL; }
+  return MCBA_OK;
+}
+
+// d_scalars slots
+enum { SC_COST = 0, SC_XE2 = 1, SC_GMAX_E = 2, SC_F0 = 3 /*..6*/, SC_PE0 = 7 /*..10*/, SC_FAIL = 11, SC_N = 12 };
+
+static FState fstate(Handle* H, int which) { return FState{H->d_cam_pose[which], H->d_intr[which], H->d_board[which]}; }
+
+// Evaluate cost, gradient pieces and the normal-equation blocks at the current point (ProgramEvaluator::Evaluate
+// with Jacobian + what SchurEliminator needs from it).
+static int eval_jacobian(Handle* H, bool first) {
+  int rc;
+  const StageDims sd = stage_dims(H->stage);
+  if ((rc = launch_prep(H, H->cur))) return rc;
+  if (H->opt.materialize_jacobian) {
+    if ((rc = ensure_jmat(H))) return rc;
+    if ((rc = launch_obs<MODE_MATERIALIZE>(H, H->cur, H->opt.huber_a))) return rc;
+    if ((rc = launch_obs<MODE_FROM_J>(H, H->cur, H->opt.huber_a))) return rc;
+  } else {
+    if ((rc = launch_obs<MODE_FUSED>(H, H->cur, H->opt.huber_a))) return rc;
+  }
+  if ((rc = reduce_rows(H, H->d_cost_bobs, H->nb, 1, 1, H->d_scalars + SC_COST))) return rc;
+  if (H->n_pose > 0) {
+    Timed t(H, KF_EASSEMBLE);
+    DISPATCH_STAGE(H->stage, (k_eblock_assemble<ST><<<H->n_pose, 192, 6 * H->ldz * 8, H->stream>>>(
+        H->d_bobs, H->d_pose_bobs_ptr, H->d_brec, H->n_cam, H->Wc, H->Wb, H->n_f, H->ldz, H->d_Hoo, H->d_Wt)));
+    CHECK_LAUNCH();
+  }
+  {
+    Timed t(H, KF_PAIR);
+    if (H->n_chunks > 0) {
+      DISPATCH_STAGE(H->stage, (k_pair_reduce<ST><<<H->n_chunks, 256, 0, H->stream>>>(H->d_chunks, H->d_pair_bobs, H->d_brec, H->d_pair_partial)));
+      CHECK_LAUNCH();
+    }
+    const int n = H->n_pair * H->NE;
+    DISPATCH_STAGE(H->stage, (k_pair_final<ST><<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_pair_chunk_ptr, H->n_pair, H->d_pair_partial, H->d_pair_rec)));
+    CHECK_LAUNCH();
+  }
+  if ((rc = allreduce_sum(H, H->d_pair_rec, (size_t)H->n_pair * H->NE))) return rc;
+  {
+    Timed t(H, KF_PAIR);
+    const int n = H->n_f * H->n_f + H->n_f;
+    DISPATCH_STAGE(H->stage, (k_ff_assemble<ST><<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_pair_rec, H->n_cam, H->n_board, H->Wc, H->Wb, H->n_f, H->d_FF, H->d_gf)));
+    CHECK_LAUNCH();
+  }
+  {
+    Timed t(H, KF_REDUCE);
+    if (H->n_pose > 0) {
+      k_eblock_grad<<<(H->n_pose + 127) / 128, 128, 0, H->stream>>>(H->d_pose[H->cur], H->d_Wt, H->n_pose, H->n_f, H->ldz, H->d_part_e);
+      CHECK_LAUNCH();
+    }
+    k_fstep<<<1, 1024, 0, H->stream>>>(fstate(H, H->cur), fstate(H, H->cur), nullptr, H->d_FF, H->d_gf, H->d_scale_f, H->n_f, H->n_cam, H->Wc, H->Wb, sd.cam ? 1 : 0, H->d_scalars + SC_F0);
+    CHECK_LAUNCH();
+  }
+  if ((rc = reduce_rows(H, H->d_part_e, H->n_pose, 2, 1, H->d_scalars + SC_XE2))) return rc;
+  if (first || !H->have_scale) {
+    Timed t(H, KF_REDUCE);
+    const int n = H->n_pose * 6 + H->n_f;
+    k_scale_diag<<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_Hoo, H->n_pose, H->d_FF, H->n_f, 1, H->opt.jacobi_scaling, H->opt.min_lm_diagonal, H->opt.max_lm_diagonal, H->d_scale_e, H->d_scale_f, H->d_diag_e, H->d_diag_f);
+    CHECK_LAUNCH();
+    H->have_scale = true;
+    H->reuse_diagonal = true;   // the diagonal was just computed from this Jacobian
+  } else {
+    H->reuse_diagonal = false;
+  }
+  std::vector<double> hs;
+  if ((rc = gather_scalars(H, H->d_scalars, SC_N, hs))) return rc;
+  double cost = 0, xe2 = 0, gmax = 0;
+  for (int r = 0; r < H->n_ranks; ++r) {
+    const double* s = &hs[(size_t)r * SC_N];
+    cost += s[SC_COST];
+    if (H->n_pose > 0 || H->n_ranks > 1) { xe2 += s[SC_XE2]; gmax = std::max(gmax, s[SC_GMAX_E]); }
+  }
+  if (H->n_pose == 0 && H->n_ranks == 1) { xe2 = 0; }
+  gmax = std::max(gmax, hs[SC_F0 + 1]);
+  H->x_cost = cost;
+  H->x_norm = std::sqrt(xe2 + hs[SC_F0 + 0]);
+  H->grad_max = gmax;
+  if (!std::isfinite(cost)) return MCBA_ERR_NUMERIC;
+  return MCBA_OK;
+}
+
+static int cholesky_reduced(Handle* H) {
+  Timed t(H, KF_CHOL);
+  const int n = H->n_f;
+  for (int j0 = 0; j0 < n; j0 += CH_B) {
+    const int jb = std::min(CH_B, n - j0);
+    k_chol_diag<<<1, 32, 0, H->stream>>>(H->d_S, n, j0, H->d_fail);
+    const int m = n - j0 - jb;
+    if (m > 0) {
+      k_chol_trsm<<<(m + 127) / 128, 128, 0, H->stream>>>(H->d_S, n, j0, H->d_fail);
+      const int nt = (m + 63) / 64;
+      k_chol_update<<<nt * (nt + 1) / 2, 256, 0, H->stream>>>(H->d_S, n, j0, H->d_fail);
+    }
+  }
+  k_chol_solve<<<1, 1024, n * sizeof(double), H->stream>>>(H->d_S, n, H->d_rhs, H->d_zf, H->d_fail);
+  CHECK_LAUNCH();
+  return MCBA_OK;
+}
+
+// LevenbergMarquardtStrategy::ComputeStep + SchurComplementSolver + candidate point + candidate cost.
+// Outputs (host): step validity ingredients.
+struct StepOut { double mcc, step_norm, cand_norm, cand_cost; bool solver_ok; };
+static int compute_step(Handle* H, StepOut* out) {
+  int rc;
+  const StageDims sd = stage_dims(H->stage);
+  CU(cudaMemsetAsync(H->d_fail, 0, sizeof(int), H->stream));
+  if (!H->reuse_diagonal) {
+    Timed t(H, KF_REDUCE);
+    const int n = H->n_pose * 6 + H->n_f;
+    k_scale_diag<<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_Hoo, H->n_pose, H->d_FF, H->n_f, 0, H->opt.jacobi_scaling, H->opt.min_lm_diagonal, H->opt.max_lm_diagonal, H->d_scale_e, H->d_scale_f, H->d_diag_e, H->d_diag_f);
+    CHECK_LAUNCH();
+  }
+  H->reuse_diagonal = true;
+  if (H->n_pose > 0) {
+    Timed t(H, KF_EFACTOR);
+    k_eblock_factor<<<H->n_pose, 128, 0, H->stream>>>(H->d_Hoo, H->d_Wt, H->d_scale_e, H->d_scale_f, H->d_diag_e, H->radius, H->n_f, H->ldz, H->d_L, H->d_Z, H->d_fail);
+    CHECK_LAUNCH();
+  }
+  {
+    Timed t(H, KF_SYRK);
+    dim3 grid(H->syrk_tiles, H->syrk_nsplit);
+    k_syrk<<<grid, 128, 0, H->stream>>>(H->d_Z, 6 * (int64_t)H->n_pose, H->ldz, H->syrk_nt, H->syrk_rows_per_split, H->d_syrk_partial);
+    k_syrk_sum<<<H->syrk_tiles, 256, 0, H->stream>>>(H->d_syrk_partial, H->syrk_tiles, H->syrk_nt, H->syrk_nsplit, H->ldz, H->d_ZtZ);
+    CHECK_LAUNCH();
+  }
+  if ((rc = allreduce_sum(H, H->d_ZtZ, (size_t)H->ldz * H->ldz))) return rc;
+  {
+    Timed t(H, KF_REDUCED);
+    const int n = H->n_f * H->n_f + H->n_f;
+    k_build_reduced<<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_FF, H->d_gf, H->d_ZtZ, H->d_scale_f, H->d_diag_f, H->radius, H->n_f, H->ldz, H->d_S, H->d_rhs);
+    CHECK_LAUNCH();
+  }
+  if ((rc = cholesky_reduced(H))) return rc;
+  const int cand = 1 - H->cur;
+  {
+    Timed t(H, KF_BACKSUBST);
+    if (H->n_pose > 0) {
+      k_backsubst<<<H->n_pose, 128, 0, H->stream>>>(H->d_Z, H->d_L, H->d_zf, H->d_scale_e, H->d_diag_e, H->radius, H->d_pose[H->cur], H->n_f, H->ldz, H->d_pose[cand], H->d_part_e);
+    }
+    k_fstep<<<1, 1024, 0, H->stream>>>(fstate(H, H->cur), fstate(H, cand), H->d_zf, H->d_FF, H->d_gf, H->d_scale_f, H->n_f, H->n_cam, H->Wc, H->Wb, sd.cam ? 1 : 0, H->d_scalars + SC_F0);
+    CHECK_LAUNCH();
+  }
+  if ((rc = reduce_rows(H, H->d_part_e, H->n_pose, 4, 4, H->d_scalars + SC_PE0))) return rc;
+  // candidate cost
+  if ((rc = launch_prep(H, cand))) return rc;
+  if ((rc = launch_obs<MODE_COST>(H, cand, H->opt.huber_a))) return rc;
+  if ((rc = reduce_rows(H, H->d_cost_bobs, H->nb, 1, 1, H->d_scalars + SC_COST))) return rc;
+  std::vector<double> hs;
+  k_flag_to_scalar<<<1, 1, 0, H->stream>>>(H->d_fail, H->d_scalars + SC_FAIL);
+  CHECK_LAUNCH();
+  if ((rc = gather_scalars(H, H->d_scalars, SC_N, hs))) return rc;
+  double py = 0, he = 0, sn = 0, xn = 0, cost = 0, h_fail = 0;
+  for (int r = 0; r < H->n_ranks; ++r) {
+    const double* s = &hs[(size_t)r * SC_N];
+    cost += s[SC_COST]; h_fail += s[SC_FAIL];
+    if (H->n_pose > 0 || H->n_ranks > 1) { py += s[SC_PE0]; he += s[SC_PE0 + 1]; sn += s[SC_PE0 + 2]; xn += s[SC_PE0 + 3]; }
+  }
+  const double* f = &hs[SC_F0];
+  const double zg = py + f[0], zhz = he + f[1];
+  out->mcc = zg - 0.5 * zhz;
+  out->step_norm = std::sqrt(sn + f[2]);
+  out->cand_norm = std::sqrt(xn + f[3]);
+  out->cand_cost = std::isfinite(cost) ? cost : std::numeric_limits<double>::max();
+  out->solver_ok = (h_fail == 0.0) && std::isfinite(out->mcc) && std::isfinite(out->step_norm);
+  return MCBA_OK;
+}
+
+static void record_iteration(Handle* H) {
+  if (H->it.step_is_successful) {
+    ++H->summ.num_successful_steps;
+    if (H->x_cost < H->minimum_cost) H->minimum_cost = H->x_cost;
+  } else {
+    ++H->summ.num_unsuccessful_steps;
+  }
+  H->it.trust_region_radius = H->radius;
+  H->trace.push_back(H->it);
+  if (H->opt.verbose && H->rank == 0)
+    std::printf("%4d % .6e % .2e % .2e % .2e % .2e % .2e\n", H->it.iteration, H->it.cost, H->it.cost_change,
+                H->it.gradient_max_norm, H->it.step_norm, H->it.relative_decrease, H->it.trust_region_radius);
+}
+
+static int upload_params(Handle* H, const mcba_params* p) {
+  const StageDims sd = stage_dims(H->stage);
+  if (!p || !p->pose || !p->intrinsics || (sd.cam && !p->cam_pose) || (sd.board && !p->board_pose)) { H->err = "missing parameter array for this stage"; return MCBA_ERR_INVALID; }
+  for (int w = 0; w < 2; ++w) {
+    CU(cudaMemcpyAsync(H->d_pose[w], p->pose, (size_t)H->n_pose * 6 * sizeof(double), cudaMemcpyHostToDevice, H->stream));
+    CU(cudaMemcpyAsync(H->d_intr[w], p->intrinsics, (size_t)H->n_cam * 9 * sizeof(double), cudaMemcpyHostToDevice, H->stream));
+    if (p->cam_pose) CU(cudaMemcpyAsync(H->d_cam_pose[w], p->cam_pose, (size_t)H->n_cam * 6 * sizeof(double), cudaMemcpyHostToDevice, H->stream));
+    else CU(cudaMemsetAsync(H->d_cam_pose[w], 0, (size_t)H->n_cam * 6 * sizeof(double), H->stream));
+    if (p->board_pose && H->n_board > 0) CU(cudaMemcpyAsync(H->d_board[w], p->board_pose, (size_t)H->n_board * 6 * sizeof(double), cudaMemcpyHostToDevice, H->stream));
+  }
+  H->cur = 0;
+  return MCBA_OK;
+}
+static int download_params(Handle* H, mcba_params* p) {
+  const StageDims sd = stage_dims(H->stage);
+  const int w = H->cur;
+  CU(cudaMemcpyAsync(p->pose, H->d_pose[w], (size_t)H->n_pose * 6 * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+  if (sd.cam) CU(cudaMemcpyAsync(p->cam_pose, H->d_cam_pose[w], (size_t)H->n_cam * 6 * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+  if (sd.board) CU(cudaMemcpyAsync(p->board_pose, H->d_board[w], (size_t)H->n_board * 6 * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+  if (sd.intr) CU(cudaMemcpyAsync(p->intrinsics, H->d_intr[w], (size_t)H->n_cam * 9 * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+  CU(cudaStreamSynchronize(H->stream));
+  return MCBA_OK;
+}
+
+extern "C" {
+
+void mcba_default_options(mcba_options* o) {
+  o->max_num_iterations = 50;   // Ceres default; the reference overrides it with YAML number_iterations
+  o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
+  o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16; o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32; o->huber_a = 1.0;
+  o->jacobi_scaling = 1; o->max_num_consecutive_invalid_steps = 5; o->verbose = 0; o->materialize_jacobian = 0;
+}
+
+const char* mcba_last_error(void* h) { return h ? ((Handle*)h)->err.c_str() : "null handle"; }
+int mcba_num_kernels(void) { return KF_COUNT; }
+const char* mcba_kernel_name(int k) { return (k >= 0 && k < KF_COUNT) ? kKernelNames[k] : ""; }
+int mcba_kernel_stats(void* h, int k, int64_t* launches, double* total_ms) {
+  Handle* H = (Handle*)h; if (!H || k < 0 || k >= KF_COUNT) return MCBA_ERR_INVALID;
+  flush_timers(H);
+  if (launches) *launches = H->kf_launches[k];
+  if (total_ms) *total_ms = H->kf_ms[k];
+  return MCBA_OK;
+}
+int mcba_reset_kernel_stats(void* h) {
+  Handle* H = (Handle*)h; if (!H) return MCBA_ERR_INVALID;
+  flush_timers(H);
+  for (int k = 0; k < KF_COUNT; ++k) { H->kf_launches[k] = 0; H->kf_ms[k] = 0; }
+  return MCBA_OK;
+}
+int mcba_jacobian_width(int stage) { return stage_dims(stage).K; }
+
+void mcba_destroy(void* h) {
+  Handle* H = (Handle*)h; if (!H) return;
+  cudaSetDevice(H->device);
+  if (H->stream) cudaStreamSynchronize(H->stream);
+  if (H->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(H->comm);
+  for (auto& p : H->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (auto e : H->free_events) cudaEventDestroy(e);
+  dfree(&H->d_u); dfree(&H->d_v); dfree(&H->d_pt); dfree(&H->d_pts); dfree(&H->d_bobs); dfree(&H->d_pose_bobs_ptr);
+  dfree(&H->d_cam_model); dfree(&H->d_cam_is_ref); dfree(&H->d_board_is_ref);
+  dfree(&H->d_pair_bobs); dfree(&H->d_chunks); dfree(&H->d_pair_chunk_ptr);
+  dfree(&H->d_brec); dfree(&H->d_cost_bobs); dfree(&H->d_Hoo); dfree(&H->d_Wt); dfree(&H->d_Z); dfree(&H->d_L);
+  dfree(&H->d_scale_e); dfree(&H->d_diag_e); dfree(&H->d_scale_f); dfree(&H->d_diag_f);
+  dfree(&H->d_FF); dfree(&H->d_gf); dfree(&H->d_S); dfree(&H->d_rhs); dfree(&H->d_zf); dfree(&H->d_ZtZ);
+  dfree(&H->d_syrk_partial); dfree(&H->d_pair_partial); dfree(&H->d_pair_rec); dfree(&H->d_part_e);
+  dfree(&H->d_red_scratch); dfree(&H->d_scalars); dfree(&H->d_gather); dfree(&H->d_fail);
+  dfree(&H->d_jmat); dfree(&H->d_resmat);
+  for (int w = 0; w < 2; ++w) { dfree(&H->d_cam_pose[w]); dfree(&H->d_pose[w]); dfree(&H->d_board[w]); dfree(&H->d_intr[w]); }
+  dfree(&H->d_prep_cam); dfree(&H->d_prep_pose); dfree(&H->d_prep_board);
+  if (H->stream) cudaStreamDestroy(H->stream);
+  delete H;
+}
+
+int mcba_create(void** handle, const mcba_problem* P, int device) {
+  if (!handle) return MCBA_ERR_INVALID;
+  Handle* H = new Handle();
+  *handle = H;
+  if (!P || P->n_obs < 0 || P->n_bobs < 0 || P->n_cam <= 0 || P->n_pose < 0) { H->err = "bad problem sizes"; return MCBA_ERR_INVALID; }
+  if (P->n_obs >= (int64_t)1 << 31 || P->n_bobs >= (int64_t)1 << 30) { H->err = "shard too large for 32-bit indices: split across handles"; return MCBA_ERR_INVALID; }
+  if (P->cam_problem || P->n_problems > 1) { H->err = "batched problems are solved through mcba_solve_batched (not built in this round)"; return MCBA_ERR_INVALID; }
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { H->err = "no CUDA device: libmcba has no CPU fallback"; return MCBA_ERR_CUDA; }
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) { H->err = "libmcba is built for sm_100a (B200) only"; return MCBA_ERR_CUDA; }
+  CU(cudaSetDevice(device));
+  H->device = device;
+  CU(cudaStreamCreate(&H->stream));
+  H->n_cam = P->n_cam; H->n_pose = P->n_pose; H->n_board = std::max(0, P->n_board); H->n_pts = P->n_pts;
+  H->n_obs = P->n_obs; H->nb = (int)P->n_bobs; H->npad = ((P->n_obs + 31) / 32) * 32; H->n_obs_global = P->n_obs;
+  // validate + pack
+  std::vector<int4> bobs(H->nb + 1);
+  std::vector<int> ppt(H->n_pose + 1, 0);
+  H->h_bobs_cam.resize(H->nb); H->h_bobs_pose.resize(H->nb); H->h_bobs_board.resize(H->nb);
+  for (int b = 0; b < H->nb; ++b) {
+    const int c = P->bobs_cam[b], o = P->bobs_pose[b], bd = P->bobs_board ? P->bobs_board[b] : 0;
+    if (c < 0 || c >= P->n_cam || o < 0 || o >= P->n_pose || (b > 0 && o < P->bobs_pose[b - 1]) ||
+        P->bobs_ptr[b] > P->bobs_ptr[b + 1] || P->bobs_ptr[b] < 0 || P->bobs_ptr[b + 1] > P->n_obs ||
+        (H->n_board > 0 && (bd < 0 || bd >= H->n_board))) { H->err = "inconsistent board-observation table"; return MCBA_ERR_INVALID; }
+    bobs[b] = make_int4((int)P->bobs_ptr[b], c, o, H->n_board > 0 ? bd : 0);
+    H->h_bobs_cam[b] = c; H->h_bobs_pose[b] = o; H->h_bobs_board[b] = H->n_board > 0 ? bd : 0;
+    ppt[o + 1] = b + 1;
+  }
+  if (H->nb > 0 && (P->bobs_ptr[0] != 0 || P->bobs_ptr[H->nb] != P->n_obs)) { H->err = "bobs_ptr must cover [0, n_obs)"; return MCBA_ERR_INVALID; }
+  bobs[H->nb] = make_int4((int)P->n_obs, 0, 0, 0);
+  for (int o = 0; o < H->n_pose; ++o) ppt[o + 1] = std::max(ppt[o + 1], ppt[o]);
+  for (int64_t i = 0; i < P->n_obs; ++i) if (P->pt_idx[i] < 0 || P->pt_idx[i] >= P->n_pts) { H->err = "pt_idx out of range"; return MCBA_ERR_INVALID; }
+  std::vector<double> pts((size_t)std::max(1, P->n_pts) * 3);
+  for (int i = 0; i < P->n_pts * 3; ++i) pts[i] = (double)P->pts_xyz[i];
+  if (dalloc(H, &H->d_u, (size_t)H->npad) || dalloc(H, &H->d_v, (size_t)H->npad) || dalloc(H, &H->d_pt, (size_t)H->npad)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_pts, pts.size()) || dalloc(H, &H->d_bobs, bobs.size()) || dalloc(H, &H->d_pose_bobs_ptr, ppt.size())) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_cam_model, (size_t)H->n_cam) || dalloc(H, &H->d_cam_is_ref, (size_t)H->n_cam) || dalloc(H, &H->d_board_is_ref, (size_t)std::max(1, H->n_board))) return MCBA_ERR_CUDA;
+  CU(cudaMemcpy(H->d_u, P->u, P->n_obs * sizeof(float), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(H->d_v, P->v, P->n_obs * sizeof(float), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(H->d_pt, P->pt_idx, P->n_obs * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(H->d_pts, pts.data(), pts.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(H->d_bobs, bobs.data(), bobs.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(H->d_pose_bobs_ptr, ppt.data(), ppt.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(H->d_cam_model, P->cam_model, H->n_cam * sizeof(int32_t), cudaMemcpyHostToDevice));
+  std::vector<uint8_t> zc((size_t)std::max(H->n_cam, std::max(1, H->n_board)), 0);
+  CU(cudaMemcpy(H->d_cam_is_ref, P->cam_is_ref ? P->cam_is_ref : zc.data(), H->n_cam, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(H->d_board_is_ref, (P->board_is_ref && H->n_board > 0) ? P->board_is_ref : zc.data(), std::max(1, H->n_board), cudaMemcpyHostToDevice));
+  for (int w = 0; w < 2; ++w) {
+    if (dalloc(H, &H->d_cam_pose[w], (size_t)H->n_cam * 6) || dalloc(H, &H->d_pose[w], (size_t)H->n_pose * 6) ||
+        dalloc(H, &H->d_board[w], (size_t)std::max(1, H->n_board) * 6) || dalloc(H, &H->d_intr[w], (size_t)H->n_cam * 9)) return MCBA_ERR_CUDA;
+    CU(cudaMemset(H->d_board[w], 0, (size_t)std::max(1, H->n_board) * 6 * sizeof(double)));
+  }
+  if (dalloc(H, &H->d_prep_cam, (size_t)H->n_cam * PREP) || dalloc(H, &H->d_prep_pose, (size_t)H->n_pose * PREP) ||
+      dalloc(H, &H->d_prep_board, (size_t)std::max(1, H->n_board) * PREP)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_red_scratch, (size_t)512 * 8) || dalloc(H, &H->d_scalars, (size_t)SC_N) || dalloc(H, &H->d_gather, (size_t)SC_N * 64) || dalloc(H, &H->d_fail, (size_t)1)) return MCBA_ERR_CUDA;
+  CU(cudaMemset(H->d_scalars, 0, SC_N * sizeof(double)));
+  mcba_default_options(&H->opt);
+  const int rc = setup_stage(H, P->stage);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  return MCBA_OK;
+}
+
+int mcba_set_stage(void* h, int stage) {
+  Handle* H = (Handle*)h; if (!H) return MCBA_ERR_INVALID;
+  CU(cudaSetDevice(H->device));
+  if (stage == H->stage) return MCBA_OK;
+  const int rc = setup_stage(H, stage);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  return MCBA_OK;
+}
+
+int mcba_nccl_unique_id(void* out) {
+  if (!g_nccl.load()) return MCBA_ERR_NCCL;
+  nccl_uid_t id;
+  if (g_nccl.GetUniqueId(&id) != 0) return MCBA_ERR_NCCL;
+  std::memcpy(out, &id, sizeof(id));
+  return MCBA_OK;
+}
+
+int mcba_comm_init(void* h, int rank, int n_ranks, const void* uid) {
+  Handle* H = (Handle*)h; if (!H) return MCBA_ERR_INVALID;
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks || n_ranks > 64) { H->err = "bad rank / n_ranks"; return MCBA_ERR_INVALID; }
+  H->rank = rank; H->n_ranks = n_ranks;
+  if (n_ranks == 1) return MCBA_OK;
+  if (!g_nccl.load()) { H->err = "libnccl.so.2 not found"; return MCBA_ERR_NCCL; }
+  CU(cudaSetDevice(H->device));
+  nccl_uid_t id; std::memcpy(&id, uid, sizeof(id));
+  const int rc = g_nccl.CommInitRank(&H->comm, n_ranks, id, rank);
+  if (rc != 0) { H->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"); return MCBA_ERR_NCCL; }
+  // global observation count for the RMS
+  double n_local = (double)H->n_obs;
+  CU(cudaMemcpy(H->d_scalars, &n_local, sizeof(double), cudaMemcpyHostToDevice));
+  if (g_nccl.AllReduce(H->d_scalars, H->d_scalars, 1, NCCL_DOUBLE, NCCL_SUM, H->comm, H->stream) != 0) { H->err = "ncclAllReduce(n_obs)"; return MCBA_ERR_NCCL; }
+  double n_glob = 0;
+  CU(cudaMemcpyAsync(&n_glob, H->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+  CU(cudaStreamSynchronize(H->stream));
+  H->n_obs_global = (int64_t)(n_glob + 0.5);
+  return MCBA_OK;
+}
+
+int mcba_solve_begin(void* h, const mcba_params* p, const mcba_options* opt) {
+  Handle* H = (Handle*)h; if (!H) return MCBA_ERR_INVALID;
+  CU(cudaSetDevice(H->device));
+  mcba_options o; if (opt) o = *opt; else mcba_default_options(&o);
+  H->opt = o;
+  int rc;
+  if ((rc = upload_params(H, p))) return rc;
+  H->solving = true; H->done = false; H->trace.clear();
+  std::memset(&H->summ, 0, sizeof(H->summ)); std::memset(&H->it, 0, sizeof(H->it));
+  H->radius = o.initial_trust_region_radius; H->decrease_factor = 2.0; H->reuse_diagonal = false;
+  H->num_consecutive_invalid = 0; H->at_least_one_success = false; H->have_scale = false;
+  H->minimum_cost = std::numeric_limits<double>::max(); H->termination = MCBA_NO_CONVERGENCE;
+  // IterationZero
+  rc = eval_jacobian(H, true);
+  if (rc == MCBA_ERR_NUMERIC) { H->err = "Initial residual and Jacobian evaluation failed."; H->summ.termination = MCBA_FAILURE; H->termination = MCBA_FAILURE; H->done = true; return rc; }
+  if (rc) return rc;
+  H->summ.initial_cost = H->x_cost;
+  H->it.iteration = 0; H->it.step_is_valid = 1; H->it.step_is_successful = 1; H->it.cost = H->x_cost; H->it.gradient_max_norm = H->grad_max;
+  return MCBA_OK;
+}
+
+// One pass of TrustRegionMinimizer's while loop: FinalizeIterationAndCheckIfMinimizerCanContinue for the
+// previous iteration, then one trust-region iteration. Returns 1 to continue, 0 when terminated.
+int mcba_solve_step(void* h) {
+  Handle* H = (Handle*)h; if (!H || !H->solving) return MCBA_ERR_INVALID;
+  if (H->done) return 0;
+  CU(cudaSetDevice(H->device));
+  const mcba_options& o = H->opt;
+  record_iteration(H);
+  if (H->it.iteration >= o.max_num_iterations) { H->termination = MCBA_NO_CONVERGENCE; H->done = true; return 0; }
+  if (H->it.step_is_successful && H->it.gradient_max_norm <= o.gradient_tolerance) { H->termination = MCBA_CONVERGENCE; H->done = true; return 0; }
+  if (H->it.trust_region_radius <= o.min_trust_region_radius) { H->termination = MCBA_CONVERGENCE; H->done = true; return 0; }
+  const double prev_grad_max = H->it.gradient_max_norm;
+  const int iter = H->it.iteration + 1;
+  std::memset(&H->it, 0, sizeof(H->it));
+  H->it.iteration = iter;
+  StepOut so;
+  int rc = compute_step(H, &so);
+  if (rc) return rc;
+  H->it.step_is_valid = so.solver_ok && so.mcc > 0.0;
+  if (!H->it.step_is_valid) {   // HandleInvalidStep
+    if (++H->num_consecutive_invalid >= o.max_num_consecutive_invalid_steps) { H->termination = MCBA_FAILURE; H->done = true; return 0; }
+    H->radius /= H->decrease_factor; H->decrease_factor *= 2.0; H->reuse_diagonal = true;
+    H->it.cost = H->x_cost; H->it.gradient_max_norm = prev_grad_max;
+    return 1;
+  }
+  H->num_consecutive_invalid = 0;
+  if (H->at_least_one_success) {
+    H->it.step_norm = so.step_norm;   // ParameterToleranceReached
+    if (so.step_norm <= o.parameter_tolerance * (H->x_norm + o.parameter_tolerance)) { H->termination = MCBA_CONVERGENCE; H->done = true; return 0; }
+    H->it.cost_change = H->x_cost - so.cand_cost;   // FunctionToleranceReached
+    if (std::fabs(H->it.cost_change) <= o.function_tolerance * H->x_cost) { H->termination = MCBA_CONVERGENCE; H->done = true; return 0; }
+  }
+  double rel;
+  if (so.cand_cost >= std::numeric_limits<double>::max()) rel = std::numeric_limits<double>::lowest();
+  else rel = (H->x_cost - so.cand_cost) / so.mcc;   // monotonic step evaluator: reference cost == current cost
+  H->it.relative_decrease = rel;
+  if (rel > o.min_relative_decrease) {   // HandleSuccessfulStep
+    H->at_least_one_success = true;
+    H->cur = 1 - H->cur;
+    H->x_norm = so.cand_norm;
+    rc = eval_jacobian(H, false);
+    if (rc == MCBA_ERR_NUMERIC) { H->termination = MCBA_FAILURE; H->done = true; return 0; }
+    if (rc) return rc;
+    H->it.step_is_successful = 1; H->it.cost = H->x_cost; H->it.gradient_max_norm = H->grad_max;
+    H->radius = H->radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
+    H->radius = std::min(o.max_trust_region_radius, H->radius);
+    H->decrease_factor = 2.0;
+  } else {
+    H->it.step_is_successful = 0; H->it.cost = so.cand_cost; H->it.gradient_max_norm = prev_grad_max;
+    H->radius /= H->decrease_factor; H->decrease_factor *= 2.0; H->reuse_diagonal = true;
+  }
+  return 1;
+}
+
+int mcba_solve_end(void* h, mcba_params* p, mcba_summary* summary) {
+  Handle* H = (Handle*)h; if (!H || !H->solving) return MCBA_ERR_INVALID;
+  CU(cudaSetDevice(H->device));
+  int rc;
+  H->summ.termination = H->termination;
+  H->summ.num_iterations = (int)H->trace.size();
+  H->summ.final_cost = H->minimum_cost < std::numeric_limits<double>::max() ? H->minimum_cost : H->x_cost;
+  // unrobustified RMS at the returned parameters: cost pass with the loss disabled
+  if ((rc = launch_prep(H, H->cur))) return rc;
+  if ((rc = launch_obs<MODE_COST>(H, H->cur, 0.0))) return rc;
+  if ((rc = reduce_rows(H, H->d_cost_bobs, H->nb, 1, 1, H->d_scalars + SC_COST))) return rc;
+  std::vector<double> hs;
+  if ((rc = gather_scalars(H, H->d_scalars, SC_N, hs))) return rc;
+  double c = 0; for (int r = 0; r < H->n_ranks; ++r) c += hs[(size_t)r * SC_N + SC_COST];
+  H->summ.rms_px = std::sqrt(2.0 * c / (double)std::max<int64_t>(1, H->n_obs_global));
+  flush_timers(H);
+  H->summ.t_jacobian_ms = H->kf_ms[KF_FUSED] + H->kf_ms[KF_MATERIALIZE] + H->kf_ms[KF_FROM_J] + H->kf_ms[KF_PREP];
+  H->summ.t_schur_ms = H->kf_ms[KF_EASSEMBLE] + H->kf_ms[KF_PAIR] + H->kf_ms[KF_EFACTOR] + H->kf_ms[KF_SYRK] + H->kf_ms[KF_REDUCED] + H->kf_ms[KF_BACKSUBST];
+  H->summ.t_chol_ms = H->kf_ms[KF_CHOL]; H->summ.t_cost_ms = H->kf_ms[KF_COST]; H->summ.t_comm_ms = H->kf_ms[KF_NCCL];
+  double tot = 0; for (int k = 0; k < KF_COUNT; ++k) tot += H->kf_ms[k];
+  H->summ.t_total_ms = tot;
+  if (p && (rc = download_params(H, p))) return rc;
+  if (summary) *summary = H->summ;
+  H->solving = false;
+  return MCBA_OK;
+}
+
+int mcba_solve(void* h, mcba_params* p, const mcba_options* opt, mcba_summary* summary, mcba_trace_row* trace, int trace_cap) {
+  Handle* H = (Handle*)h; if (!H) return MCBA_ERR_INVALID;
+  int rc = mcba_solve_begin(h, p, opt);
+  if (rc) { if (summary) *summary = H->summ; return rc; }
+  for (;;) { rc = mcba_solve_step(h); if (rc <= 0) break; }
+  if (rc < 0) return rc;
+  rc = mcba_solve_end(h, p, summary);
+  if (trace) for (int i = 0; i < (int)H->trace.size() && i < trace_cap; ++i) trace[i] = H->trace[i];
+  return rc;
+}
+
+int mcba_solve_batched(void* h, mcba_params*, const mcba_options*, mcba_summary*) {
+  Handle* H = (Handle*)h; if (!H) return MCBA_ERR_INVALID;
+  H->err = "mcba_solve_batched: not built in this round";
+  return MCBA_ERR_INVALID;
+}
+
+int mcba_eval(void* h, const mcba_params* p, const mcba_options* opt, double* cost, double* residuals, double* jacobian) {
+  Handle* H = (Handle*)h; if (!H) return MCBA_ERR_INVALID;
+  CU(cudaSetDevice(H->device));
+  mcba_options o; if (opt) o = *opt; else mcba_default_options(&o);
+  int rc;
+  if ((rc = upload_params(H, p))) return rc;
+  if ((rc = ensure_jmat(H))) return rc;
+  if ((rc = launch_prep(H, 0))) return rc;
+  if ((rc = launch_obs<MODE_MATERIALIZE>(H, 0, o.huber_a))) return rc;
+  if ((rc = reduce_rows(H, H->d_cost_bobs, H->nb, 1, 1, H->d_scalars + SC_COST))) return rc;
+  double c = 0;
+  CU(cudaMemcpyAsync(&c, H->d_scalars + SC_COST, sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+  CU(cudaStreamSynchronize(H->stream));
+  if (cost) *cost = c;
+  const int64_t n = H->n_obs, npad = H->npad; const int K = H->K;
+  if (residuals) {
+    std::vector<double> r((size_t)2 * npad);
+    CU(cudaMemcpy(r.data(), H->d_resmat, r.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n; ++i) { residuals[2 * i] = r[i]; residuals[2 * i + 1] = r[npad + i]; }
+  }
+  if (jacobian) {
+    std::vector<double> plane((size_t)npad);
+    for (int k = 0; k < K; ++k) for (int r = 0; r < 2; ++r) {
+      CU(cudaMemcpy(plane.data(), H->d_jmat + (size_t)(2 * k + r) * npad, npad * sizeof(double), cudaMemcpyDeviceToHost));
+      for (int64_t i = 0; i < n; ++i) jacobian[((size_t)i * 2 + r) * K + k] = plane[i];
+    }
+  }
+  return std::isfinite(c) ? MCBA_OK : MCBA_ERR_NUMERIC;
+}
+
+int mcba_reprojection_errors(void* h, const mcba_params* p, double* err) {
+  Handle* H = (Handle*)h; if (!H || !err) return MCBA_ERR_INVALID;
+  CU(cudaSetDevice(H->device));
+  int rc;
+  if ((rc = upload_params(H, p))) return rc;
+  if ((rc = launch_prep(H, 0))) return rc;
+  double* d_err = nullptr;
+  if (dalloc(H, &d_err, (size_t)H->npad)) return MCBA_ERR_CUDA;
+  ObsArgs a = obs_args(H, 0, 0.0);
+  if (H->nb > 0) {
+    DISPATCH_STAGE(H->stage, (k_reproj_err<ST><<<grid_for(H->nb, 8), OBS_WARPS * 32, OBS_WARPS * CTX_SIZE * 8, H->stream>>>(a, d_err)));
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(err, d_err, H->n_obs * sizeof(double), cudaMemcpyDeviceToHost, H->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(H->stream);
+  cudaFree(d_err);
+  if (e != cudaSuccess) { H->err = cudaGetErrorString(e); return MCBA_ERR_CUDA; }
+  return MCBA_OK;
+}
+
+// Debug/test hook: copy an internal device buffer to the host. Names: "FF","gf","S","rhs","zf","ZtZ","Hoo","Wt","Z","brec","scale_e","scale_f","diag_e","diag_f"
+int mcba_debug_fetch(void* h, const char* name, double* out, int64_t cap, int64_t* n_out) {
+  Handle* H = (Handle*)h; if (!H) return MCBA_ERR_INVALID;
+  CU(cudaSetDevice(H->device));
+  const std::string s(name);
+  const double* src = nullptr; int64_t n = 0;
+  const int64_t nf = H->n_f, np = H->n_pose, ldz = H->ldz;
+  if (s == "FF") { src = H->d_FF; n = nf * nf; } else if (s == "gf") { src = H->d_gf; n = nf; }
+  else if (s == "S") { src = H->d_S; n = nf * nf; } else if (s == "rhs") { src = H->d_rhs; n = nf; }
+  else if (s == "zf") { src = H->d_zf; n = nf; } else if (s == "ZtZ") { src = H->d_ZtZ; n = ldz * ldz; }
+  else if (s == "Hoo") { src = H->d_Hoo; n = np * 36; } else if (s == "Wt") { src = H->d_Wt; n = np * 6 * ldz; }
+  else if (s == "Z") { src = H->d_Z; n = np * 6 * ldz; } else if (s == "brec") { src = H->d_brec; n = (int64_t)H->nb * H->NT * 64; }
+  else if (s == "scale_e") { src = H->d_scale_e; n = np * 6; } else if (s == "scale_f") { src = H->d_scale_f; n = nf; }
+  else if (s == "diag_e") { src = H->d_diag_e; n = np * 6; } else if (s == "diag_f") { src = H->d_diag_f; n = nf; }
+  else { H->err = "unknown buffer"; return MCBA_ERR_INVALID; }
+  if (n_out) *n_out = n;
+  if (out) { CU(cudaStreamSynchronize(H->stream)); CU(cudaMemcpy(out, src, std::min(n, cap) * sizeof(double), cudaMemcpyDeviceToHost)); }
+  return MCBA_OK;
+}
+
+}  // extern "C"

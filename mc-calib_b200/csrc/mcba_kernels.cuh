@@ -1,0 +1,762 @@
+// mcba_kernels.cuh — sm_100a kernels of the bundle-adjustment hot path (fp64 throughout).
+//
+//   k_prep_blocks        K0  R, dR/dw_k, t per parameter block (replaces the per-residual Rodrigues setup
+//                            inside ceres::AngleAxisRotatePoint)
+//   k_observations<MODE> K1  one warp per board observation. MODE_FUSED: residual + Jacobian + J^T J / J^T r
+//                            accumulation with fp64 tensor-core MMA (DMMA m8n8k4) without materialising J;
+//                            MODE_MATERIALIZE: writes residuals + Jacobian planes to HBM (the HBM-roofline
+//                            kernel of BASELINE.json); MODE_FROM_J: reads those planes back and accumulates;
+//                            MODE_COST: residual-only pass for the candidate point.
+//   k_eblock_assemble    K2a per e-block: E^T E, E^T r and the dense row block [E^T F | E^T r]
+//   k_pair_reduce/final  K2b per (camera, board) pair: F^T F blocks and F^T r, fixed-order (deterministic)
+//   k_eblock_factor      K2c (E^T E + D^2) = L L^T, Z = L^-1 [E^T F | E^T r] (Jacobi-scaled)
+//   k_syrk / k_syrk_sum  K2d Schur complement sum_o Z_o^T Z_o with DMMA, split-K with fixed-order sum
+//   k_build_reduced      K2e S = F^T F + D^2 - Z^T Z, rhs
+//   k_chol_*             K3  blocked dense Cholesky + triangular solves of the reduced system
+//   k_backsubst, k_fstep K4  e-block back-substitution, candidate point, model-cost-change pieces
+// Replaces ProgramEvaluator / SchurEliminator / CHOLMOD of ceres-solver 2.2.0 as used by the reference
+// (SURVEY.md §2.2, §8a rows a12-a15).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "mcba_math.cuh"
+
+namespace mcba {
+
+constexpr int TS = 68;            // row stride (doubles) of the per-warp J^T tile: 64 rows + 4 (bank spread)
+constexpr int OBS_WARPS = 4;      // warps per CTA in the observation kernels
+enum { MODE_FUSED = 0, MODE_MATERIALIZE = 1, MODE_FROM_J = 2, MODE_COST = 3 };
+
+struct ObsArgs {
+  const float* u; const float* v; const int32_t* pt; const double* pts;   // observations (SoA) + point table
+  const int4* bobs;                 // [nb+1] {obs_begin, cam, pose, board}
+  const double* prep_cam; const double* prep_pose; const double* prep_board; const double* intr;
+  const int32_t* cam_model; const uint8_t* cam_is_ref; const uint8_t* board_is_ref;
+  double huber_a;
+  int nb;
+  double* brec;                     // [nb][NT*64] per-bobs J^T J tiles
+  double* cost_bobs;                // [nb]
+  double* jmat; double* resmat;     // materialised planes: jmat[(k*2+r)*npad + i], resmat[r*npad + i]
+  int64_t npad;
+};
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void k_prep_blocks(const double* __restrict__ cam_pose, int n_cam, const double* __restrict__ pose,
+                              int n_pose, const double* __restrict__ board_pose, int n_board,
+                              double* __restrict__ prep_cam, double* __restrict__ prep_pose,
+                              double* __restrict__ prep_board) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double* src; double* dst;
+  if (i < n_pose) { src = pose + 6 * (size_t)i; dst = prep_pose + PREP * (size_t)i; }
+  else if (i < n_pose + n_cam) { src = cam_pose + 6 * (size_t)(i - n_pose); dst = prep_cam + PREP * (size_t)(i - n_pose); }
+  else if (i < n_pose + n_cam + n_board) { const int b = i - n_pose - n_cam; src = board_pose + 6 * (size_t)b; dst = prep_board + PREP * (size_t)b; }
+  else return;
+  double p[6], out[PREP];
+  for (int k = 0; k < 6; ++k) p[k] = src[k];
+  prep_block(p, out);
+  for (int k = 0; k < PREP; ++k) dst[k] = out[k];
+}
+
+// Sinks for obs_jacobian
+struct TileSink {            // J^T tile in shared memory: T[col][2*lane + {0,1}]
+  double* T; int lane;
+  __device__ __forceinline__ void put(int col, double ju, double jv) {
+    *reinterpret_cast<double2*>(T + col * TS + 2 * lane) = make_double2(ju, jv);
+  }
+};
+template <int STAGE> struct PlaneSink {   // materialised planes in the reference column order
+  double* jmat; double* resmat; int64_t npad; int64_t i;
+  __device__ __forceinline__ void put(int col, double ju, double jv) {
+    typedef Cols<STAGE> C;
+    if (col == C::R0) { resmat[i] = ju; resmat[npad + i] = jv; return; }
+    const int k = C::to_ref(col);
+    jmat[(size_t)(2 * k) * npad + i] = ju;
+    jmat[(size_t)(2 * k + 1) * npad + i] = jv;
+  }
+};
+
+template <int STAGE, int MODE>
+__global__ void __launch_bounds__(OBS_WARPS * 32) k_observations(ObsArgs a) {
+  typedef Cols<STAGE> C;
+  typedef StageTraits<STAGE> ST;
+  constexpr bool ACC = (MODE == MODE_FUSED || MODE == MODE_FROM_J);
+  constexpr int TILE_DOUBLES = ACC ? C::NBLK * 8 * TS : 0;
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* ctx = smem + warp * (CTX_SIZE + TILE_DOUBLES);
+  double* T = ctx + CTX_SIZE;
+  if (ACC) {
+    for (int e = lane; e < TILE_DOUBLES; e += 32) T[e] = 0.0;
+  }
+  const int g = lane >> 2, q = lane & 3;
+  const int total_warps = gridDim.x * OBS_WARPS;
+  for (int b = blockIdx.x * OBS_WARPS + warp; b < a.nb; b += total_warps) {
+    const int4 rec = a.bobs[b];
+    const int obs_begin = rec.x, obs_end = a.bobs[b + 1].x;
+    const int cam = rec.y;
+    const bool act_c = ST::CAM && !(a.cam_is_ref && a.cam_is_ref[cam]);
+    const bool act_b = ST::BOARD && !(a.board_is_ref && a.board_is_ref[rec.w]);
+    const int model = a.cam_model[cam];
+    const double* pc = ST::CAM ? a.prep_cam + (size_t)PREP * cam : nullptr;
+    const double* po = a.prep_pose + (size_t)PREP * rec.z;
+    const double* pb = ST::BOARD ? a.prep_board + (size_t)PREP * rec.w : nullptr;
+    const double* in = a.intr + 9 * (size_t)cam;
+    __syncwarp();
+    if (MODE != MODE_FROM_J) {
+      for (int e = lane; e < CTX_SIZE; e += 32)
+        if (e < CTX_NO || e >= CTX_IN) ctx[e] = ctx_entry_a(e, pc, act_c, po, pb, act_b, in);
+      __syncwarp();
+      if (MODE != MODE_COST) {
+        for (int e = CTX_NO + lane; e < CTX_IN; e += 32) ctx[e] = ctx_entry_b(e, ctx, po, pb, act_b);
+        __syncwarp();
+      }
+    }
+    double acc[ACC ? C::NT : 1][2];
+#pragma unroll
+    for (int t = 0; t < (ACC ? C::NT : 1); ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    double cost = 0.0;
+    for (int base = obs_begin; base < obs_end; base += 32) {
+      const int i = base + lane;
+      const bool active = i < obs_end;
+      if (active) {
+        if (MODE == MODE_FROM_J) {
+#pragma unroll
+          for (int col = 0; col < C::NC; ++col) {
+            double ju, jv;
+            if (col == C::R0) { ju = a.resmat[i]; jv = a.resmat[a.npad + i]; }
+            else { const int k = C::to_ref(col); ju = a.jmat[(size_t)(2 * k) * a.npad + i]; jv = a.jmat[(size_t)(2 * k + 1) * a.npad + i]; }
+            *reinterpret_cast<double2*>(T + col * TS + 2 * lane) = make_double2(ju, jv);
+          }
+        } else {
+          const double* p3 = a.pts + 3 * (size_t)a.pt[i];
+          const double X0[3] = {p3[0], p3[1], p3[2]};
+          const double uu = (double)a.u[i], vv = (double)a.v[i];
+          if (MODE == MODE_COST) {
+            double ru, rv;
+            cost += obs_cost(ctx, model, X0, uu, vv, a.huber_a, ru, rv);
+          } else if (MODE == MODE_FUSED) {
+            TileSink sink{T, lane};
+            cost += obs_jacobian<STAGE>(ctx, act_c, act_b, model, X0, uu, vv, a.huber_a, sink);
+          } else {
+            PlaneSink<STAGE> sink{a.jmat, a.resmat, a.npad, (int64_t)i};
+            cost += obs_jacobian<STAGE>(ctx, act_c, act_b, model, X0, uu, vv, a.huber_a, sink);
+          }
+        }
+      } else if (ACC) {
+#pragma unroll
+        for (int col = 0; col < C::NC; ++col)
+          *reinterpret_cast<double2*>(T + col * TS + 2 * lane) = make_double2(0.0, 0.0);
+      }
+      if (ACC) {
+        __syncwarp();
+        const int nrows = 2 * min(32, obs_end - base);
+        const int ksteps = (nrows + 3) >> 2;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          double f[C::NBLK];
+#pragma unroll
+          for (int c = 0; c < C::NBLK; ++c) f[c] = T[(8 * c + g) * TS + 4 * ks + q];
+          int t = 0;
+#pragma unroll
+          for (int bi = 0; bi < C::NBLK; ++bi)
+#pragma unroll
+            for (int bj = bi; bj < C::NBLK; ++bj) { dmma884(acc[t][0], acc[t][1], f[bi], f[bj]); ++t; }
+        }
+        __syncwarp();
+      }
+    }
+    if (ACC) {
+      double* out = a.brec + (size_t)b * (C::NT * 64);
+#pragma unroll
+      for (int t = 0; t < C::NT; ++t)
+        *reinterpret_cast<double2*>(out + t * 64 + lane * 2) = make_double2(acc[t][0], acc[t][1]);
+    }
+    if (MODE != MODE_FROM_J) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, off);
+      if (lane == 0) a.cost_bobs[b] = cost;
+    }
+  }
+}
+
+// Unrobustified per-observation reprojection error sqrt(du^2+dv^2) (McCalib.cpp:2168-2245 averages these).
+template <int STAGE>
+__global__ void __launch_bounds__(OBS_WARPS * 32) k_reproj_err(ObsArgs a, double* __restrict__ err) {
+  typedef StageTraits<STAGE> ST;
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* ctx = smem + warp * CTX_SIZE;
+  const int total_warps = gridDim.x * OBS_WARPS;
+  for (int b = blockIdx.x * OBS_WARPS + warp; b < a.nb; b += total_warps) {
+    const int4 rec = a.bobs[b];
+    const int obs_begin = rec.x, obs_end = a.bobs[b + 1].x, cam = rec.y;
+    const bool act_c = ST::CAM && !(a.cam_is_ref && a.cam_is_ref[cam]);
+    const bool act_b = ST::BOARD && !(a.board_is_ref && a.board_is_ref[rec.w]);
+    const double* pc = ST::CAM ? a.prep_cam + (size_t)PREP * cam : nullptr;
+    const double* pb = ST::BOARD ? a.prep_board + (size_t)PREP * rec.w : nullptr;
+    __syncwarp();
+    for (int e = lane; e < CTX_SIZE; e += 32)
+      if (e < CTX_NO || e >= CTX_IN) ctx[e] = ctx_entry_a(e, pc, act_c, a.prep_pose + (size_t)PREP * rec.z, pb, act_b, a.intr + 9 * (size_t)cam);
+    __syncwarp();
+    for (int i = obs_begin + lane; i < obs_end; i += 32) {
+      const double* p3 = a.pts + 3 * (size_t)a.pt[i];
+      const double X0[3] = {p3[0], p3[1], p3[2]};
+      double ru, rv;
+      obs_cost(ctx, a.cam_model[cam], X0, (double)a.u[i], (double)a.v[i], 0.0, ru, rv);
+      err[i] = sqrt(ru * ru + rv * rv);
+    }
+  }
+}
+
+__global__ void k_flag_to_scalar(const int* __restrict__ flag, double* __restrict__ out) { *out = (double)*flag; }
+
+// ---------------------------------------------------------------------------------------------
+// Deterministic reductions: out[c] = op_c over rows of in[n][m]; columns < m_sum are summed, the others maxed.
+// Stage 1: fixed contiguous chunks; stage 2: one CTA. Summation order depends only on (n, grid).
+constexpr int RED_T = 256;
+__device__ __forceinline__ double red_op(double x, double y, bool is_max) { return is_max ? fmax(x, y) : x + y; }
+__global__ void __launch_bounds__(RED_T) k_reduce_rows(const double* __restrict__ in, int64_t n, int m, int m_sum,
+                                                       int64_t rows_per_block, double* __restrict__ out) {
+  __shared__ double sh[RED_T];
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(n, r0 + rows_per_block);
+  for (int c = 0; c < m; ++c) {
+    const bool is_max = c >= m_sum;
+    double acc = is_max ? -DBL_MAX : 0.0;
+    for (int64_t r = r0 + threadIdx.x; r < r1; r += RED_T) acc = red_op(acc, in[r * m + c], is_max);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = RED_T / 2; s > 0; s >>= 1) {
+      if (threadIdx.x < s) sh[threadIdx.x] = red_op(sh[threadIdx.x], sh[threadIdx.x + s], is_max);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[(size_t)blockIdx.x * m + c] = sh[0];
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2a: per e-block sums over its board observations (fixed order): Hoo (6x6 full), and the dense row block
+// Wt[o] = [E^T F (6 x n_f) | E^T r] with leading dimension ldz.
+template <int STAGE>
+__global__ void __launch_bounds__(192) k_eblock_assemble(const int4* __restrict__ bobs, const int* __restrict__ pose_bobs_ptr,
+                                                         const double* __restrict__ brec, int n_cam, int Wc, int Wb,
+                                                         int n_f, int ldz, double* __restrict__ Hoo,
+                                                         double* __restrict__ Wt) {
+  typedef Cols<STAGE> C;
+  extern __shared__ double W[];   // [6][ldz]
+  const int o = blockIdx.x, tid = threadIdx.x;
+  for (int e = tid; e < 6 * ldz; e += blockDim.x) W[e] = 0.0;
+  __syncthreads();
+  const int b0 = pose_bobs_ptr[o], b1 = pose_bobs_ptr[o + 1];
+  if (tid < 6 * C::WF) {
+    const int k = tid / C::WF, j = tid % C::WF;           // e-row k, local f column j
+    const int ecol = C::E0 + k;
+    const int off = tile_index(j >> 3, ecol >> 3, C::NBLK) * 64 + (j & 7) * 8 + (ecol & 7);
+    for (int b = b0; b < b1; ++b) {
+      const int4 rec = bobs[b];
+      const int gcol = (j < C::B0) ? rec.y * Wc + j : n_cam * Wc + rec.w * Wb + (j - C::B0);
+      W[k * ldz + gcol] += brec[(size_t)b * (C::NT * 64) + off];
+    }
+  } else if (tid < 6 * C::WF + 36) {
+    const int e = tid - 6 * C::WF, p = e / 6, r = e % 6;
+    const int lo = C::E0 + min(p, r), hi = C::E0 + max(p, r);
+    const int off = tile_index(lo >> 3, hi >> 3, C::NBLK) * 64 + (lo & 7) * 8 + (hi & 7);
+    double s = 0.0;
+    for (int b = b0; b < b1; ++b) s += brec[(size_t)b * (C::NT * 64) + off];
+    Hoo[(size_t)o * 36 + e] = s;
+  } else if (tid < 6 * C::WF + 42) {
+    const int k = tid - 6 * C::WF - 36;
+    const int ecol = C::E0 + k;
+    const int off = tile_index(ecol >> 3, C::R0 >> 3, C::NBLK) * 64 + (ecol & 7) * 8 + (C::R0 & 7);
+    double s = 0.0;
+    for (int b = b0; b < b1; ++b) s += brec[(size_t)b * (C::NT * 64) + off];
+    W[k * ldz + n_f] = s;
+  }
+  __syncthreads();
+  double* dst = Wt + (size_t)o * 6 * ldz;
+  for (int e = tid; e < 6 * ldz; e += blockDim.x) dst[e] = W[e];
+}
+
+// K2b: per (camera[,board]) pair, fixed-order sum over the pair's board observations of the f x f upper
+// triangle and the f x r column. Entry t of a pair record: a <= b < WF -> a*WF - a(a-1)/2 + (b-a);
+// then WF(WF+1)/2 + a for (a, r).
+template <int STAGE> struct PairRec {
+  typedef Cols<STAGE> C;
+  static constexpr int NFF = C::WF * (C::WF + 1) / 2;
+  static constexpr int NE = NFF + C::WF;
+  __host__ __device__ static int ff(int a, int b) { return a * C::WF - a * (a - 1) / 2 + (b - a); }   // a <= b
+};
+struct PairChunk { int pair, begin, end, first; };   // [begin,end) in pair_bobs; first = 1 for the pair's first chunk
+
+template <int STAGE>
+__global__ void __launch_bounds__(256) k_pair_reduce(const PairChunk* __restrict__ chunks, const int* __restrict__ pair_bobs,
+                                                     const double* __restrict__ brec, double* __restrict__ partial) {
+  typedef Cols<STAGE> C;
+  typedef PairRec<STAGE> PR;
+  const int t = threadIdx.x;
+  if (t >= PR::NE) return;
+  int a, b;
+  if (t < PR::NFF) {   // invert the triangular index
+    a = 0; int rem = t;
+    while (rem >= C::WF - a) { rem -= C::WF - a; ++a; }
+    b = a + rem;
+  } else { a = t - PR::NFF; b = C::R0; }
+  const int off = tile_index(a >> 3, b >> 3, C::NBLK) * 64 + (a & 7) * 8 + (b & 7);
+  const PairChunk ch = chunks[blockIdx.x];
+  double s = 0.0;
+  for (int i = ch.begin; i < ch.end; ++i) s += brec[(size_t)pair_bobs[i] * (C::NT * 64) + off];
+  partial[(size_t)blockIdx.x * PR::NE + t] = s;
+}
+template <int STAGE>
+__global__ void k_pair_final(const int* __restrict__ pair_chunk_ptr, int n_pair, const double* __restrict__ partial,
+                             double* __restrict__ pair_rec) {
+  typedef PairRec<STAGE> PR;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_pair * PR::NE) return;
+  const int p = idx / PR::NE, t = idx % PR::NE;
+  double s = 0.0;
+  for (int c = pair_chunk_ptr[p]; c < pair_chunk_ptr[p + 1]; ++c) s += partial[(size_t)c * PR::NE + t];
+  pair_rec[idx] = s;
+}
+
+// Dense F^T F (n_f x n_f, full symmetric, unscaled) and F^T r from the pair records.
+template <int STAGE>
+__global__ void k_ff_assemble(const double* __restrict__ pair_rec, int n_cam, int n_board, int Wc, int Wb, int n_f,
+                              double* __restrict__ FF, double* __restrict__ gf) {
+  typedef Cols<STAGE> C;
+  typedef PairRec<STAGE> PR;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nbp = C::T::BOARD ? n_board : 1;   // pairs per camera
+  if (idx < n_f * n_f) {
+    const int i = idx / n_f, j = idx % n_f;
+    const int lo = min(i, j), hi = max(i, j);
+    const int ncw = n_cam * Wc;
+    double s = 0.0;
+    if (hi < ncw) {                         // camera x camera
+      const int c = lo / Wc;
+      if (hi / Wc == c) { const int e = PR::ff(lo - c * Wc, hi - c * Wc); for (int b = 0; b < nbp; ++b) s += pair_rec[(size_t)(c * nbp + b) * PR::NE + e]; }
+    } else if (lo >= ncw) {                 // board x board
+      const int b = (lo - ncw) / Wb;
+      if ((hi - ncw) / Wb == b) { const int e = PR::ff(C::B0 + lo - ncw - b * Wb, C::B0 + hi - ncw - b * Wb); for (int c = 0; c < n_cam; ++c) s += pair_rec[(size_t)(c * nbp + b) * PR::NE + e]; }
+    } else {                                // camera x board
+      const int c = lo / Wc, b = (hi - ncw) / Wb;
+      s = pair_rec[(size_t)(c * nbp + b) * PR::NE + PR::ff(lo - c * Wc, C::B0 + hi - ncw - b * Wb)];
+    }
+    FF[idx] = s;
+  } else if (idx < n_f * n_f + n_f) {
+    const int i = idx - n_f * n_f;
+    const int ncw = n_cam * Wc;
+    double s = 0.0;
+    if (i < ncw) { const int c = i / Wc; for (int b = 0; b < nbp; ++b) s += pair_rec[(size_t)(c * nbp + b) * PR::NE + PR::NFF + (i - c * Wc)]; }
+    else { const int b = (i - ncw) / Wb; for (int c = 0; c < n_cam; ++c) s += pair_rec[(size_t)(c * nbp + b) * PR::NE + PR::NFF + C::B0 + (i - ncw - b * Wb)]; }
+    gf[i] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Jacobi scaling (TrustRegionMinimizer, iteration 0): s_j = 1/(1+sqrt(|J_j|^2)); LM diagonal
+// (LevenbergMarquardtStrategy::ComputeStep): diag_j = clamp(s_j^2 |J_j|^2, min, max).
+__global__ void k_scale_diag(const double* __restrict__ Hoo, int n_pose, const double* __restrict__ FF, int n_f,
+                             int compute_scale, int jacobi, double min_diag, double max_diag,
+                             double* __restrict__ scale_e, double* __restrict__ scale_f,
+                             double* __restrict__ diag_e, double* __restrict__ diag_f) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ne = n_pose * 6;
+  if (idx >= ne + n_f) return;
+  const bool is_e = idx < ne;
+  const int j = is_e ? idx : idx - ne;
+  const double h = is_e ? Hoo[(size_t)(j / 6) * 36 + (j % 6) * 7] : FF[(size_t)j * n_f + j];
+  double* sc = is_e ? scale_e : scale_f;
+  if (compute_scale) sc[j] = jacobi ? 1.0 / (1.0 + sqrt(h)) : 1.0;
+  const double s = sc[j];
+  const double d = fmin(fmax(s * s * h, min_diag), max_diag);
+  (is_e ? diag_e : diag_f)[j] = d;
+}
+
+// Gradient max-norm pieces |x - (x + (-g))| (computed through Plus as Ceres does) and |x|^2, per e-block.
+// part[o] = {sum x^2, max |x - (x - g)|}
+__global__ void k_eblock_grad(const double* __restrict__ pose, const double* __restrict__ Wt, int n_pose, int n_f,
+                              int ldz, double* __restrict__ part) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_pose) return;
+  double s = 0.0, m = 0.0;
+  for (int k = 0; k < 6; ++k) {
+    const double x = pose[(size_t)o * 6 + k], gk = Wt[((size_t)o * 6 + k) * ldz + n_f];
+    const double pg = x + (-gk);
+    s += x * x; m = fmax(m, fabs(x - pg));
+  }
+  part[(size_t)o * 2] = s; part[(size_t)o * 2 + 1] = m;
+}
+
+// K2c: factor the e-block, Z[o] = L^-1 (s_e [W | g] s_f). One CTA per e-block; every thread factors its own
+// copy of the 6x6 in registers (cheaper than a barrier), then handles columns j = tid, tid+T, ...
+__global__ void __launch_bounds__(128) k_eblock_factor(const double* __restrict__ Hoo, const double* __restrict__ Wt,
+                                                       const double* __restrict__ scale_e, const double* __restrict__ scale_f,
+                                                       const double* __restrict__ diag_e, double radius, int n_f, int ldz,
+                                                       double* __restrict__ Lout, double* __restrict__ Z,
+                                                       int* __restrict__ fail) {
+  const int o = blockIdx.x;
+  double L[36], se[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) se[k] = scale_e[(size_t)o * 6 + k];
+#pragma unroll
+  for (int p = 0; p < 6; ++p)
+#pragma unroll
+    for (int r = 0; r < 6; ++r) L[p * 6 + r] = se[p] * Hoo[(size_t)o * 36 + p * 6 + r] * se[r];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) L[k * 7] += diag_e[(size_t)o * 6 + k] / radius;
+  const bool ok = chol6(L);
+  if (!ok) { if (threadIdx.x == 0) atomicExch(fail, 1); }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int e = 0; e < 36; ++e) Lout[(size_t)o * 36 + e] = ok ? L[e] : 0.0;
+  }
+  const double* W = Wt + (size_t)o * 6 * ldz;
+  double* Zo = Z + (size_t)o * 6 * ldz;
+  for (int j = threadIdx.x; j < ldz; j += blockDim.x) {
+    double w[6];
+    const double sf = (j < n_f) ? scale_f[j] : 1.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) w[k] = (j <= n_f) ? se[k] * W[k * ldz + j] * sf : 0.0;
+    if (ok) chol6_fwd(L, w);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Zo[k * ldz + j] = ok ? w[k] : 0.0;
+  }
+}
+
+// K2d: C = Z^T Z restricted to upper tile pairs, split over row ranges. 64x64 tile per CTA, 4 warps (2x2),
+// each warp 32x32 = 4x4 DMMA tiles; K chunk of 16 rows staged through shared memory with register prefetch.
+constexpr int SY_T = 64, SY_K = 16, SY_LD = 68;
+__global__ void __launch_bounds__(128) k_syrk(const double* __restrict__ Z, int64_t n_rows, int ldz, int nt,
+                                              int64_t rows_per_split, double* __restrict__ partial) {
+  __shared__ double As[SY_K * SY_LD];
+  __shared__ double Bs[SY_K * SY_LD];
+  // tile pair from linear index (ti <= tj)
+  int ti = 0, rem = blockIdx.x;
+  while (rem >= nt - ti) { rem -= nt - ti; ++ti; }
+  const int tj = ti + rem;
+  const int split = blockIdx.y;
+  const int64_t r0 = (int64_t)split * rows_per_split, r1 = min(n_rows, r0 + rows_per_split);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+  // each thread stages 8 doubles of A and of B per chunk: row = e / 16, col4 = (e % 16) * 4 ... as 4 double2 loads
+  double2 ra[4], rb[4];
+  const bool diag = (ti == tj);
+  auto gload = [&](int64_t rbase) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 128;            // 0..511 double2 slots: 16 rows x 32 double2
+      const int row = e >> 5, c2 = (e & 31) * 2;
+      const int64_t r = rbase + row;
+      const int ca = ti * SY_T + c2, cb = tj * SY_T + c2;
+      ra[i] = (r < r1 && ca < ldz) ? *reinterpret_cast<const double2*>(Z + r * ldz + ca) : make_double2(0.0, 0.0);
+      if (!diag) rb[i] = (r < r1 && cb < ldz) ? *reinterpret_cast<const double2*>(Z + r * ldz + cb) : make_double2(0.0, 0.0);
+    }
+  };
+  auto sstore = [&]() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 128;
+      const int row = e >> 5, c2 = (e & 31) * 2;
+      *reinterpret_cast<double2*>(As + row * SY_LD + c2) = ra[i];
+      if (!diag) *reinterpret_cast<double2*>(Bs + row * SY_LD + c2) = rb[i];
+    }
+  };
+  const double* Bp = diag ? As : Bs;
+  if (r0 < r1) gload(r0);
+  for (int64_t rbase = r0; rbase < r1; rbase += SY_K) {
+    __syncthreads();
+    sstore();
+    __syncthreads();
+    if (rbase + SY_K < r1) gload(rbase + SY_K);
+#pragma unroll
+    for (int ks = 0; ks < SY_K / 4; ++ks) {
+      double fa[4], fb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) fa[i] = As[(4 * ks + q) * SY_LD + wm + 8 * i + g];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) fb[j] = Bp[(4 * ks + q) * SY_LD + wn + 8 * j + g];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+    }
+  }
+  double* out = partial + ((size_t)split * gridDim.x + blockIdx.x) * (SY_T * SY_T);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<double2*>(out + (wm + 8 * i + g) * SY_T + wn + 8 * j + 2 * q) = make_double2(acc[i][j][0], acc[i][j][1]);
+}
+// Fixed-order sum of the split-K partials into the dense upper part of ZtZ (ldz x ldz).
+__global__ void k_syrk_sum(const double* __restrict__ partial, int n_tiles, int nt, int nsplit, int ldz,
+                           double* __restrict__ ZtZ) {
+  const int tile = blockIdx.x;
+  int ti = 0, rem = tile;
+  while (rem >= nt - ti) { rem -= nt - ti; ++ti; }
+  const int tj = ti + rem;
+  for (int e = threadIdx.x; e < SY_T * SY_T; e += blockDim.x) {
+    const int i = ti * SY_T + e / SY_T, j = tj * SY_T + e % SY_T;
+    if (i >= ldz || j >= ldz) continue;
+    double s = 0.0;
+    for (int sp = 0; sp < nsplit; ++sp) s += partial[((size_t)sp * n_tiles + tile) * (SY_T * SY_T) + e];
+    ZtZ[(size_t)i * ldz + j] = s;
+  }
+}
+
+// K2e: reduced system. S = s_f F^T F s_f + D_f^2 - Z^T Z (full symmetric, n_f x n_f, ld n_f); rhs = s_f g_f - Z^T y.
+__global__ void k_build_reduced(const double* __restrict__ FF, const double* __restrict__ gf,
+                                const double* __restrict__ ZtZ, const double* __restrict__ scale_f,
+                                const double* __restrict__ diag_f, double radius, int n_f, int ldz,
+                                double* __restrict__ S, double* __restrict__ rhs) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n_f * n_f) {
+    const int i = idx / n_f, j = idx % n_f;
+    const int lo = min(i, j), hi = max(i, j);
+    double s = scale_f[i] * FF[idx] * scale_f[j] - ZtZ[(size_t)lo * ldz + hi];
+    if (i == j) s += diag_f[i] / radius;
+    S[idx] = s;
+  } else if (idx < n_f * n_f + n_f) {
+    const int i = idx - n_f * n_f;
+    rhs[i] = scale_f[i] * gf[i] - ZtZ[(size_t)i * ldz + n_f];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: blocked right-looking Cholesky of S (lower, in place, row-major ld n). Panel width 32.
+constexpr int CH_B = 32;
+__global__ void __launch_bounds__(32) k_chol_diag(double* __restrict__ S, int n, int j0, int* __restrict__ fail) {
+  __shared__ double A[CH_B][CH_B + 1];
+  const int jb = min(CH_B, n - j0), t = threadIdx.x;
+  for (int r = 0; r < jb; ++r) if (t < jb) A[r][t] = S[(size_t)(j0 + r) * n + j0 + t];
+  __syncwarp();
+  for (int j = 0; j < jb; ++j) {
+    // column j: rows t >= j
+    double s = 0.0;
+    if (t >= j && t < jb) { s = A[t][j]; for (int k = 0; k < j; ++k) s -= A[t][k] * A[j][k]; }
+    const double d = __shfl_sync(0xffffffffu, s, j);
+    if (!(d > 0.0) || !(d < DBL_MAX)) { if (t == 0) atomicExch(fail, 1); return; }
+    const double l = sqrt(d);
+    if (t == j) A[t][j] = l; else if (t > j && t < jb) A[t][j] = s / l;
+    __syncwarp();
+  }
+  for (int r = 0; r < jb; ++r) if (t <= r && t < jb) S[(size_t)(j0 + r) * n + j0 + t] = A[r][t];
+}
+// rows below the panel: L21 = A21 L11^-T, one thread per row
+__global__ void __launch_bounds__(128) k_chol_trsm(double* __restrict__ S, int n, int j0, const int* __restrict__ fail) {
+  __shared__ double L[CH_B][CH_B + 1];
+  __shared__ double X[128][CH_B + 1];
+  if (*fail) return;
+  const int jb = min(CH_B, n - j0), t = threadIdx.x;
+  for (int e = t; e < jb * jb; e += 128) L[e / jb][e % jb] = S[(size_t)(j0 + e / jb) * n + j0 + e % jb];
+  const int i = j0 + jb + blockIdx.x * 128 + t;
+  // coalesced load of the 128 x jb block
+  for (int e = t; e < 128 * jb; e += 128) {
+    const int r = e / jb, c = e % jb, gi = j0 + jb + blockIdx.x * 128 + r;
+    X[r][c] = (gi < n) ? S[(size_t)gi * n + j0 + c] : 0.0;
+  }
+  __syncthreads();
+  if (i < n) {
+    for (int j = 0; j < jb; ++j) {
+      double s = X[t][j];
+      for (int k = 0; k < j; ++k) s -= X[t][k] * L[j][k];
+      X[t][j] = s / L[j][j];
+    }
+  }
+  __syncthreads();
+  for (int e = t; e < 128 * jb; e += 128) {
+    const int r = e / jb, c = e % jb, gi = j0 + jb + blockIdx.x * 128 + r;
+    if (gi < n) S[(size_t)gi * n + j0 + c] = X[r][c];
+  }
+}
+// trailing update A22 -= L21 L21^T on lower-triangle 64x64 tiles; 256 threads, 4x4 per thread
+__global__ void __launch_bounds__(256) k_chol_update(double* __restrict__ S, int n, int j0, const int* __restrict__ fail) {
+  __shared__ double Pi[64][CH_B + 1];
+  __shared__ double Pj[64][CH_B + 1];
+  if (*fail) return;
+  const int jb = min(CH_B, n - j0), base = j0 + jb;
+  // tile pair (ti >= tj) from linear index
+  int tj = 0, rem = blockIdx.x; const int nt = (n - base + 63) / 64;
+  while (rem >= nt - tj) { rem -= nt - tj; ++tj; }
+  const int ti = tj + rem;
+  const int t = threadIdx.x;
+  for (int e = t; e < 64 * jb; e += 256) {
+    const int r = e / jb, c = e % jb;
+    const int gi = base + ti * 64 + r, gj = base + tj * 64 + r;
+    Pi[r][c] = (gi < n) ? S[(size_t)gi * n + j0 + c] : 0.0;
+    Pj[r][c] = (gj < n) ? S[(size_t)gj * n + j0 + c] : 0.0;
+  }
+  __syncthreads();
+  const int tr = (t / 16) * 4, tc = (t % 16) * 4;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  for (int k = 0; k < jb; ++k) {
+    double x[4], y[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { x[a] = Pi[tr + a][k]; y[a] = Pj[tc + a][k]; }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] += x[a] * y[b];
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int gi = base + ti * 64 + tr + a, gj = base + tj * 64 + tc + b;
+      if (gi < n && gj <= gi) S[(size_t)gi * n + gj] -= acc[a][b];
+    }
+}
+// z = L^-T L^-1 rhs, single CTA, blocked by 32 columns
+__global__ void __launch_bounds__(1024) k_chol_solve(const double* __restrict__ S, int n, const double* __restrict__ rhs,
+                                                     double* __restrict__ z, const int* __restrict__ fail) {
+  extern __shared__ double b[];   // [n]
+  const int t = threadIdx.x;
+  if (*fail) { for (int i = t; i < n; i += blockDim.x) z[i] = 0.0; return; }
+  for (int i = t; i < n; i += blockDim.x) b[i] = rhs[i];
+  __syncthreads();
+  for (int j0 = 0; j0 < n; j0 += CH_B) {          // forward: L y = b
+    const int jb = min(CH_B, n - j0);
+    if (t < 32) {
+      for (int j = 0; j < jb; ++j) {
+        if (t == 0) b[j0 + j] /= S[(size_t)(j0 + j) * n + j0 + j];
+        __syncwarp();
+        const int i = j + 1 + t;
+        if (i < jb) b[j0 + i] -= S[(size_t)(j0 + i) * n + j0 + j] * b[j0 + j];
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    for (int i = j0 + jb + t; i < n; i += blockDim.x) {
+      double s = b[i]; const double* Li = S + (size_t)i * n + j0;
+      for (int k = 0; k < jb; ++k) s -= Li[k] * b[j0 + k];
+      b[i] = s;
+    }
+    __syncthreads();
+  }
+  for (int j0 = ((n - 1) / CH_B) * CH_B; j0 >= 0; j0 -= CH_B) {   // backward: L^T z = y
+    const int jb = min(CH_B, n - j0);
+    if (t < 32) {
+      for (int j = jb - 1; j >= 0; --j) {
+        if (t == 0) b[j0 + j] /= S[(size_t)(j0 + j) * n + j0 + j];
+        __syncwarp();
+        if (t < j) b[j0 + t] -= S[(size_t)(j0 + j) * n + j0 + t] * b[j0 + j];
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    for (int i = t; i < j0; i += blockDim.x) {
+      double s = b[i];
+      for (int k = 0; k < jb; ++k) s -= S[(size_t)(j0 + k) * n + i] * b[j0 + k];
+      b[i] = s;
+    }
+    __syncthreads();
+  }
+  for (int i = t; i < n; i += blockDim.x) z[i] = b[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: e-block back-substitution z_o = L^-T (y_o - Z_o z_f); candidate x+ = x + s_e * (-z_o); pieces of
+// model_cost_change and of the norms. part[o] = {p.y, |p|^2 - sum D^2 z^2 + 2 p.q, sum (x - x+)^2, sum x+^2}
+__global__ void __launch_bounds__(128) k_backsubst(const double* __restrict__ Z, const double* __restrict__ Lall,
+                                                   const double* __restrict__ zf, const double* __restrict__ scale_e,
+                                                   const double* __restrict__ diag_e, double radius,
+                                                   const double* __restrict__ pose, int n_f, int ldz,
+                                                   double* __restrict__ pose_cand, double* __restrict__ part) {
+  __shared__ double red[6][128];
+  const int o = blockIdx.x, t = threadIdx.x;
+  const double* Zo = Z + (size_t)o * 6 * ldz;
+  double qa[6] = {0, 0, 0, 0, 0, 0};
+  for (int j = t; j < n_f; j += 128) {
+    const double zj = zf[j];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) qa[k] += Zo[k * ldz + j] * zj;
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) red[k][t] = qa[k];
+  __syncthreads();
+  for (int s = 64; s > 0; s >>= 1) {
+    if (t < s) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) red[k][t] += red[k][t + s];
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    double L[36], p[6], q[6], y[6], zo[6];
+    for (int e = 0; e < 36; ++e) L[e] = Lall[(size_t)o * 36 + e];
+    double py = 0, pp = 0, pq = 0;
+    for (int k = 0; k < 6; ++k) { q[k] = red[k][0]; y[k] = Zo[k * ldz + n_f]; p[k] = y[k] - q[k]; zo[k] = p[k]; py += p[k] * y[k]; pp += p[k] * p[k]; pq += p[k] * q[k]; }
+    chol6_bwd(L, zo);
+    double dz = 0, sn = 0, xn = 0;
+    for (int k = 0; k < 6; ++k) {
+      const double d2 = diag_e[(size_t)o * 6 + k] / radius;
+      dz += d2 * zo[k] * zo[k];
+      const double x = pose[(size_t)o * 6 + k];
+      const double delta = scale_e[(size_t)o * 6 + k] * (-zo[k]);
+      const double xc = x + delta;
+      pose_cand[(size_t)o * 6 + k] = xc;
+      sn += (x - xc) * (x - xc); xn += xc * xc;
+    }
+    part[(size_t)o * 4 + 0] = py; part[(size_t)o * 4 + 1] = pp - dz + 2.0 * pq;
+    part[(size_t)o * 4 + 2] = sn; part[(size_t)o * 4 + 3] = xn;
+  }
+}
+
+// f part of the step (single CTA): candidate f-blocks, z_f.gs_f, z_f^T (s FF s) z_f, sum (x-x+)^2, sum x+^2,
+// and at Jacobian evaluation time (zf == nullptr): sum x_f^2 and max |x - (x - g)| only.
+// State layout of f: camera c -> [pose 6][intr 9] (whichever exist), then boards.
+struct FState { double* cam_pose; double* intr; double* board; };
+__device__ __forceinline__ double* f_slot(const FState& s, int j, int n_cam, int Wc, int Wb, bool has_cam) {
+  const int ncw = n_cam * Wc;
+  if (j < ncw) { const int c = j / Wc, l = j % Wc; return (has_cam && l < 6) ? s.cam_pose + 6 * c + l : s.intr + 9 * c + (l - (has_cam ? 6 : 0)); }
+  const int b = (j - ncw) / Wb, l = (j - ncw) % Wb;
+  return s.board + 6 * b + l;
+}
+__global__ void __launch_bounds__(1024) k_fstep(FState cur, FState cand, const double* __restrict__ zf,
+                                                const double* __restrict__ FF, const double* __restrict__ gf,
+                                                const double* __restrict__ scale_f, int n_f, int n_cam, int Wc, int Wb,
+                                                int has_cam, double* __restrict__ out /*[4]*/) {
+  __shared__ double red[4][1024];
+  const int t = threadIdx.x;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  for (int j = t; j < n_f; j += 1024) {
+    const double x = *f_slot(cur, j, n_cam, Wc, Wb, has_cam);
+    if (zf) {
+      const double z = zf[j], sj = scale_f[j];
+      const double xc = x + sj * (-z);
+      *f_slot(cand, j, n_cam, Wc, Wb, has_cam) = xc;
+      double hz = 0.0;
+      for (int k = 0; k < n_f; ++k) hz += FF[(size_t)k * n_f + j] * scale_f[k] * zf[k];   // symmetric: column read is coalesced
+      a0 += z * sj * gf[j]; a1 += z * sj * hz; a2 += (x - xc) * (x - xc); a3 += xc * xc;
+    } else {
+      const double pg = x + (-gf[j]);
+      a0 += x * x; a1 = fmax(a1, fabs(x - pg));
+    }
+  }
+  red[0][t] = a0; red[1][t] = a1; red[2][t] = a2; red[3][t] = a3;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if (t < s) {
+      red[0][t] += red[0][t + s]; red[2][t] += red[2][t + s]; red[3][t] += red[3][t + s];
+      red[1][t] = zf ? red[1][t] + red[1][t + s] : fmax(red[1][t], red[1][t + s]);
+    }
+    __syncthreads();
+  }
+  if (t < 4) out[t] = red[t][0];
+}
+
+}  // namespace mcba

@@ -186,6 +186,7 @@ def load_lib():
     L.mcba_kernel_name.restype = C.c_char_p
     L.mcba_kernel_stats.argtypes = [vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     L.mcba_reset_kernel_stats.argtypes = [vp]
+    L.mcba_debug_fetch.argtypes = [vp, C.c_char_p, c_f64p, C.c_int64, C.POINTER(C.c_int64)]
     _lib = L
     return L
 
@@ -276,6 +277,14 @@ class Handle:
             n, ms = C.c_int64(), C.c_double()
             self.lib.mcba_kernel_stats(self.h, k, C.byref(n), C.byref(ms))
             out[self.lib.mcba_kernel_name(k).decode()] = (n.value, ms.value)
+        return out
+
+    def debug_fetch(self, name):
+        n = C.c_int64()
+        self._check(self.lib.mcba_debug_fetch(self.h, name.encode(), c_f64p(), 0, C.byref(n)), "mcba_debug_fetch")
+        out = np.zeros(n.value)
+        self._check(self.lib.mcba_debug_fetch(self.h, name.encode(), _ptr(out, c_f64p), n.value, C.byref(n)),
+                    "mcba_debug_fetch")
         return out
 
     def reset_kernel_stats(self):

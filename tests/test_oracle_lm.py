@@ -1,0 +1,111 @@
+"""Pins the oracle's Levenberg-Marquardt restatement: the committed traces, the minimum found by an independent
+algorithm (scipy trust-region-reflective with the same Huber objective), and Ceres' bookkeeping rules."""
+import json
+import os
+
+import numpy as np
+import pytest
+from scipy.optimize import least_squares
+
+import mcba
+from mcba import synth
+from util import dense_jacobian, layout, params_to_x
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("cfg,stage", [("c1", 4), ("c1", 5), ("c2", 4), ("c2", 5)])
+def test_trace_fixture(cfg, stage, oracle):
+    doc = json.load(open(os.path.join(GOLD, f"trace_{cfg}_stage{stage}.json")))
+    prob4, init, gt, s, o = synth.config_problem(cfg, 4)
+    p = init.copy()
+    if stage == 5:   # the fixture chain is stage 4 then stage 5, like apps/calibrate/src/calibrate.cpp:60-64
+        rc, _, _ = oracle.solve(prob4, p)
+        p.intrinsics[:] = s.intr_init
+    rc, summ, tr = oracle.solve(prob4.with_stage(stage), p)
+    assert rc == 0 and prob4.n_obs == doc["n_obs"]
+    assert summ.termination == doc["termination"]
+    assert (summ.num_successful_steps, summ.num_unsuccessful_steps) == (doc["num_successful_steps"], doc["num_unsuccessful_steps"])
+    assert len(tr) == len(doc["rows"])
+    for r, d in zip(tr, doc["rows"]):
+        assert (r.iteration, r.step_is_valid, r.step_is_successful) == (d["iteration"], d["valid"], d["successful"])
+        assert abs(r.cost - d["cost"]) <= 1e-9 * d["cost"]
+        assert abs(r.trust_region_radius - d["radius"]) <= 1e-6 * d["radius"]
+    assert abs(summ.rms_px - doc["rms_px"]) <= 1e-8
+    assert np.abs(p.intrinsics - np.array(doc["intrinsics"])).max() <= 1e-7 * np.abs(p.intrinsics).max()
+
+
+def test_trace_bookkeeping(oracle):
+    """Ceres rules: iteration 0 is recorded as a successful step with radius = initial radius; after a successful
+    step with ratio rho the radius grows by 1/max(1/3, 1-(2 rho-1)^3); cost is monotone over successful steps."""
+    prob, init, gt, s, o = synth.config_problem("c1", 5)
+    rc, summ, tr = oracle.solve(prob, init.copy())
+    assert tr[0].iteration == 0 and tr[0].step_is_successful == 1 and tr[0].trust_region_radius == 1e4
+    assert summ.num_successful_steps + summ.num_unsuccessful_steps == len(tr)
+    for a, b in zip(tr[:-1], tr[1:]):
+        if b.step_is_successful:
+            assert b.cost < a.cost
+            grow = 1.0 / max(1.0 / 3.0, 1.0 - (2.0 * b.relative_decrease - 1.0) ** 3)
+            assert abs(b.trust_region_radius - min(1e16, a.trust_region_radius * grow)) <= 1e-9 * b.trust_region_radius
+    assert summ.termination == 0
+
+
+def test_max_iterations_and_no_convergence(oracle):
+    prob, init, gt, s, o = synth.config_problem("c1", 5)
+    rc, summ, tr = oracle.solve(prob, init.copy(), mcba.default_options(max_num_iterations=2))
+    assert summ.termination == 1 and len(tr) == 3 and tr[-1].iteration == 2
+
+
+def test_rejected_steps_shrink_radius(oracle):
+    """A tiny min_relative_decrease can't be violated, so force rejections with an absurd one: every step is
+    rejected, radius halves, then quarters ... (StepRejected: radius /= decrease_factor; decrease_factor *= 2)."""
+    prob, init, gt, s, o = synth.config_problem("c1", 4)
+    rc, summ, tr = oracle.solve(prob, init.copy(), mcba.default_options(max_num_iterations=4, min_relative_decrease=1e9))
+    radii = [r.trust_region_radius for r in tr]
+    assert [r.step_is_successful for r in tr] == [1, 0, 0, 0, 0]
+    assert np.allclose(radii, [1e4, 5e3, 1.25e3, 156.25, 9.765625])
+
+
+def test_minimum_matches_scipy_huber(oracle):
+    """Independent minimiser, same objective 1/2 sum rho(|r_i|^2): scipy's loss applies rho per scalar residual, so
+    the per-observation Huber on the 2-vector is reproduced by handing scipy the pre-robustified residuals."""
+    s = synth.make_scene("c1", n_frames=40)
+    o = synth.generate_observations(s)
+    prob, init, gt = synth.make_problem(s, o, 4)
+    p = init.copy()
+    rc, summ, tr = oracle.solve(prob, p, mcba.default_options(function_tolerance=1e-14, parameter_tolerance=1e-14))
+    x_star = params_to_x(prob, p)
+    L = layout(prob)
+
+    def unpack(x):
+        q = init.copy()
+        q.pose[:] = x[:L["n_e"]].reshape(-1, 6)
+        f = x[L["n_e"]:]
+        q.cam_pose[:] = f[:prob.n_cam * 6].reshape(-1, 6)
+        q.board_pose[:] = f[prob.n_cam * 6:].reshape(-1, 6)
+        return q
+
+    def fun_jac(x):     # sqrt(rho(|r|^2)) per observation: 1/2 sum fun^2 = the Ceres objective
+        q = unpack(x)
+        _, cost, res, jac, _ = oracle.eval(prob, q, mcba.default_options(huber_a=0.0))
+        sq = (res ** 2).sum(1)
+        rho = np.where(sq <= 1, sq, 2 * np.sqrt(sq) - 1)
+        drho = np.where(sq <= 1, 1.0, 1.0 / np.sqrt(np.maximum(sq, 1e-300)))
+        f = np.sqrt(rho)
+        J = dense_jacobian(prob, jac)                       # (2N, n_x), rows 2i, 2i+1
+        Jf = (drho / np.maximum(f, 1e-300))[:, None] * (res[:, 0:1] * J[0::2] + res[:, 1:2] * J[1::2])
+        return f, Jf
+
+    free = np.ones(L["n_e"] + L["n_f"], bool)
+    free[L["n_e"]:L["n_e"] + 6] = False                      # reference camera
+    free[L["n_e"] + prob.n_cam * 6:L["n_e"] + prob.n_cam * 6 + 6] = False   # reference board
+    x0 = params_to_x(prob, init)
+
+    def full(z):
+        x = x0.copy(); x[free] = z
+        return x
+
+    sol = least_squares(lambda z: fun_jac(full(z))[0], x0[free], jac=lambda z: fun_jac(full(z))[1][:, free],
+                        method="trf", xtol=1e-15, ftol=1e-15, gtol=1e-13, max_nfev=100)
+    assert abs(sol.cost - summ.final_cost) <= 1e-9 * summ.final_cost
+    assert np.abs(sol.x - x_star[free]).max() <= 1e-6
