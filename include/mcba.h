@@ -160,6 +160,9 @@ int mcba_num_kernels(void);
 const char *mcba_kernel_name(int k);
 int mcba_kernel_stats(void *handle, int k, int64_t *launches, double *total_ms);
 int mcba_reset_kernel_stats(void *handle);
+int64_t mcba_kernel_launches(void *handle);          /* kernels launched by this handle so far */
+int mcba_timer_start(void *handle);                  /* CUDA event on the library's stream (after a stream sync) */
+int mcba_timer_stop(void *handle, double *ms);       /* second event + elapsed device time between the two */
 
 /* Test hook: copy an internal device buffer (normal-equation blocks, reduced system, scaling) to the host.
  * Names: "FF" "gf" "S" "rhs" "zf" "ZtZ" "Hoo" "Wt" "Z" "brec" "scale_e" "scale_f" "diag_e" "diag_f". */

@@ -100,6 +100,8 @@ struct Handle {
   struct Pending { int fam; cudaEvent_t a, b; };
   std::vector<Pending> pending; std::vector<cudaEvent_t> free_events;
   int64_t kf_launches[KF_COUNT] = {0}; double kf_ms[KF_COUNT] = {0};
+  int64_t n_launches = 0;   // kernels launched by this handle
+  cudaEvent_t tm_a = nullptr, tm_b = nullptr;
 };
 
 #define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { H->err = std::string(#x) + ": " + cudaGetErrorString(e_); return MCBA_ERR_CUDA; } } while (0)
@@ -224,9 +226,12 @@ static int reduce_rows(Handle* H, const double* in, int64_t n, int m, int m_sum,
   int nblk = (int)std::min<int64_t>(512, std::max<int64_t>(1, (n + 2047) / 2048));
   const int64_t rpb = (n + nblk - 1) / std::max(1, nblk);
   if (nblk == 1) {
+    ++H->n_launches;
     k_reduce_rows<<<1, RED_T, 0, H->stream>>>(in, n, m, m_sum, std::max<int64_t>(n, 1), out_dev);
   } else {
+    ++H->n_launches;
     k_reduce_rows<<<nblk, RED_T, 0, H->stream>>>(in, n, m, m_sum, rpb, H->d_red_scratch);
+    ++H->n_launches;
     k_reduce_rows<<<1, RED_T, 0, H->stream>>>(H->d_red_scratch, nblk, m, m_sum, nblk, out_dev);
   }
   CHECK_LAUNCH();
@@ -246,6 +251,7 @@ static ObsArgs obs_args(Handle* H, int which, double huber_a) {
 static int launch_prep(Handle* H, int which) {
   Timed t(H, KF_PREP);
   const int n = H->n_pose + H->n_cam + H->n_board;
+  ++H->n_launches;
   k_prep_blocks<<<(n + 127) / 128, 128, 0, H->stream>>>(H->d_cam_pose[which], H->n_cam, H->d_pose[which], H->n_pose,
                                                         H->d_board[which], H->n_board, H->d_prep_cam, H->d_prep_pose,
                                                         H->d_prep_board);
@@ -264,6 +270,7 @@ template <int MODE> static int launch_obs(Handle* H, int which, double huber_a) 
     constexpr bool ACC = (MODE == MODE_FUSED || MODE == MODE_FROM_J);
     const int sm = OBS_WARPS * (CTX_SIZE + (ACC ? Cols<ST>::NBLK * 8 * TS : 0)) * 8;
     const int grid = grid_for(H->nb, ACC ? std::max(1, (227 * 1024) / (sm + 1024)) : 8);
+    ++H->n_launches;
     k_observations<ST, MODE><<<grid, OBS_WARPS * 32, sm, H->stream>>>(a);
   });
   CHECK_LAUNCH();
@@ -319,6 +326,7 @@ static int eval_jacobian(Handle* H, bool first) {
   if ((rc = reduce_rows(H, H->d_cost_bobs, H->nb, 1, 1, H->d_scalars + SC_COST))) return rc;
   if (H->n_pose > 0) {
     Timed t(H, KF_EASSEMBLE);
+    ++H->n_launches;
     DISPATCH_STAGE(H->stage, (k_eblock_assemble<ST><<<H->n_pose, 192, 6 * H->ldz * 8, H->stream>>>(
         H->d_bobs, H->d_pose_bobs_ptr, H->d_brec, H->n_cam, H->Wc, H->Wb, H->n_f, H->ldz, H->d_Hoo, H->d_Wt)));
     CHECK_LAUNCH();
@@ -326,10 +334,12 @@ static int eval_jacobian(Handle* H, bool first) {
   {
     Timed t(H, KF_PAIR);
     if (H->n_chunks > 0) {
+      ++H->n_launches;
       DISPATCH_STAGE(H->stage, (k_pair_reduce<ST><<<H->n_chunks, 256, 0, H->stream>>>(H->d_chunks, H->d_pair_bobs, H->d_brec, H->d_pair_partial)));
       CHECK_LAUNCH();
     }
     const int n = H->n_pair * H->NE;
+    ++H->n_launches;
     DISPATCH_STAGE(H->stage, (k_pair_final<ST><<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_pair_chunk_ptr, H->n_pair, H->d_pair_partial, H->d_pair_rec)));
     CHECK_LAUNCH();
   }
@@ -337,15 +347,18 @@ static int eval_jacobian(Handle* H, bool first) {
   {
     Timed t(H, KF_PAIR);
     const int n = H->n_f * H->n_f + H->n_f;
+    ++H->n_launches;
     DISPATCH_STAGE(H->stage, (k_ff_assemble<ST><<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_pair_rec, H->n_cam, H->n_board, H->Wc, H->Wb, H->n_f, H->d_FF, H->d_gf)));
     CHECK_LAUNCH();
   }
   {
     Timed t(H, KF_REDUCE);
     if (H->n_pose > 0) {
+      ++H->n_launches;
       k_eblock_grad<<<(H->n_pose + 127) / 128, 128, 0, H->stream>>>(H->d_pose[H->cur], H->d_Wt, H->n_pose, H->n_f, H->ldz, H->d_part_e);
       CHECK_LAUNCH();
     }
+    ++H->n_launches;
     k_fstep<<<1, 1024, 0, H->stream>>>(fstate(H, H->cur), fstate(H, H->cur), nullptr, H->d_FF, H->d_gf, H->d_scale_f, H->n_f, H->n_cam, H->Wc, H->Wb, sd.cam ? 1 : 0, H->d_scalars + SC_F0);
     CHECK_LAUNCH();
   }
@@ -353,6 +366,7 @@ static int eval_jacobian(Handle* H, bool first) {
   if (first || !H->have_scale) {
     Timed t(H, KF_REDUCE);
     const int n = H->n_pose * 6 + H->n_f;
+    ++H->n_launches;
     k_scale_diag<<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_Hoo, H->n_pose, H->d_FF, H->n_f, 1, H->opt.jacobi_scaling, H->opt.min_lm_diagonal, H->opt.max_lm_diagonal, H->d_scale_e, H->d_scale_f, H->d_diag_e, H->d_diag_f);
     CHECK_LAUNCH();
     H->have_scale = true;
@@ -382,14 +396,18 @@ static int cholesky_reduced(Handle* H) {
   const int n = H->n_f;
   for (int j0 = 0; j0 < n; j0 += CH_B) {
     const int jb = std::min(CH_B, n - j0);
+    ++H->n_launches;
     k_chol_diag<<<1, 32, 0, H->stream>>>(H->d_S, n, j0, H->d_fail);
     const int m = n - j0 - jb;
     if (m > 0) {
+      ++H->n_launches;
       k_chol_trsm<<<(m + 127) / 128, 128, 0, H->stream>>>(H->d_S, n, j0, H->d_fail);
       const int nt = (m + 63) / 64;
+      ++H->n_launches;
       k_chol_update<<<nt * (nt + 1) / 2, 256, 0, H->stream>>>(H->d_S, n, j0, H->d_fail);
     }
   }
+  ++H->n_launches;
   k_chol_solve<<<1, 1024, n * sizeof(double), H->stream>>>(H->d_S, n, H->d_rhs, H->d_zf, H->d_fail);
   CHECK_LAUNCH();
   return MCBA_OK;
@@ -405,19 +423,23 @@ static int compute_step(Handle* H, StepOut* out) {
   if (!H->reuse_diagonal) {
     Timed t(H, KF_REDUCE);
     const int n = H->n_pose * 6 + H->n_f;
+    ++H->n_launches;
     k_scale_diag<<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_Hoo, H->n_pose, H->d_FF, H->n_f, 0, H->opt.jacobi_scaling, H->opt.min_lm_diagonal, H->opt.max_lm_diagonal, H->d_scale_e, H->d_scale_f, H->d_diag_e, H->d_diag_f);
     CHECK_LAUNCH();
   }
   H->reuse_diagonal = true;
   if (H->n_pose > 0) {
     Timed t(H, KF_EFACTOR);
+    ++H->n_launches;
     k_eblock_factor<<<H->n_pose, 128, 0, H->stream>>>(H->d_Hoo, H->d_Wt, H->d_scale_e, H->d_scale_f, H->d_diag_e, H->radius, H->n_f, H->ldz, H->d_L, H->d_Z, H->d_fail);
     CHECK_LAUNCH();
   }
   {
     Timed t(H, KF_SYRK);
     dim3 grid(H->syrk_tiles, H->syrk_nsplit);
+    ++H->n_launches;
     k_syrk<<<grid, 128, 0, H->stream>>>(H->d_Z, 6 * (int64_t)H->n_pose, H->ldz, H->syrk_nt, H->syrk_rows_per_split, H->d_syrk_partial);
+    ++H->n_launches;
     k_syrk_sum<<<H->syrk_tiles, 256, 0, H->stream>>>(H->d_syrk_partial, H->syrk_tiles, H->syrk_nt, H->syrk_nsplit, H->ldz, H->d_ZtZ);
     CHECK_LAUNCH();
   }
@@ -425,6 +447,7 @@ static int compute_step(Handle* H, StepOut* out) {
   {
     Timed t(H, KF_REDUCED);
     const int n = H->n_f * H->n_f + H->n_f;
+    ++H->n_launches;
     k_build_reduced<<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_FF, H->d_gf, H->d_ZtZ, H->d_scale_f, H->d_diag_f, H->radius, H->n_f, H->ldz, H->d_S, H->d_rhs);
     CHECK_LAUNCH();
   }
@@ -433,8 +456,10 @@ static int compute_step(Handle* H, StepOut* out) {
   {
     Timed t(H, KF_BACKSUBST);
     if (H->n_pose > 0) {
+      ++H->n_launches;
       k_backsubst<<<H->n_pose, 128, 0, H->stream>>>(H->d_Z, H->d_L, H->d_zf, H->d_scale_e, H->d_diag_e, H->radius, H->d_pose[H->cur], H->n_f, H->ldz, H->d_pose[cand], H->d_part_e);
     }
+    ++H->n_launches;
     k_fstep<<<1, 1024, 0, H->stream>>>(fstate(H, H->cur), fstate(H, cand), H->d_zf, H->d_FF, H->d_gf, H->d_scale_f, H->n_f, H->n_cam, H->Wc, H->Wb, sd.cam ? 1 : 0, H->d_scalars + SC_F0);
     CHECK_LAUNCH();
   }
@@ -444,6 +469,7 @@ static int compute_step(Handle* H, StepOut* out) {
   if ((rc = launch_obs<MODE_COST>(H, cand, H->opt.huber_a))) return rc;
   if ((rc = reduce_rows(H, H->d_cost_bobs, H->nb, 1, 1, H->d_scalars + SC_COST))) return rc;
   std::vector<double> hs;
+  ++H->n_launches;
   k_flag_to_scalar<<<1, 1, 0, H->stream>>>(H->d_fail, H->d_scalars + SC_FAIL);
   CHECK_LAUNCH();
   if ((rc = gather_scalars(H, H->d_scalars, SC_N, hs))) return rc;
@@ -528,6 +554,22 @@ int mcba_reset_kernel_stats(void* h) {
   return MCBA_OK;
 }
 int mcba_jacobian_width(int stage) { return stage_dims(stage).K; }
+int64_t mcba_kernel_launches(void* h) { return h ? ((Handle*)h)->n_launches : 0; }
+int mcba_timer_start(void* h) {
+  Handle* H = (Handle*)h; if (!H) return MCBA_ERR_INVALID;
+  if (!H->tm_a) { CU(cudaEventCreate(&H->tm_a)); CU(cudaEventCreate(&H->tm_b)); }
+  CU(cudaStreamSynchronize(H->stream));
+  CU(cudaEventRecord(H->tm_a, H->stream));
+  return MCBA_OK;
+}
+int mcba_timer_stop(void* h, double* ms) {
+  Handle* H = (Handle*)h; if (!H || !H->tm_a) return MCBA_ERR_INVALID;
+  CU(cudaEventRecord(H->tm_b, H->stream));
+  CU(cudaEventSynchronize(H->tm_b));
+  float f = 0; CU(cudaEventElapsedTime(&f, H->tm_a, H->tm_b));
+  if (ms) *ms = f;
+  return MCBA_OK;
+}
 
 void mcba_destroy(void* h) {
   Handle* H = (Handle*)h; if (!H) return;
@@ -536,6 +578,7 @@ void mcba_destroy(void* h) {
   if (H->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(H->comm);
   for (auto& p : H->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : H->free_events) cudaEventDestroy(e);
+  if (H->tm_a) { cudaEventDestroy(H->tm_a); cudaEventDestroy(H->tm_b); }
   dfree(&H->d_u); dfree(&H->d_v); dfree(&H->d_pt); dfree(&H->d_pts); dfree(&H->d_bobs); dfree(&H->d_pose_bobs_ptr);
   dfree(&H->d_cam_model); dfree(&H->d_cam_is_ref); dfree(&H->d_board_is_ref);
   dfree(&H->d_pair_bobs); dfree(&H->d_chunks); dfree(&H->d_pair_chunk_ptr);
@@ -814,6 +857,7 @@ int mcba_reprojection_errors(void* h, const mcba_params* p, double* err) {
   if (dalloc(H, &d_err, (size_t)H->npad)) return MCBA_ERR_CUDA;
   ObsArgs a = obs_args(H, 0, 0.0);
   if (H->nb > 0) {
+    ++H->n_launches;
     DISPATCH_STAGE(H->stage, (k_reproj_err<ST><<<grid_for(H->nb, 8), OBS_WARPS * 32, OBS_WARPS * CTX_SIZE * 8, H->stream>>>(a, d_err)));
   }
   cudaError_t e = cudaGetLastError();

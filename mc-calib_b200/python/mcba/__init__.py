@@ -186,6 +186,10 @@ def load_lib():
     L.mcba_kernel_name.restype = C.c_char_p
     L.mcba_kernel_stats.argtypes = [vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     L.mcba_reset_kernel_stats.argtypes = [vp]
+    L.mcba_kernel_launches.argtypes = [vp]
+    L.mcba_kernel_launches.restype = C.c_int64
+    L.mcba_timer_start.argtypes = [vp]
+    L.mcba_timer_stop.argtypes = [vp, c_f64p]
     L.mcba_debug_fetch.argtypes = [vp, C.c_char_p, c_f64p, C.c_int64, C.POINTER(C.c_int64)]
     _lib = L
     return L
@@ -278,6 +282,17 @@ class Handle:
             self.lib.mcba_kernel_stats(self.h, k, C.byref(n), C.byref(ms))
             out[self.lib.mcba_kernel_name(k).decode()] = (n.value, ms.value)
         return out
+
+    def kernel_launches(self):
+        return self.lib.mcba_kernel_launches(self.h)
+
+    def timer_start(self):
+        self._check(self.lib.mcba_timer_start(self.h), "mcba_timer_start")
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._check(self.lib.mcba_timer_stop(self.h, C.byref(ms)), "mcba_timer_stop")
+        return ms.value
 
     def debug_fetch(self, name):
         n = C.c_int64()
