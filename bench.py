@@ -153,6 +153,10 @@ def workload_config(n_gpus, n_obs_global, frames_global, sample_note=None):
 
 
 def main():
+    # libraries (NCCL, torch) may print to stdout: keep fd 1 for the single JSON line only
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

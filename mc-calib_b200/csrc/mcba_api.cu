@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -73,12 +74,14 @@ struct Handle {
   int* d_pair_bobs = nullptr; PairChunk* d_chunks = nullptr; int* d_pair_chunk_ptr = nullptr;
   double *d_brec = nullptr, *d_cost_bobs = nullptr, *d_Hoo = nullptr, *d_Wt = nullptr, *d_Z = nullptr, *d_L = nullptr;
   double *d_scale_e = nullptr, *d_diag_e = nullptr, *d_scale_f = nullptr, *d_diag_f = nullptr;
-  double *d_FF = nullptr, *d_gf = nullptr, *d_S = nullptr, *d_rhs = nullptr, *d_zf = nullptr, *d_ZtZ = nullptr;
+  double *d_FF = nullptr, *d_gf = nullptr, *d_S = nullptr, *d_rhs = nullptr, *d_zf = nullptr, *d_ZtZ = nullptr, *d_hz = nullptr;
   double *d_syrk_partial = nullptr, *d_pair_partial = nullptr, *d_pair_rec = nullptr, *d_part_e = nullptr;
   double *d_red_scratch = nullptr, *d_scalars = nullptr, *d_gather = nullptr;
   int* d_fail = nullptr;
   double *d_jmat = nullptr, *d_resmat = nullptr;   // lazily allocated
   int syrk_nt = 0, syrk_tiles = 0, syrk_nsplit = 0; int64_t syrk_rows_per_split = 0;
+  int chol_grid = 1, n_sm = 148;
+  long long* d_chol_prof = nullptr;
   // parameters: two copies (current / candidate), swapped on acceptance
   double *d_cam_pose[2] = {nullptr, nullptr}, *d_pose[2] = {nullptr, nullptr}, *d_board[2] = {nullptr, nullptr},
          *d_intr[2] = {nullptr, nullptr};
@@ -194,12 +197,14 @@ static int setup_stage(Handle* H, int stage) {
   if (dalloc(H, &H->d_Wt, np * 6 * ldz) || dalloc(H, &H->d_Z, np * 6 * ldz)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_scale_e, np * 6) || dalloc(H, &H->d_diag_e, np * 6)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_scale_f, nf) || dalloc(H, &H->d_diag_f, nf)) return MCBA_ERR_CUDA;
-  if (dalloc(H, &H->d_FF, nf * nf) || dalloc(H, &H->d_gf, nf) || dalloc(H, &H->d_S, nf * nf)) return MCBA_ERR_CUDA;
-  if (dalloc(H, &H->d_rhs, nf) || dalloc(H, &H->d_zf, nf) || dalloc(H, &H->d_ZtZ, ldz * ldz)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_FF, nf * nf) || dalloc(H, &H->d_gf, nf) || dalloc(H, &H->d_S, (nf + 1) * nf)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_hz, nf) || dalloc(H, &H->d_rhs, nf) || dalloc(H, &H->d_zf, nf) || dalloc(H, &H->d_ZtZ, ldz * ldz)) return MCBA_ERR_CUDA;
   H->syrk_nt = (H->ldz + SY_T - 1) / SY_T;
   H->syrk_tiles = H->syrk_nt * (H->syrk_nt + 1) / 2;
   const int64_t n_rows = 6 * (int64_t)H->n_pose;
-  int nsplit = (4 * 148 + H->syrk_tiles - 1) / H->syrk_tiles;
+  int syrk_per_sm = 4;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&syrk_per_sm, k_syrk, 128, 0);
+  int nsplit = std::max(1, (std::max(1, syrk_per_sm) * H->n_sm) / H->syrk_tiles);   // one full wave of CTAs, no tail
   nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(nsplit, (n_rows + 63) / 64));
   H->syrk_rows_per_split = (((n_rows + nsplit - 1) / nsplit + SY_K - 1) / SY_K) * SY_K;
   if (H->syrk_rows_per_split == 0) H->syrk_rows_per_split = SY_K;
@@ -393,23 +398,15 @@ static int eval_jacobian(Handle* H, bool first) {
 
 static int cholesky_reduced(Handle* H) {
   Timed t(H, KF_CHOL);
-  const int n = H->n_f;
-  for (int j0 = 0; j0 < n; j0 += CH_B) {
-    const int jb = std::min(CH_B, n - j0);
-    ++H->n_launches;
-    k_chol_diag<<<1, 32, 0, H->stream>>>(H->d_S, n, j0, H->d_fail);
-    const int m = n - j0 - jb;
-    if (m > 0) {
-      ++H->n_launches;
-      k_chol_trsm<<<(m + 127) / 128, 128, 0, H->stream>>>(H->d_S, n, j0, H->d_fail);
-      const int nt = (m + 63) / 64;
-      ++H->n_launches;
-      k_chol_update<<<nt * (nt + 1) / 2, 256, 0, H->stream>>>(H->d_S, n, j0, H->d_fail);
-    }
-  }
+  int n = H->n_f;
+  if (n > 2 * CC_B * CC_LD) { H->err = "reduced system too large for the cooperative Cholesky (n_f > 8704)"; return MCBA_ERR_INVALID; }
+  double* S = H->d_S; double* z = H->d_zf; int* fail = H->d_fail;
+  static const bool want_prof = getenv("MCBA_CHOL_PROF") != nullptr;
+  if (want_prof && !H->d_chol_prof) { CU(cudaMalloc((void**)&H->d_chol_prof, 8 * sizeof(long long))); CU(cudaMemset(H->d_chol_prof, 0, 8 * sizeof(long long))); }
+  long long* prof = H->d_chol_prof;
+  void* args[] = {&S, &n, &z, &fail, &prof};
   ++H->n_launches;
-  k_chol_solve<<<1, 1024, n * sizeof(double), H->stream>>>(H->d_S, n, H->d_rhs, H->d_zf, H->d_fail);
-  CHECK_LAUNCH();
+  CU(cudaLaunchCooperativeKernel((void*)k_chol_coop, dim3(H->chol_grid), dim3(CC_THREADS), args, CC_SMEM, H->stream));
   return MCBA_OK;
 }
 
@@ -457,10 +454,12 @@ static int compute_step(Handle* H, StepOut* out) {
     Timed t(H, KF_BACKSUBST);
     if (H->n_pose > 0) {
       ++H->n_launches;
-      k_backsubst<<<H->n_pose, 128, 0, H->stream>>>(H->d_Z, H->d_L, H->d_zf, H->d_scale_e, H->d_diag_e, H->radius, H->d_pose[H->cur], H->n_f, H->ldz, H->d_pose[cand], H->d_part_e);
+      k_backsubst<<<(H->n_pose + 7) / 8, 256, 0, H->stream>>>(H->d_Z, H->d_L, H->d_zf, H->d_scale_e, H->d_diag_e, H->radius, H->d_pose[H->cur], H->n_pose, H->n_f, H->ldz, H->d_pose[cand], H->d_part_e);
     }
     ++H->n_launches;
-    k_fstep<<<1, 1024, 0, H->stream>>>(fstate(H, H->cur), fstate(H, cand), H->d_zf, H->d_FF, H->d_gf, H->d_scale_f, H->n_f, H->n_cam, H->Wc, H->Wb, sd.cam ? 1 : 0, H->d_scalars + SC_F0);
+    k_ffz<<<(H->n_f + 7) / 8, 256, 0, H->stream>>>(H->d_FF, H->d_scale_f, H->d_zf, H->n_f, H->d_hz);
+    ++H->n_launches;
+    k_fstep<<<1, 1024, 0, H->stream>>>(fstate(H, H->cur), fstate(H, cand), H->d_zf, H->d_hz, H->d_gf, H->d_scale_f, H->n_f, H->n_cam, H->Wc, H->Wb, sd.cam ? 1 : 0, H->d_scalars + SC_F0);
     CHECK_LAUNCH();
   }
   if ((rc = reduce_rows(H, H->d_part_e, H->n_pose, 4, 4, H->d_scalars + SC_PE0))) return rc;
@@ -575,6 +574,11 @@ void mcba_destroy(void* h) {
   Handle* H = (Handle*)h; if (!H) return;
   cudaSetDevice(H->device);
   if (H->stream) cudaStreamSynchronize(H->stream);
+  if (H->d_chol_prof) {
+    long long p[8]; cudaMemcpy(p, H->d_chol_prof, sizeof(p), cudaMemcpyDeviceToHost);
+    std::fprintf(stderr, "[mcba chol prof, CTA0 cycles] diag %lld trsm %lld sync1 %lld update %lld sync2 %lld backsolve %lld\n", p[0], p[1], p[2], p[3], p[4], p[5]);
+    cudaFree(H->d_chol_prof);
+  }
   if (H->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(H->comm);
   for (auto& p : H->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : H->free_events) cudaEventDestroy(e);
@@ -584,7 +588,7 @@ void mcba_destroy(void* h) {
   dfree(&H->d_pair_bobs); dfree(&H->d_chunks); dfree(&H->d_pair_chunk_ptr);
   dfree(&H->d_brec); dfree(&H->d_cost_bobs); dfree(&H->d_Hoo); dfree(&H->d_Wt); dfree(&H->d_Z); dfree(&H->d_L);
   dfree(&H->d_scale_e); dfree(&H->d_diag_e); dfree(&H->d_scale_f); dfree(&H->d_diag_f);
-  dfree(&H->d_FF); dfree(&H->d_gf); dfree(&H->d_S); dfree(&H->d_rhs); dfree(&H->d_zf); dfree(&H->d_ZtZ);
+  dfree(&H->d_FF); dfree(&H->d_gf); dfree(&H->d_S); dfree(&H->d_rhs); dfree(&H->d_zf); dfree(&H->d_ZtZ); dfree(&H->d_hz);
   dfree(&H->d_syrk_partial); dfree(&H->d_pair_partial); dfree(&H->d_pair_rec); dfree(&H->d_part_e);
   dfree(&H->d_red_scratch); dfree(&H->d_scalars); dfree(&H->d_gather); dfree(&H->d_fail);
   dfree(&H->d_jmat); dfree(&H->d_resmat);
@@ -652,6 +656,11 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
       dalloc(H, &H->d_prep_board, (size_t)std::max(1, H->n_board) * PREP)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_red_scratch, (size_t)512 * 8) || dalloc(H, &H->d_scalars, (size_t)SC_N) || dalloc(H, &H->d_gather, (size_t)SC_N * 64) || dalloc(H, &H->d_fail, (size_t)1)) return MCBA_ERR_CUDA;
   CU(cudaMemset(H->d_scalars, 0, SC_N * sizeof(double)));
+  H->n_sm = prop.multiProcessorCount;
+  CU(cudaFuncSetAttribute(k_chol_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, CC_SMEM));
+  { int per_sm = 0; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chol_coop, CC_THREADS, CC_SMEM));
+    if (per_sm < 1 || !prop.cooperativeLaunch) { H->err = "cooperative launch unavailable"; return MCBA_ERR_CUDA; }
+    H->chol_grid = H->n_sm; }
   mcba_default_options(&H->opt);
   const int rc = setup_stage(H, P->stage);
   if (rc) return rc;

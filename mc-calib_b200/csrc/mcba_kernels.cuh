@@ -18,6 +18,7 @@
 // (SURVEY.md §2.2, §8a rows a12-a15).
 #pragma once
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 #include "mcba_math.cuh"
 
@@ -528,7 +529,9 @@ __global__ void k_build_reduced(const double* __restrict__ FF, const double* __r
     S[idx] = s;
   } else if (idx < n_f * n_f + n_f) {
     const int i = idx - n_f * n_f;
-    rhs[i] = scale_f[i] * gf[i] - ZtZ[(size_t)i * ldz + n_f];
+    const double v = scale_f[i] * gf[i] - ZtZ[(size_t)i * ldz + n_f];
+    rhs[i] = v;
+    S[(size_t)n_f * n_f + i] = v;   // extra row n_f: the factorisation turns it into L^-1 rhs
   }
 }
 
@@ -668,52 +671,243 @@ __global__ void __launch_bounds__(1024) k_chol_solve(const double* __restrict__ 
   for (int i = t; i < n; i += blockDim.x) z[i] = b[i];
 }
 
-// ---------------------------------------------------------------------------------------------
-// K4: e-block back-substitution z_o = L^-T (y_o - Z_o z_f); candidate x+ = x + s_e * (-z_o); pieces of
-// model_cost_change and of the norms. part[o] = {p.y, |p|^2 - sum D^2 z^2 + 2 p.q, sum (x - x+)^2, sum x+^2}
-__global__ void __launch_bounds__(128) k_backsubst(const double* __restrict__ Z, const double* __restrict__ Lall,
-                                                   const double* __restrict__ zf, const double* __restrict__ scale_e,
-                                                   const double* __restrict__ diag_e, double radius,
-                                                   const double* __restrict__ pose, int n_f, int ldz,
-                                                   double* __restrict__ pose_cand, double* __restrict__ part) {
-  __shared__ double red[6][128];
-  const int o = blockIdx.x, t = threadIdx.x;
-  const double* Zo = Z + (size_t)o * 6 * ldz;
-  double qa[6] = {0, 0, 0, 0, 0, 0};
-  for (int j = t; j < n_f; j += 128) {
-    const double zj = zf[j];
+// K3 (production): one cooperative persistent kernel for the whole factorisation + both triangular solves.
+// S is (n+1) x n row-major: rows 0..n-1 the symmetric reduced matrix (lower part used), row n the rhs.
+// Right-looking with 64-wide panels. Per panel: every CTA factors the 64x64 diagonal block redundantly in shared
+// memory (no broadcast needed), warps solve one row each of the panel below it (the rhs row included, which
+// performs the forward substitution for free), grid sync, DMMA trailing update on 64x64 lower tiles, grid sync.
+// CTA 0 finishes with the backward substitution L^T z = y.
+constexpr int CC_B = 64, CC_LD = 68, CC_DL = 65, CC_THREADS = 256;
+constexpr int CC_SMEM = (2 * CC_B * CC_DL + 2 * CC_B * CC_LD + CC_B) * 8;
+__global__ void __launch_bounds__(CC_THREADS) k_chol_coop(double* __restrict__ S, int n, double* __restrict__ z,
+                                                          int* __restrict__ fail, long long* __restrict__ prof) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) double sm[];
+  double* D = sm;                        // [64][65] working copy of the diagonal block
+  double* Lm = D + CC_B * CC_DL;         // [64][65] its Cholesky factor
+  double* Pa = Lm + CC_B * CC_DL;        // [64][68] panel rows of tile i
+  double* Pb = Pa + CC_B * CC_LD;        // [64][68] panel rows of tile j
+  double* invd = Pb + CC_B * CC_LD;      // [64] 1 / L_jj
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  long long tprev = clock64();
+#define CC_PROF(slot) do { if (prof && blockIdx.x == 0 && tid == 0) { const long long tn = clock64(); prof[slot] += tn - tprev; tprev = tn; } } while (0)
+  for (int j0 = 0; j0 < n; j0 += CC_B) {
+    const int jb = min(CC_B, n - j0);
+    // ---- diagonal block: register-resident right-looking factorisation. Thread (ty,tx) of the 16x16 layout owns the
+    // 4x4 entries (ty+16a, tx+16b); per pivot the owners publish column j through shared memory (double-buffered:
+    // one barrier per pivot), everybody applies the rank-1 update to its registers.
+    {
+      const int ty = tid >> 4, tx = tid & 15;
+      double a[4][4];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) qa[k] += Zo[k * ldz + j] * zj;
+      for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          const int r = ty + 16 * aa, c = tx + 16 * bb;
+          a[aa][bb] = (r < jb && c <= r) ? S[(size_t)(j0 + r) * n + j0 + c] : (r == c ? 1.0 : 0.0);
+        }
+      double* colbuf = D;   // [2][64]
+#pragma unroll
+      for (int bj = 0; bj < 4; ++bj) {
+        for (int jj = 0; jj < 16; ++jj) {
+          const int j = 16 * bj + jj;
+          if (j >= jb) break;
+          double* col = colbuf + (j & 1) * 64;
+          if (tx == jj) {
+#pragma unroll
+            for (int aa = 0; aa < 4; ++aa) col[ty + 16 * aa] = a[aa][bj];
+          }
+          __syncthreads();
+          const double d = col[j];
+          const bool bad = !(d > 0.0) || !(d < DBL_MAX);
+          const double inv = bad ? 1.0 : rsqrt(d);
+          if (bad && tid == 0 && blockIdx.x == 0) atomicExch(fail, 1);
+          double ri[4], ci[4];
+#pragma unroll
+          for (int aa = 0; aa < 4; ++aa) ri[aa] = col[ty + 16 * aa] * inv;
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) ci[bb] = col[tx + 16 * bb] * inv;
+#pragma unroll
+          for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) {
+              const int c = tx + 16 * bb;
+              if (c > j) a[aa][bb] -= ri[aa] * ci[bb];
+            }
+          if (tx == jj) {
+#pragma unroll
+            for (int aa = 0; aa < 4; ++aa) { a[aa][bj] = ri[aa]; Lm[(ty + 16 * aa) * CC_DL + j] = ri[aa]; }
+          }
+          if (tid == 0) invd[j] = inv;
+        }
+      }
+      __syncthreads();
+    }
+    CC_PROF(0);
+    // ---- panel below (rows base..n, the rhs row n included): one row per warp, column-oriented substitution
+    const int base = j0 + jb;
+    for (int r = base + blockIdx.x * (CC_THREADS / 32) + warp; r <= n; r += gridDim.x * (CC_THREADS / 32)) {
+      double* row = S + (size_t)r * n + j0;
+      double a0 = (lane < jb) ? row[lane] : 0.0, a1 = (lane + 32 < jb) ? row[lane + 32] : 0.0;
+      for (int j = 0; j < jb; ++j) {
+        const double xj = __shfl_sync(0xffffffffu, (j < 32) ? a0 : a1, j & 31) * invd[j];
+        if (lane == (j & 31)) { if (j < 32) a0 = xj; else a1 = xj; }
+        if (lane > j && lane < jb) a0 -= xj * Lm[lane * CC_DL + j];
+        if (lane + 32 > j && lane + 32 < jb) a1 -= xj * Lm[(lane + 32) * CC_DL + j];
+      }
+      if (lane < jb) row[lane] = a0;
+      if (lane + 32 < jb) row[lane + 32] = a1;
+    }
+    CC_PROF(1);
+    __threadfence();
+    grid.sync();
+    CC_PROF(2);
+    // every CTA has loaded the diagonal block by now: CTA 0 may overwrite it with its factor
+    if (blockIdx.x == 0)
+      for (int e = tid; e < jb * jb; e += CC_THREADS) { const int r = e / jb, c = e % jb; if (c <= r) S[(size_t)(j0 + r) * n + j0 + c] = Lm[r * CC_DL + c]; }
+    if (base >= n) break;   // last panel: only the rhs row was below it
+    // ---- trailing update on lower 64x64 tiles: C -= Pa Pb^T with DMMA; rows base..n (incl. rhs row), cols base..n-1
+    const int ntr = (n + 1 - base + CC_B - 1) / CC_B, ntc = (n - base + CC_B - 1) / CC_B;
+    int ntiles = 0;
+    for (int ti = 0; ti < ntr; ++ti) ntiles += min(ti, ntc - 1) + 1;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      int ti = 0, rem = t;
+      while (rem >= min(ti, ntc - 1) + 1) { rem -= min(ti, ntc - 1) + 1; ++ti; }
+      const int tj = rem;
+      const int row0 = base + ti * CC_B, col0 = base + tj * CC_B;
+      __syncthreads();
+      for (int e = tid; e < CC_B * CC_B; e += CC_THREADS) {
+        const int r = e >> 6, c = e & 63;
+        Pa[r * CC_LD + c] = (row0 + r <= n && c < jb) ? S[(size_t)(row0 + r) * n + j0 + c] : 0.0;
+        Pb[r * CC_LD + c] = (col0 + r < n && c < jb) ? S[(size_t)(col0 + r) * n + j0 + c] : 0.0;
+      }
+      __syncthreads();
+      const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;
+      double acc[4][2][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+      const int ksteps = (jb + 3) >> 2;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        double fa[4], fb[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) fa[i] = Pa[(wm + 8 * i + g) * CC_LD + 4 * ks + q];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) fb[j] = Pb[(wn + 8 * j + g) * CC_LD + 4 * ks + q];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int gr = row0 + wm + 8 * i + g, gc = col0 + wn + 8 * j + 2 * q + h;
+            if (gr <= n && gc < n && gc <= gr) S[(size_t)gr * n + gc] -= acc[i][j][h];
+          }
+    }
+    CC_PROF(3);
+    __threadfence();
+    grid.sync();
+    CC_PROF(4);
   }
-#pragma unroll
-  for (int k = 0; k < 6; ++k) red[k][t] = qa[k];
+  // ---- backward substitution L^T z = y (y = row n), CTA 0 only
+  if (blockIdx.x != 0) return;
   __syncthreads();
-  for (int s = 64; s > 0; s >>= 1) {
-    if (t < s) {
-#pragma unroll
-      for (int k = 0; k < 6; ++k) red[k][t] += red[k][t + s];
+  double* y = Pa;   // needs n doubles: n <= 64*68*2 = 8704
+  for (int i = tid; i < n; i += CC_THREADS) y[i] = S[(size_t)n * n + i];
+  __syncthreads();
+  for (int j0 = ((n - 1) / CC_B) * CC_B; j0 >= 0; j0 -= CC_B) {
+    const int jb = min(CC_B, n - j0);
+    for (int e = tid; e < jb * jb; e += CC_THREADS) { const int r = e / jb, c = e % jb; Lm[r * CC_DL + c] = (c <= r) ? S[(size_t)(j0 + r) * n + j0 + c] : 0.0; }
+    __syncthreads();
+    if (warp == 0) {
+      double a0 = (lane < jb) ? y[j0 + lane] : 0.0, a1 = (lane + 32 < jb) ? y[j0 + lane + 32] : 0.0;
+      for (int j = jb - 1; j >= 0; --j) {
+        const double zj = __shfl_sync(0xffffffffu, (j < 32) ? a0 : a1, j & 31) / Lm[j * CC_DL + j];
+        if (lane == (j & 31)) { if (j < 32) a0 = zj; else a1 = zj; }
+        if (lane < j) a0 -= zj * Lm[j * CC_DL + lane];
+        if (lane + 32 < j) a1 -= zj * Lm[j * CC_DL + lane + 32];
+      }
+      if (lane < jb) y[j0 + lane] = a0;
+      if (lane + 32 < jb) y[j0 + lane + 32] = a1;
+    }
+    __syncthreads();
+    for (int i = tid; i < j0; i += CC_THREADS) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int k = 0;
+#pragma unroll 4
+      for (; k + 4 <= jb; k += 4) {
+        s0 += S[(size_t)(j0 + k) * n + i] * y[j0 + k];
+        s1 += S[(size_t)(j0 + k + 1) * n + i] * y[j0 + k + 1];
+        s2 += S[(size_t)(j0 + k + 2) * n + i] * y[j0 + k + 2];
+        s3 += S[(size_t)(j0 + k + 3) * n + i] * y[j0 + k + 3];
+      }
+      for (; k < jb; ++k) s0 += S[(size_t)(j0 + k) * n + i] * y[j0 + k];
+      y[i] -= (s0 + s1) + (s2 + s3);
     }
     __syncthreads();
   }
-  if (t == 0) {
-    double L[36], p[6], q[6], y[6], zo[6];
-    for (int e = 0; e < 36; ++e) L[e] = Lall[(size_t)o * 36 + e];
-    double py = 0, pp = 0, pq = 0;
-    for (int k = 0; k < 6; ++k) { q[k] = red[k][0]; y[k] = Zo[k * ldz + n_f]; p[k] = y[k] - q[k]; zo[k] = p[k]; py += p[k] * y[k]; pp += p[k] * p[k]; pq += p[k] * q[k]; }
-    chol6_bwd(L, zo);
-    double dz = 0, sn = 0, xn = 0;
-    for (int k = 0; k < 6; ++k) {
-      const double d2 = diag_e[(size_t)o * 6 + k] / radius;
-      dz += d2 * zo[k] * zo[k];
-      const double x = pose[(size_t)o * 6 + k];
-      const double delta = scale_e[(size_t)o * 6 + k] * (-zo[k]);
-      const double xc = x + delta;
-      pose_cand[(size_t)o * 6 + k] = xc;
-      sn += (x - xc) * (x - xc); xn += xc * xc;
-    }
-    part[(size_t)o * 4 + 0] = py; part[(size_t)o * 4 + 1] = pp - dz + 2.0 * pq;
-    part[(size_t)o * 4 + 2] = sn; part[(size_t)o * 4 + 3] = xn;
+  const bool failed = *fail != 0;
+  for (int i = tid; i < n; i += CC_THREADS) z[i] = failed ? 0.0 : y[i];
+  CC_PROF(5);
+#undef CC_PROF
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: e-block back-substitution z_o = L^-T (y_o - Z_o z_f); candidate x+ = x + s_e * (-z_o); pieces of
+// model_cost_change and of the norms. part[o] = {p.y, |p|^2 - sum D^2 z^2 + 2 p.q, sum (x - x+)^2, sum x+^2}
+__global__ void __launch_bounds__(256) k_backsubst(const double* __restrict__ Z, const double* __restrict__ Lall,
+                                                   const double* __restrict__ zf, const double* __restrict__ scale_e,
+                                                   const double* __restrict__ diag_e, double radius,
+                                                   const double* __restrict__ pose, int n_pose, int n_f, int ldz,
+                                                   double* __restrict__ pose_cand, double* __restrict__ part) {
+  // one warp per e-block: q = Z_o z_f by lanes striding the columns (coalesced), xor-shuffle tree (fixed order)
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (o >= n_pose) return;
+  const double* Zo = Z + (size_t)o * 6 * ldz;
+  double q[6] = {0, 0, 0, 0, 0, 0};
+  for (int j = lane; j < n_f; j += 32) {
+    const double zj = zf[j];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) q[k] += Zo[k * ldz + j] * zj;
   }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) q[k] += __shfl_xor_sync(0xffffffffu, q[k], off);
+  }
+  if (lane != 0) return;
+  double L[36], p[6], zo[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c <= r; ++c) L[r * 6 + c] = Lall[(size_t)o * 36 + r * 6 + c];
+  double py = 0, pp = 0, pq = 0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double y = Zo[k * ldz + n_f];
+    p[k] = y - q[k]; zo[k] = p[k]; py += p[k] * y; pp += p[k] * p[k]; pq += p[k] * q[k];
+  }
+  chol6_bwd(L, zo);
+  double dz = 0, sn = 0, xn = 0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double d2 = diag_e[(size_t)o * 6 + k] / radius;
+    dz += d2 * zo[k] * zo[k];
+    const double x = pose[(size_t)o * 6 + k];
+    const double delta = scale_e[(size_t)o * 6 + k] * (-zo[k]);
+    const double xc = x + delta;
+    pose_cand[(size_t)o * 6 + k] = xc;
+    sn += (x - xc) * (x - xc); xn += xc * xc;
+  }
+  part[(size_t)o * 4 + 0] = py; part[(size_t)o * 4 + 1] = pp - dz + 2.0 * pq;
+  part[(size_t)o * 4 + 2] = sn; part[(size_t)o * 4 + 3] = xn;
 }
 
 // f part of the step (single CTA): candidate f-blocks, z_f.gs_f, z_f^T (s FF s) z_f, sum (x-x+)^2, sum x+^2,
@@ -726,8 +920,19 @@ __device__ __forceinline__ double* f_slot(const FState& s, int j, int n_cam, int
   const int b = (j - ncw) / Wb, l = (j - ncw) % Wb;
   return s.board + 6 * b + l;
 }
+// hz = (s FF s) z_f, one warp per row (FF is symmetric: row j read contiguously), xor-shuffle tree
+__global__ void __launch_bounds__(256) k_ffz(const double* __restrict__ FF, const double* __restrict__ scale_f,
+                                             const double* __restrict__ zf, int n_f, double* __restrict__ hz) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= n_f) return;
+  double s = 0.0;
+  for (int k = lane; k < n_f; k += 32) s += FF[(size_t)j * n_f + k] * scale_f[k] * zf[k];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) hz[j] = s * scale_f[j];
+}
 __global__ void __launch_bounds__(1024) k_fstep(FState cur, FState cand, const double* __restrict__ zf,
-                                                const double* __restrict__ FF, const double* __restrict__ gf,
+                                                const double* __restrict__ hzv, const double* __restrict__ gf,
                                                 const double* __restrict__ scale_f, int n_f, int n_cam, int Wc, int Wb,
                                                 int has_cam, double* __restrict__ out /*[4]*/) {
   __shared__ double red[4][1024];
@@ -739,9 +944,7 @@ __global__ void __launch_bounds__(1024) k_fstep(FState cur, FState cand, const d
       const double z = zf[j], sj = scale_f[j];
       const double xc = x + sj * (-z);
       *f_slot(cand, j, n_cam, Wc, Wb, has_cam) = xc;
-      double hz = 0.0;
-      for (int k = 0; k < n_f; ++k) hz += FF[(size_t)k * n_f + j] * scale_f[k] * zf[k];   // symmetric: column read is coalesced
-      a0 += z * sj * gf[j]; a1 += z * sj * hz; a2 += (x - xc) * (x - xc); a3 += xc * xc;
+      a0 += z * sj * gf[j]; a1 += z * hzv[j]; a2 += (x - xc) * (x - xc); a3 += xc * xc;
     } else {
       const double pg = x + (-gf[j]);
       a0 += x * x; a1 = fmax(a1, fabs(x - pg));

@@ -1,0 +1,68 @@
+"""Worker for test_gpu_multi.py, launched with torch.distributed.run: frame-sharded solve of config 2 (hybrid
+Brown + Kannala rig) on WORLD_SIZE GPUs; rank 0 checks the result against the CPU oracle on the full problem."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, "mc-calib_b200", "python"))
+sys.path.insert(0, os.path.join(REPO, "oracle"))
+import mcba  # noqa: E402
+from mcba import synth  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    frames = 240
+    per = frames // world
+    s = synth.make_scene("c2", n_frames=frames)
+    for stage in (4, 5):
+        o = synth.generate_observations(s, rank * per, (rank + 1) * per)
+        prob, init, gt = synth.make_problem(s, o, stage)
+        h = mcba.Handle(prob, device=local)
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = ctypes.create_string_buffer(128)
+            assert h.lib.mcba_nccl_unique_id(buf) == 0
+            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        h.comm_init(rank, world, uid.cpu().numpy().tobytes())
+        p = init.copy()
+        summ, trace = h.solve(p)
+        h.close()
+        # gather the sharded e-blocks
+        poses = [torch.zeros(per * 6, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(poses, torch.from_numpy(p.pose.reshape(-1)).cuda())
+        if rank == 0:
+            import oracle_py
+            of = synth.generate_observations(s)
+            pf, initf, _ = synth.make_problem(s, of, stage)
+            po = initf.copy()
+            rc, so, to = oracle_py.solve(pf, po)
+            assert rc == 0
+            got = [(r.iteration, r.step_is_valid, r.step_is_successful) for r in trace]
+            want = [(r.iteration, r.step_is_valid, r.step_is_successful) for r in to]
+            assert got == want, (got, want)
+            assert summ.termination == so.termination
+            assert abs(summ.rms_px - so.rms_px) <= 1e-6, (summ.rms_px, so.rms_px)
+            for a, b in zip(trace, to):
+                assert abs(a.cost - b.cost) <= 1e-9 * abs(b.cost)
+            allpose = torch.cat(poses).cpu().numpy().reshape(-1, 6)
+            assert np.abs(allpose - po.pose).max() <= 1e-6 * max(1.0, np.abs(po.pose).max())
+            assert np.abs(p.cam_pose - po.cam_pose).max() <= 1e-6
+            assert np.abs(p.board_pose - po.board_pose).max() <= 1e-6
+            assert np.abs(p.intrinsics - po.intrinsics).max() <= 1e-6 * np.abs(po.intrinsics).max()
+            print(f"MGPU_OK stage {stage} world {world} iterations {summ.num_iterations} rms {summ.rms_px:.6f}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
