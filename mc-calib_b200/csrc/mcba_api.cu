@@ -65,6 +65,7 @@ struct Handle {
   int stage = 0, n_cam = 0, n_pose = 0, n_board = 0, n_pts = 0, nb = 0;
   int64_t n_obs = 0, npad = 0;
   std::vector<int32_t> h_bobs_cam, h_bobs_pose, h_bobs_board;
+  std::vector<int64_t> h_bobs_ptr;
   // static device data
   float *d_u = nullptr, *d_v = nullptr; int32_t* d_pt = nullptr; double* d_pts = nullptr;
   int4* d_bobs = nullptr; int* d_pose_bobs_ptr = nullptr;
@@ -284,7 +285,7 @@ template <int MODE> static int launch_obs(Handle* H, int which, double huber_a) 
 
 static int ensure_jmat(Handle* H) {
   if (H->d_jmat) return MCBA_OK;
-  if (dalloc(H, &H->d_jmat, (size_t)2 * H->K * H->npad) || dalloc(H, &H->d_resmat, (size_t)2 * H->npad)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_jmat, (size_t)2 * (H->K + 1) * H->npad) || dalloc(H, &H->d_resmat, (size_t)2)) return MCBA_ERR_CUDA;
   return MCBA_OK;
 }
 
@@ -619,6 +620,7 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   std::vector<int4> bobs(H->nb + 1);
   std::vector<int> ppt(H->n_pose + 1, 0);
   H->h_bobs_cam.resize(H->nb); H->h_bobs_pose.resize(H->nb); H->h_bobs_board.resize(H->nb);
+  H->h_bobs_ptr.assign(P->bobs_ptr, P->bobs_ptr + H->nb + 1);
   for (int b = 0; b < H->nb; ++b) {
     const int c = P->bobs_cam[b], o = P->bobs_pose[b], bd = P->bobs_board ? P->bobs_board[b] : 0;
     if (c < 0 || c >= P->n_cam || o < 0 || o >= P->n_pose || (b > 0 && o < P->bobs_pose[b - 1]) ||
@@ -840,17 +842,24 @@ int mcba_eval(void* h, const mcba_params* p, const mcba_options* opt, double* co
   CU(cudaMemcpyAsync(&c, H->d_scalars + SC_COST, sizeof(double), cudaMemcpyDeviceToHost, H->stream));
   CU(cudaStreamSynchronize(H->stream));
   if (cost) *cost = c;
-  const int64_t n = H->n_obs, npad = H->npad; const int K = H->K;
-  if (residuals) {
-    std::vector<double> r((size_t)2 * npad);
-    CU(cudaMemcpy(r.data(), H->d_resmat, r.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    for (int64_t i = 0; i < n; ++i) { residuals[2 * i] = r[i]; residuals[2 * i + 1] = r[npad + i]; }
-  }
-  if (jacobian) {
-    std::vector<double> plane((size_t)npad);
-    for (int k = 0; k < K; ++k) for (int r = 0; r < 2; ++r) {
-      CU(cudaMemcpy(plane.data(), H->d_jmat + (size_t)(2 * k + r) * npad, npad * sizeof(double), cudaMemcpyDeviceToHost));
-      for (int64_t i = 0; i < n; ++i) jacobian[((size_t)i * 2 + r) * K + k] = plane[i];
+  const int K = H->K, NC = K + 1;
+  if (residuals || jacobian) {
+    std::vector<double> blk((size_t)2 * NC * H->n_obs);
+    CU(cudaMemcpy(blk.data(), H->d_jmat, blk.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    int ref_of[32];
+    DISPATCH_STAGE(H->stage, { for (int c = 0; c < K; ++c) ref_of[c] = Cols<ST>::to_ref(c); });
+    for (int b = 0; b < H->nb; ++b) {
+      const int64_t o0 = H->h_bobs_ptr[b], nobs = H->h_bobs_ptr[b + 1] - o0;
+      const double* base = blk.data() + (size_t)2 * NC * o0;
+      for (int64_t j = 0; j < nobs; ++j) {
+        const int64_t i = o0 + j;
+        if (jacobian)
+          for (int c = 0; c < K; ++c) {
+            jacobian[((size_t)i * 2 + 0) * K + ref_of[c]] = base[((size_t)c * nobs + j) * 2];
+            jacobian[((size_t)i * 2 + 1) * K + ref_of[c]] = base[((size_t)c * nobs + j) * 2 + 1];
+          }
+        if (residuals) { residuals[2 * i] = base[((size_t)K * nobs + j) * 2]; residuals[2 * i + 1] = base[((size_t)K * nobs + j) * 2 + 1]; }
+      }
     }
   }
   return std::isfinite(c) ? MCBA_OK : MCBA_ERR_NUMERIC;

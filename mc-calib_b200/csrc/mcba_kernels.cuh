@@ -37,7 +37,7 @@ struct ObsArgs {
   int nb;
   double* brec;                     // [nb][NT*64] per-bobs J^T J tiles
   double* cost_bobs;                // [nb]
-  double* jmat; double* resmat;     // materialised planes: jmat[(k*2+r)*npad + i], resmat[r*npad + i]
+  double* jmat; double* resmat;     // materialised Jacobian blocks (see BlockSink); resmat unused
   int64_t npad;
 };
 
@@ -69,14 +69,14 @@ struct TileSink {            // J^T tile in shared memory: T[col][2*lane + {0,1}
     *reinterpret_cast<double2*>(T + col * TS + 2 * lane) = make_double2(ju, jv);
   }
 };
-template <int STAGE> struct PlaneSink {   // materialised planes in the reference column order
-  double* jmat; double* resmat; int64_t npad; int64_t i;
+// Materialised Jacobian layout (MODE_MATERIALIZE writes, MODE_FROM_J reads): per board observation one contiguous
+// block of n_obs(bobs) x NC x 2 doubles starting at jmat + 2*NC*obs_begin, column-major inside the block:
+// element (local column c, corner j) = double2{u-row, v-row} at ((c * n_obs(bobs) + j) * 2). Column R0 holds the
+// corrected residual. A warp pass writes 512 contiguous bytes per column, all inside one ~21 KB region.
+struct BlockSink {
+  double* blk; int nobs, j;
   __device__ __forceinline__ void put(int col, double ju, double jv) {
-    typedef Cols<STAGE> C;
-    if (col == C::R0) { resmat[i] = ju; resmat[npad + i] = jv; return; }
-    const int k = C::to_ref(col);
-    jmat[(size_t)(2 * k) * npad + i] = ju;
-    jmat[(size_t)(2 * k + 1) * npad + i] = jv;
+    *reinterpret_cast<double2*>(blk + ((size_t)col * nobs + j) * 2) = make_double2(ju, jv);
   }
 };
 
@@ -125,13 +125,12 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) k_observations(ObsArgs a) {
       const bool active = i < obs_end;
       if (active) {
         if (MODE == MODE_FROM_J) {
+          const double* blk = a.jmat + (size_t)2 * C::NC * obs_begin;
+          const int nobs = obs_end - obs_begin, j = i - obs_begin;
 #pragma unroll
-          for (int col = 0; col < C::NC; ++col) {
-            double ju, jv;
-            if (col == C::R0) { ju = a.resmat[i]; jv = a.resmat[a.npad + i]; }
-            else { const int k = C::to_ref(col); ju = a.jmat[(size_t)(2 * k) * a.npad + i]; jv = a.jmat[(size_t)(2 * k + 1) * a.npad + i]; }
-            *reinterpret_cast<double2*>(T + col * TS + 2 * lane) = make_double2(ju, jv);
-          }
+          for (int col = 0; col < C::NC; ++col)
+            *reinterpret_cast<double2*>(T + col * TS + 2 * lane) =
+                *reinterpret_cast<const double2*>(blk + ((size_t)col * nobs + j) * 2);
         } else {
           const double* p3 = a.pts + 3 * (size_t)a.pt[i];
           const double X0[3] = {p3[0], p3[1], p3[2]};
@@ -143,7 +142,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) k_observations(ObsArgs a) {
             TileSink sink{T, lane};
             cost += obs_jacobian<STAGE>(ctx, act_c, act_b, model, X0, uu, vv, a.huber_a, sink);
           } else {
-            PlaneSink<STAGE> sink{a.jmat, a.resmat, a.npad, (int64_t)i};
+            BlockSink sink{a.jmat + (size_t)2 * C::NC * obs_begin, obs_end - obs_begin, i - obs_begin};
             cost += obs_jacobian<STAGE>(ctx, act_c, act_b, model, X0, uu, vv, a.huber_a, sink);
           }
         }
@@ -694,52 +693,67 @@ __global__ void __launch_bounds__(CC_THREADS) k_chol_coop(double* __restrict__ S
 #define CC_PROF(slot) do { if (prof && blockIdx.x == 0 && tid == 0) { const long long tn = clock64(); prof[slot] += tn - tprev; tprev = tn; } } while (0)
   for (int j0 = 0; j0 < n; j0 += CC_B) {
     const int jb = min(CC_B, n - j0);
-    // ---- diagonal block: register-resident right-looking factorisation. Thread (ty,tx) of the 16x16 layout owns the
-    // 4x4 entries (ty+16a, tx+16b); per pivot the owners publish column j through shared memory (double-buffered:
-    // one barrier per pivot), everybody applies the rank-1 update to its registers.
-    {
-      const int ty = tid >> 4, tx = tid & 15;
-      double a[4][4];
-#pragma unroll
-      for (int aa = 0; aa < 4; ++aa)
-#pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-          const int r = ty + 16 * aa, c = tx + 16 * bb;
-          a[aa][bb] = (r < jb && c <= r) ? S[(size_t)(j0 + r) * n + j0 + c] : (r == c ? 1.0 : 0.0);
-        }
-      double* colbuf = D;   // [2][64]
-#pragma unroll
-      for (int bj = 0; bj < 4; ++bj) {
-        for (int jj = 0; jj < 16; ++jj) {
-          const int j = 16 * bj + jj;
-          if (j >= jb) break;
-          double* col = colbuf + (j & 1) * 64;
-          if (tx == jj) {
-#pragma unroll
-            for (int aa = 0; aa < 4; ++aa) col[ty + 16 * aa] = a[aa][bj];
-          }
-          __syncthreads();
-          const double d = col[j];
-          const bool bad = !(d > 0.0) || !(d < DBL_MAX);
-          const double inv = bad ? 1.0 : rsqrt(d);
-          if (bad && tid == 0 && blockIdx.x == 0) atomicExch(fail, 1);
-          double ri[4], ci[4];
-#pragma unroll
-          for (int aa = 0; aa < 4; ++aa) ri[aa] = col[ty + 16 * aa] * inv;
-#pragma unroll
-          for (int bb = 0; bb < 4; ++bb) ci[bb] = col[tx + 16 * bb] * inv;
-#pragma unroll
-          for (int aa = 0; aa < 4; ++aa)
-#pragma unroll
-            for (int bb = 0; bb < 4; ++bb) {
-              const int c = tx + 16 * bb;
-              if (c > j) a[aa][bb] -= ri[aa] * ci[bb];
+    // ---- diagonal block in shared memory, factored in 8-wide sub-panels: (a) all threads apply the previous columns
+    // to the sub-panel, (b) every row-thread factors the 8x8 diagonal sub-block redundantly in registers (no barrier
+    // inside the 8 dependent pivots) and solves its own row of the sub-panel.
+    for (int e = tid; e < CC_B * CC_B; e += CC_THREADS) {
+      const int r = e >> 6, c = e & 63;
+      D[r * CC_DL + c] = (r < jb && c <= r) ? S[(size_t)(j0 + r) * n + j0 + c] : (r == c ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    for (int c0 = 0; c0 < jb; c0 += 8) {
+      if (c0 > 0) {
+        for (int e = tid; e < (CC_B - c0) * 8; e += CC_THREADS) {
+          const int i = c0 + (e >> 3), c = c0 + (e & 7);
+          if (c <= i) {
+            double s0 = D[i * CC_DL + c], s1 = 0.0;
+            for (int k = 0; k < c0; k += 2) {
+              s0 -= Lm[i * CC_DL + k] * Lm[c * CC_DL + k];
+              s1 -= Lm[i * CC_DL + k + 1] * Lm[c * CC_DL + k + 1];
             }
-          if (tx == jj) {
-#pragma unroll
-            for (int aa = 0; aa < 4; ++aa) { a[aa][bj] = ri[aa]; Lm[(ty + 16 * aa) * CC_DL + j] = ri[aa]; }
+            D[i * CC_DL + c] = s0 + s1;
           }
-          if (tid == 0) invd[j] = inv;
+        }
+        __syncthreads();
+      }
+      if (tid < CC_B - c0) {
+        const int i = c0 + tid;
+        double l[8][8], inv[8], x[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int c = 0; c <= r; ++c) l[r][c] = D[(c0 + r) * CC_DL + c0 + c];
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          double d = l[j][j];
+#pragma unroll
+          for (int k = 0; k < j; ++k) d -= l[j][k] * l[j][k];
+          const bool b = !(d > 0.0) || !(d < DBL_MAX);
+          bad = bad || b;
+          inv[j] = b ? 1.0 : rsqrt(d);
+          l[j][j] = d * inv[j];
+#pragma unroll
+          for (int r = j + 1; r < 8; ++r) {
+            double t = l[r][j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) t -= l[r][k] * l[j][k];
+            l[r][j] = t * inv[j];
+          }
+        }
+        if (bad && tid == 0 && blockIdx.x == 0) atomicExch(fail, 1);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          double t = D[i * CC_DL + c0 + c];
+#pragma unroll
+          for (int k = 0; k < c; ++k) t -= x[k] * l[c][k];
+          x[c] = t * inv[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) Lm[i * CC_DL + c0 + c] = x[c];
+        if (tid == 0) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) invd[c0 + c] = inv[c];
         }
       }
       __syncthreads();
@@ -777,10 +791,20 @@ __global__ void __launch_bounds__(CC_THREADS) k_chol_coop(double* __restrict__ S
       const int tj = rem;
       const int row0 = base + ti * CC_B, col0 = base + tj * CC_B;
       __syncthreads();
-      for (int e = tid; e < CC_B * CC_B; e += CC_THREADS) {
-        const int r = e >> 6, c = e & 63;
-        Pa[r * CC_LD + c] = (row0 + r <= n && c < jb) ? S[(size_t)(row0 + r) * n + j0 + c] : 0.0;
-        Pb[r * CC_LD + c] = (col0 + r < n && c < jb) ? S[(size_t)(col0 + r) * n + j0 + c] : 0.0;
+      {
+        double va[16], vb[16];
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          const int e = tid + it * CC_THREADS, r = e >> 6, c = e & 63;
+          va[it] = (row0 + r <= n && c < jb) ? S[(size_t)(row0 + r) * n + j0 + c] : 0.0;
+          vb[it] = (col0 + r < n && c < jb) ? S[(size_t)(col0 + r) * n + j0 + c] : 0.0;
+        }
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          const int e = tid + it * CC_THREADS, r = e >> 6, c = e & 63;
+          Pa[r * CC_LD + c] = va[it];
+          Pb[r * CC_LD + c] = vb[it];
+        }
       }
       __syncthreads();
       const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;
@@ -801,15 +825,27 @@ __global__ void __launch_bounds__(CC_THREADS) k_chol_coop(double* __restrict__ S
 #pragma unroll
           for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
       }
+      {
+        double cur[4][2][2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
+          for (int j = 0; j < 2; ++j)
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int gr = row0 + wm + 8 * i + g, gc = col0 + wn + 8 * j + 2 * q + h;
-            if (gr <= n && gc < n && gc <= gr) S[(size_t)gr * n + gc] -= acc[i][j][h];
-          }
+            for (int h = 0; h < 2; ++h) {
+              const int gr = row0 + wm + 8 * i + g, gc = col0 + wn + 8 * j + 2 * q + h;
+              cur[i][j][h] = (gr <= n && gc < n && gc <= gr) ? S[(size_t)gr * n + gc] : 0.0;
+            }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int gr = row0 + wm + 8 * i + g, gc = col0 + wn + 8 * j + 2 * q + h;
+              if (gr <= n && gc < n && gc <= gr) S[(size_t)gr * n + gc] = cur[i][j][h] - acc[i][j][h];
+            }
+      }
     }
     CC_PROF(3);
     __threadfence();
@@ -826,10 +862,12 @@ __global__ void __launch_bounds__(CC_THREADS) k_chol_coop(double* __restrict__ S
     const int jb = min(CC_B, n - j0);
     for (int e = tid; e < jb * jb; e += CC_THREADS) { const int r = e / jb, c = e % jb; Lm[r * CC_DL + c] = (c <= r) ? S[(size_t)(j0 + r) * n + j0 + c] : 0.0; }
     __syncthreads();
+    if (tid < jb) invd[tid] = 1.0 / Lm[tid * CC_DL + tid];
+    __syncthreads();
     if (warp == 0) {
       double a0 = (lane < jb) ? y[j0 + lane] : 0.0, a1 = (lane + 32 < jb) ? y[j0 + lane + 32] : 0.0;
       for (int j = jb - 1; j >= 0; --j) {
-        const double zj = __shfl_sync(0xffffffffu, (j < 32) ? a0 : a1, j & 31) / Lm[j * CC_DL + j];
+        const double zj = __shfl_sync(0xffffffffu, (j < 32) ? a0 : a1, j & 31) * invd[j];
         if (lane == (j & 31)) { if (j < 32) a0 = zj; else a1 = zj; }
         if (lane < j) a0 -= zj * Lm[j * CC_DL + lane];
         if (lane + 32 < j) a1 -= zj * Lm[j * CC_DL + lane + 32];
@@ -839,17 +877,18 @@ __global__ void __launch_bounds__(CC_THREADS) k_chol_coop(double* __restrict__ S
     }
     __syncthreads();
     for (int i = tid; i < j0; i += CC_THREADS) {
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int k = 0;
-#pragma unroll 4
-      for (; k + 4 <= jb; k += 4) {
-        s0 += S[(size_t)(j0 + k) * n + i] * y[j0 + k];
-        s1 += S[(size_t)(j0 + k + 1) * n + i] * y[j0 + k + 1];
-        s2 += S[(size_t)(j0 + k + 2) * n + i] * y[j0 + k + 2];
-        s3 += S[(size_t)(j0 + k + 3) * n + i] * y[j0 + k + 3];
+      double v[16], s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int kb = 0; kb < CC_B; kb += 16) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = (kb + k < jb) ? S[(size_t)(j0 + kb + k) * n + i] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+          if (kb + k < jb) s0 += v[k] * y[j0 + kb + k];
+          if (kb + k + 1 < jb) s1 += v[k + 1] * y[j0 + kb + k + 1];
+        }
       }
-      for (; k < jb; ++k) s0 += S[(size_t)(j0 + k) * n + i] * y[j0 + k];
-      y[i] -= (s0 + s1) + (s2 + s3);
+      y[i] -= s0 + s1;
     }
     __syncthreads();
   }
