@@ -8,6 +8,8 @@
 // There is no CPU fallback: every entry point fails with MCBA_ERR_CUDA when no sm_100 device is usable.
 #include "../../include/mcba.h"
 #include "mcba_kernels.cuh"
+#include "mcba_lm.cuh"
+#include "mcba_batched.cuh"
 
 #include <dlfcn.h>
 #include <algorithm>
@@ -83,6 +85,12 @@ struct Handle {
   int syrk_nt = 0, syrk_tiles = 0, syrk_nsplit = 0; int64_t syrk_rows_per_split = 0;
   int chol_grid = 1, n_sm = 148;
   long long* d_chol_prof = nullptr;
+  // batched independent problems (config 5)
+  bool batched = false;
+  const uint8_t* obs_gate = nullptr;
+  int* d_cam_ptr = nullptr; LmState* d_lm = nullptr; uint8_t *d_gate_jac = nullptr, *d_active = nullptr;
+  int *d_cam_fail = nullptr, *d_n_active = nullptr; double *d_cam_sc = nullptr, *d_cam_cost = nullptr;
+  std::vector<int> h_cam_ptr;
   // parameters: two copies (current / candidate), swapped on acceptance
   double *d_cam_pose[2] = {nullptr, nullptr}, *d_pose[2] = {nullptr, nullptr}, *d_board[2] = {nullptr, nullptr},
          *d_intr[2] = {nullptr, nullptr};
@@ -92,11 +100,9 @@ struct Handle {
   int rank = 0, n_ranks = 1; nccl_comm_t comm = nullptr;
   // LM state
   mcba_options opt;
-  bool solving = false, done = false;
-  double radius = 0, decrease_factor = 2, x_cost = 0, x_norm = 0, grad_max = 0, minimum_cost = 0, cand_cost = 0;
-  bool reuse_diagonal = false, at_least_one_success = false, have_scale = false;
-  int num_consecutive_invalid = 0, termination = MCBA_NO_CONVERGENCE;
-  mcba_trace_row it;
+  bool solving = false, have_scale = false;
+  LmState lm;
+  double ev_cost = 0, ev_x_norm = 0, ev_grad_max = 0;   // outputs of the last eval_jacobian
   mcba_summary summ;
   std::vector<mcba_trace_row> trace;
   int64_t n_obs_global = 0;
@@ -160,7 +166,31 @@ static StageDims stage_dims(int stage) {
     case 5: { constexpr int ST = 5; __VA_ARGS__; } break; \
   }
 
+static int setup_batched(Handle* H) {
+  H->stage = 1; H->K = Cols<1>::K; H->NT = Cols<1>::NT; H->NE = PairRec<1>::NE;
+  H->Wc = 9; H->Wb = 0; H->n_f = 9 * H->n_cam; H->ldz = 16;
+  const size_t np = H->n_pose, nc = H->n_cam;
+  H->h_cam_ptr.assign(nc + 1, 0);
+  for (int b = 0; b < H->nb; ++b) H->h_cam_ptr[H->h_bobs_cam[b] + 1] = b + 1;
+  for (size_t c = 0; c < nc; ++c) H->h_cam_ptr[c + 1] = std::max(H->h_cam_ptr[c + 1], H->h_cam_ptr[c]);
+  if (dalloc(H, &H->d_cam_ptr, nc + 1)) return MCBA_ERR_CUDA;
+  CU(cudaMemcpy(H->d_cam_ptr, H->h_cam_ptr.data(), (nc + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  if (dalloc(H, &H->d_brec, (size_t)H->nb * B_REC) || dalloc(H, &H->d_cost_bobs, (size_t)H->nb)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_L, np * 36) || dalloc(H, &H->d_Z, np * 60) || dalloc(H, &H->d_part_e, np * 4)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_scale_e, np * 6) || dalloc(H, &H->d_diag_e, np * 6)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_scale_f, nc * 9) || dalloc(H, &H->d_diag_f, nc * 9) || dalloc(H, &H->d_zf, nc * 9)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_FF, nc * 81) || dalloc(H, &H->d_gf, nc * 9)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_cam_sc, nc * BC_N) || dalloc(H, &H->d_cam_cost, nc)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_lm, nc) || dalloc(H, &H->d_gate_jac, nc) || dalloc(H, &H->d_active, nc)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_cam_fail, nc) || dalloc(H, &H->d_n_active, (size_t)1)) return MCBA_ERR_CUDA;
+  CU(cudaMemset(H->d_cam_fail, 0, nc * sizeof(int)));
+  const int sm = OBS_WARPS * (CTX_SIZE + Cols<1>::NC * TS) * 8;
+  CU(cudaFuncSetAttribute(k_observations<1, MODE_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  return MCBA_OK;
+}
+
 static int setup_stage(Handle* H, int stage) {
+  if (H->batched) return setup_batched(H);
   const StageDims sd = stage_dims(stage);
   if (sd.K == 0) { H->err = "stage must be 1..5"; return MCBA_ERR_INVALID; }
   if (sd.board && H->n_board <= 0) { H->err = "stage needs board blocks but n_board == 0"; return MCBA_ERR_INVALID; }
@@ -218,7 +248,7 @@ static int setup_stage(Handle* H, int stage) {
   H->have_scale = false;
   // opt in to > 48 KB dynamic shared memory
   DISPATCH_STAGE(stage, {
-    const int sm = OBS_WARPS * (CTX_SIZE + Cols<ST>::NBLK * 8 * TS) * 8;
+    const int sm = OBS_WARPS * (CTX_SIZE + Cols<ST>::NC * TS) * 8;
     CU(cudaFuncSetAttribute(k_observations<ST, MODE_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     CU(cudaFuncSetAttribute(k_observations<ST, MODE_FROM_J>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     CU(cudaFuncSetAttribute(k_eblock_assemble<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * H->ldz * 8));
@@ -250,7 +280,7 @@ static ObsArgs obs_args(Handle* H, int which, double huber_a) {
   a.prep_cam = H->d_prep_cam; a.prep_pose = H->d_prep_pose; a.prep_board = H->d_prep_board; a.intr = H->d_intr[which];
   a.cam_model = H->d_cam_model; a.cam_is_ref = H->d_cam_is_ref; a.board_is_ref = H->d_board_is_ref;
   a.huber_a = huber_a; a.nb = H->nb; a.brec = H->d_brec; a.cost_bobs = H->d_cost_bobs;
-  a.jmat = H->d_jmat; a.resmat = H->d_resmat; a.npad = H->npad;
+  a.jmat = H->d_jmat; a.resmat = H->d_resmat; a.npad = H->npad; a.gate = H->obs_gate;
   return a;
 }
 
@@ -274,8 +304,8 @@ template <int MODE> static int launch_obs(Handle* H, int which, double huber_a) 
   ObsArgs a = obs_args(H, which, huber_a);
   DISPATCH_STAGE(H->stage, {
     constexpr bool ACC = (MODE == MODE_FUSED || MODE == MODE_FROM_J);
-    const int sm = OBS_WARPS * (CTX_SIZE + (ACC ? Cols<ST>::NBLK * 8 * TS : 0)) * 8;
-    const int grid = grid_for(H->nb, ACC ? std::max(1, (227 * 1024) / (sm + 1024)) : 8);
+    const int sm = OBS_WARPS * (CTX_SIZE + (ACC ? Cols<ST>::NC * TS : 0)) * 8;
+    const int grid = grid_for(H->nb, ACC ? std::min(4, std::max(1, (227 * 1024) / (sm + 1024))) : 8);
     ++H->n_launches;
     k_observations<ST, MODE><<<grid, OBS_WARPS * 32, sm, H->stream>>>(a);
   });
@@ -376,9 +406,9 @@ static int eval_jacobian(Handle* H, bool first) {
     k_scale_diag<<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_Hoo, H->n_pose, H->d_FF, H->n_f, 1, H->opt.jacobi_scaling, H->opt.min_lm_diagonal, H->opt.max_lm_diagonal, H->d_scale_e, H->d_scale_f, H->d_diag_e, H->d_diag_f);
     CHECK_LAUNCH();
     H->have_scale = true;
-    H->reuse_diagonal = true;   // the diagonal was just computed from this Jacobian
+    H->lm.reuse_diagonal = 1;   // the diagonal was just computed from this Jacobian
   } else {
-    H->reuse_diagonal = false;
+    H->lm.reuse_diagonal = 0;
   }
   std::vector<double> hs;
   if ((rc = gather_scalars(H, H->d_scalars, SC_N, hs))) return rc;
@@ -390,9 +420,9 @@ static int eval_jacobian(Handle* H, bool first) {
   }
   if (H->n_pose == 0 && H->n_ranks == 1) { xe2 = 0; }
   gmax = std::max(gmax, hs[SC_F0 + 1]);
-  H->x_cost = cost;
-  H->x_norm = std::sqrt(xe2 + hs[SC_F0 + 0]);
-  H->grad_max = gmax;
+  H->ev_cost = cost;
+  H->ev_x_norm = std::sqrt(xe2 + hs[SC_F0 + 0]);
+  H->ev_grad_max = gmax;
   if (!std::isfinite(cost)) return MCBA_ERR_NUMERIC;
   return MCBA_OK;
 }
@@ -413,23 +443,22 @@ static int cholesky_reduced(Handle* H) {
 
 // LevenbergMarquardtStrategy::ComputeStep + SchurComplementSolver + candidate point + candidate cost.
 // Outputs (host): step validity ingredients.
-struct StepOut { double mcc, step_norm, cand_norm, cand_cost; bool solver_ok; };
-static int compute_step(Handle* H, StepOut* out) {
+static int compute_step(Handle* H, LmStep* out) {
   int rc;
   const StageDims sd = stage_dims(H->stage);
   CU(cudaMemsetAsync(H->d_fail, 0, sizeof(int), H->stream));
-  if (!H->reuse_diagonal) {
+  if (!H->lm.reuse_diagonal) {
     Timed t(H, KF_REDUCE);
     const int n = H->n_pose * 6 + H->n_f;
     ++H->n_launches;
     k_scale_diag<<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_Hoo, H->n_pose, H->d_FF, H->n_f, 0, H->opt.jacobi_scaling, H->opt.min_lm_diagonal, H->opt.max_lm_diagonal, H->d_scale_e, H->d_scale_f, H->d_diag_e, H->d_diag_f);
     CHECK_LAUNCH();
   }
-  H->reuse_diagonal = true;
+  H->lm.reuse_diagonal = 1;
   if (H->n_pose > 0) {
     Timed t(H, KF_EFACTOR);
     ++H->n_launches;
-    k_eblock_factor<<<H->n_pose, 128, 0, H->stream>>>(H->d_Hoo, H->d_Wt, H->d_scale_e, H->d_scale_f, H->d_diag_e, H->radius, H->n_f, H->ldz, H->d_L, H->d_Z, H->d_fail);
+    k_eblock_factor<<<H->n_pose, 128, 0, H->stream>>>(H->d_Hoo, H->d_Wt, H->d_scale_e, H->d_scale_f, H->d_diag_e, H->lm.radius, H->n_f, H->ldz, H->d_L, H->d_Z, H->d_fail);
     CHECK_LAUNCH();
   }
   {
@@ -446,7 +475,7 @@ static int compute_step(Handle* H, StepOut* out) {
     Timed t(H, KF_REDUCED);
     const int n = H->n_f * H->n_f + H->n_f;
     ++H->n_launches;
-    k_build_reduced<<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_FF, H->d_gf, H->d_ZtZ, H->d_scale_f, H->d_diag_f, H->radius, H->n_f, H->ldz, H->d_S, H->d_rhs);
+    k_build_reduced<<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_FF, H->d_gf, H->d_ZtZ, H->d_scale_f, H->d_diag_f, H->lm.radius, H->n_f, H->ldz, H->d_S, H->d_rhs);
     CHECK_LAUNCH();
   }
   if ((rc = cholesky_reduced(H))) return rc;
@@ -455,7 +484,7 @@ static int compute_step(Handle* H, StepOut* out) {
     Timed t(H, KF_BACKSUBST);
     if (H->n_pose > 0) {
       ++H->n_launches;
-      k_backsubst<<<(H->n_pose + 7) / 8, 256, 0, H->stream>>>(H->d_Z, H->d_L, H->d_zf, H->d_scale_e, H->d_diag_e, H->radius, H->d_pose[H->cur], H->n_pose, H->n_f, H->ldz, H->d_pose[cand], H->d_part_e);
+      k_backsubst<<<(H->n_pose + 7) / 8, 256, 0, H->stream>>>(H->d_Z, H->d_L, H->d_zf, H->d_scale_e, H->d_diag_e, H->lm.radius, H->d_pose[H->cur], H->n_pose, H->n_f, H->ldz, H->d_pose[cand], H->d_part_e);
     }
     ++H->n_launches;
     k_ffz<<<(H->n_f + 7) / 8, 256, 0, H->stream>>>(H->d_FF, H->d_scale_f, H->d_zf, H->n_f, H->d_hz);
@@ -485,22 +514,8 @@ static int compute_step(Handle* H, StepOut* out) {
   out->step_norm = std::sqrt(sn + f[2]);
   out->cand_norm = std::sqrt(xn + f[3]);
   out->cand_cost = std::isfinite(cost) ? cost : std::numeric_limits<double>::max();
-  out->solver_ok = (h_fail == 0.0) && std::isfinite(out->mcc) && std::isfinite(out->step_norm);
+  out->solver_ok = ((h_fail == 0.0) && std::isfinite(out->mcc) && std::isfinite(out->step_norm)) ? 1 : 0;
   return MCBA_OK;
-}
-
-static void record_iteration(Handle* H) {
-  if (H->it.step_is_successful) {
-    ++H->summ.num_successful_steps;
-    if (H->x_cost < H->minimum_cost) H->minimum_cost = H->x_cost;
-  } else {
-    ++H->summ.num_unsuccessful_steps;
-  }
-  H->it.trust_region_radius = H->radius;
-  H->trace.push_back(H->it);
-  if (H->opt.verbose && H->rank == 0)
-    std::printf("%4d % .6e % .2e % .2e % .2e % .2e % .2e\n", H->it.iteration, H->it.cost, H->it.cost_change,
-                H->it.gradient_max_norm, H->it.step_norm, H->it.relative_decrease, H->it.trust_region_radius);
 }
 
 static int upload_params(Handle* H, const mcba_params* p) {
@@ -593,6 +608,8 @@ void mcba_destroy(void* h) {
   dfree(&H->d_syrk_partial); dfree(&H->d_pair_partial); dfree(&H->d_pair_rec); dfree(&H->d_part_e);
   dfree(&H->d_red_scratch); dfree(&H->d_scalars); dfree(&H->d_gather); dfree(&H->d_fail);
   dfree(&H->d_jmat); dfree(&H->d_resmat);
+  dfree(&H->d_cam_ptr); dfree(&H->d_lm); dfree(&H->d_gate_jac); dfree(&H->d_active); dfree(&H->d_cam_fail); dfree(&H->d_n_active);
+  dfree(&H->d_cam_sc); dfree(&H->d_cam_cost);
   for (int w = 0; w < 2; ++w) { dfree(&H->d_cam_pose[w]); dfree(&H->d_pose[w]); dfree(&H->d_board[w]); dfree(&H->d_intr[w]); }
   dfree(&H->d_prep_cam); dfree(&H->d_prep_pose); dfree(&H->d_prep_board);
   if (H->stream) cudaStreamDestroy(H->stream);
@@ -605,7 +622,14 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   *handle = H;
   if (!P || P->n_obs < 0 || P->n_bobs < 0 || P->n_cam <= 0 || P->n_pose < 0) { H->err = "bad problem sizes"; return MCBA_ERR_INVALID; }
   if (P->n_obs >= (int64_t)1 << 31 || P->n_bobs >= (int64_t)1 << 30) { H->err = "shard too large for 32-bit indices: split across handles"; return MCBA_ERR_INVALID; }
-  if (P->cam_problem || P->n_problems > 1) { H->err = "batched problems are solved through mcba_solve_batched (not built in this round)"; return MCBA_ERR_INVALID; }
+  if (P->cam_problem || P->n_problems > 1) {
+    // batched independent problems: stage 1, one problem per camera, one board observation per e-block, camera-major
+    bool ok = P->stage == 1 && P->cam_problem && P->n_problems == P->n_cam && P->n_pose == P->n_bobs;
+    for (int c = 0; ok && c < P->n_cam; ++c) ok = P->cam_problem[c] == c;
+    for (int64_t b = 0; ok && b < P->n_bobs; ++b) ok = P->bobs_pose[b] == b && (b == 0 || P->bobs_cam[b] >= P->bobs_cam[b - 1]);
+    if (!ok) { H->err = "batched mode needs stage 1, cam_problem[c] == c, bobs_pose[b] == b and bobs sorted by camera"; return MCBA_ERR_INVALID; }
+    H->batched = true;
+  }
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { H->err = "no CUDA device: libmcba has no CPU fallback"; return MCBA_ERR_CUDA; }
   cudaDeviceProp prop;
@@ -672,6 +696,7 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
 
 int mcba_set_stage(void* h, int stage) {
   Handle* H = (Handle*)h; if (!H) return MCBA_ERR_INVALID;
+  if (H->batched) { H->err = "batched handles are stage 1 only"; return MCBA_ERR_INVALID; }
   CU(cudaSetDevice(H->device));
   if (stage == H->stage) return MCBA_OK;
   const int rc = setup_stage(H, stage);
@@ -711,75 +736,47 @@ int mcba_comm_init(void* h, int rank, int n_ranks, const void* uid) {
 
 int mcba_solve_begin(void* h, const mcba_params* p, const mcba_options* opt) {
   Handle* H = (Handle*)h; if (!H) return MCBA_ERR_INVALID;
+  if (H->batched) { H->err = "batched handle: use mcba_solve_batched"; return MCBA_ERR_INVALID; }
   CU(cudaSetDevice(H->device));
   mcba_options o; if (opt) o = *opt; else mcba_default_options(&o);
   H->opt = o;
   int rc;
   if ((rc = upload_params(H, p))) return rc;
-  H->solving = true; H->done = false; H->trace.clear();
-  std::memset(&H->summ, 0, sizeof(H->summ)); std::memset(&H->it, 0, sizeof(H->it));
-  H->radius = o.initial_trust_region_radius; H->decrease_factor = 2.0; H->reuse_diagonal = false;
-  H->num_consecutive_invalid = 0; H->at_least_one_success = false; H->have_scale = false;
-  H->minimum_cost = std::numeric_limits<double>::max(); H->termination = MCBA_NO_CONVERGENCE;
-  // IterationZero
-  rc = eval_jacobian(H, true);
-  if (rc == MCBA_ERR_NUMERIC) { H->err = "Initial residual and Jacobian evaluation failed."; H->summ.termination = MCBA_FAILURE; H->termination = MCBA_FAILURE; H->done = true; return rc; }
+  H->solving = true; H->trace.clear(); H->have_scale = false;
+  std::memset(&H->summ, 0, sizeof(H->summ));
+  lm_init(H->lm, o);
+  rc = eval_jacobian(H, true);   // IterationZero
+  if (rc == MCBA_ERR_NUMERIC) { H->err = "Initial residual and Jacobian evaluation failed."; H->summ.termination = MCBA_FAILURE; H->lm.termination = MCBA_FAILURE; H->lm.done = 1; return rc; }
   if (rc) return rc;
-  H->summ.initial_cost = H->x_cost;
-  H->it.iteration = 0; H->it.step_is_valid = 1; H->it.step_is_successful = 1; H->it.cost = H->x_cost; H->it.gradient_max_norm = H->grad_max;
+  lm_iteration_zero(H->lm, H->ev_cost, H->ev_grad_max, H->ev_x_norm);
+  H->summ.initial_cost = H->lm.initial_cost;
   return MCBA_OK;
 }
 
-// One pass of TrustRegionMinimizer's while loop: FinalizeIterationAndCheckIfMinimizerCanContinue for the
-// previous iteration, then one trust-region iteration. Returns 1 to continue, 0 when terminated.
+// One pass of TrustRegionMinimizer's while loop (decision rules in mcba_lm.cuh): FinalizeIterationAndCheck... for the
+// iteration in flight, then one trust-region iteration. Returns 1 to continue, 0 when terminated.
 int mcba_solve_step(void* h) {
   Handle* H = (Handle*)h; if (!H || !H->solving) return MCBA_ERR_INVALID;
-  if (H->done) return 0;
+  if (H->lm.done) return 0;
   CU(cudaSetDevice(H->device));
-  const mcba_options& o = H->opt;
-  record_iteration(H);
-  if (H->it.iteration >= o.max_num_iterations) { H->termination = MCBA_NO_CONVERGENCE; H->done = true; return 0; }
-  if (H->it.step_is_successful && H->it.gradient_max_norm <= o.gradient_tolerance) { H->termination = MCBA_CONVERGENCE; H->done = true; return 0; }
-  if (H->it.trust_region_radius <= o.min_trust_region_radius) { H->termination = MCBA_CONVERGENCE; H->done = true; return 0; }
-  const double prev_grad_max = H->it.gradient_max_norm;
-  const int iter = H->it.iteration + 1;
-  std::memset(&H->it, 0, sizeof(H->it));
-  H->it.iteration = iter;
-  StepOut so;
+  mcba_trace_row row;
+  const int cont = lm_finalize(H->lm, H->opt, &row);
+  H->trace.push_back(row);
+  if (H->opt.verbose && H->rank == 0)
+    std::printf("%4d % .6e % .2e % .2e % .2e % .2e % .2e\n", row.iteration, row.cost, row.cost_change, row.gradient_max_norm,
+                row.step_norm, row.relative_decrease, row.trust_region_radius);
+  if (!cont) return 0;
+  LmStep so;
   int rc = compute_step(H, &so);
   if (rc) return rc;
-  H->it.step_is_valid = so.solver_ok && so.mcc > 0.0;
-  if (!H->it.step_is_valid) {   // HandleInvalidStep
-    if (++H->num_consecutive_invalid >= o.max_num_consecutive_invalid_steps) { H->termination = MCBA_FAILURE; H->done = true; return 0; }
-    H->radius /= H->decrease_factor; H->decrease_factor *= 2.0; H->reuse_diagonal = true;
-    H->it.cost = H->x_cost; H->it.gradient_max_norm = prev_grad_max;
-    return 1;
-  }
-  H->num_consecutive_invalid = 0;
-  if (H->at_least_one_success) {
-    H->it.step_norm = so.step_norm;   // ParameterToleranceReached
-    if (so.step_norm <= o.parameter_tolerance * (H->x_norm + o.parameter_tolerance)) { H->termination = MCBA_CONVERGENCE; H->done = true; return 0; }
-    H->it.cost_change = H->x_cost - so.cand_cost;   // FunctionToleranceReached
-    if (std::fabs(H->it.cost_change) <= o.function_tolerance * H->x_cost) { H->termination = MCBA_CONVERGENCE; H->done = true; return 0; }
-  }
-  double rel;
-  if (so.cand_cost >= std::numeric_limits<double>::max()) rel = std::numeric_limits<double>::lowest();
-  else rel = (H->x_cost - so.cand_cost) / so.mcc;   // monotonic step evaluator: reference cost == current cost
-  H->it.relative_decrease = rel;
-  if (rel > o.min_relative_decrease) {   // HandleSuccessfulStep
-    H->at_least_one_success = true;
+  const int d = lm_decide(H->lm, H->opt, so);
+  if (d == LM_TERMINATED) return 0;
+  if (d == LM_ACCEPT) {   // HandleSuccessfulStep
     H->cur = 1 - H->cur;
-    H->x_norm = so.cand_norm;
     rc = eval_jacobian(H, false);
-    if (rc == MCBA_ERR_NUMERIC) { H->termination = MCBA_FAILURE; H->done = true; return 0; }
+    if (rc == MCBA_ERR_NUMERIC) { H->lm.termination = MCBA_FAILURE; H->lm.done = 1; return 0; }
     if (rc) return rc;
-    H->it.step_is_successful = 1; H->it.cost = H->x_cost; H->it.gradient_max_norm = H->grad_max;
-    H->radius = H->radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
-    H->radius = std::min(o.max_trust_region_radius, H->radius);
-    H->decrease_factor = 2.0;
-  } else {
-    H->it.step_is_successful = 0; H->it.cost = so.cand_cost; H->it.gradient_max_norm = prev_grad_max;
-    H->radius /= H->decrease_factor; H->decrease_factor *= 2.0; H->reuse_diagonal = true;
+    lm_accepted_eval(H->lm, H->opt, H->ev_cost, H->ev_grad_max);
   }
   return 1;
 }
@@ -788,9 +785,10 @@ int mcba_solve_end(void* h, mcba_params* p, mcba_summary* summary) {
   Handle* H = (Handle*)h; if (!H || !H->solving) return MCBA_ERR_INVALID;
   CU(cudaSetDevice(H->device));
   int rc;
-  H->summ.termination = H->termination;
-  H->summ.num_iterations = (int)H->trace.size();
-  H->summ.final_cost = H->minimum_cost < std::numeric_limits<double>::max() ? H->minimum_cost : H->x_cost;
+  H->summ.termination = H->lm.termination;
+  H->summ.num_iterations = H->lm.num_recorded;
+  H->summ.num_successful_steps = H->lm.num_successful; H->summ.num_unsuccessful_steps = H->lm.num_unsuccessful;
+  H->summ.final_cost = H->lm.minimum_cost < DBL_MAX ? H->lm.minimum_cost : H->lm.x_cost;
   // unrobustified RMS at the returned parameters: cost pass with the loss disabled
   if ((rc = launch_prep(H, H->cur))) return rc;
   if ((rc = launch_obs<MODE_COST>(H, H->cur, 0.0))) return rc;
@@ -822,10 +820,102 @@ int mcba_solve(void* h, mcba_params* p, const mcba_options* opt, mcba_summary* s
   return rc;
 }
 
-int mcba_solve_batched(void* h, mcba_params*, const mcba_options*, mcba_summary*) {
+// Jacobian phase of the batched driver for the cameras flagged in d_gate_jac
+static int batched_eval(Handle* H, bool first) {
+  int rc;
+  if ((rc = launch_prep(H, 0))) return rc;
+  H->obs_gate = H->d_gate_jac;
+  rc = launch_obs<MODE_FUSED>(H, 0, H->opt.huber_a);
+  H->obs_gate = nullptr;
+  if (rc) return rc;
+  Timed t(H, KF_PAIR);
+  const int nc = H->n_cam, np = H->n_pose;
+  if (first) { ++H->n_launches; k_b_escale<<<(np + 127) / 128, 128, 0, H->stream>>>(H->d_bobs, H->d_gate_jac, H->d_brec, np, H->opt.jacobi_scaling, H->d_scale_e); }
+  ++H->n_launches;
+  k_b_cam_reduce<<<nc, 64, 0, H->stream>>>(H->d_gate_jac, H->d_cam_ptr, H->d_brec, H->d_cost_bobs, H->d_pose[0], H->d_FF, H->d_gf, H->d_cam_sc);
+  ++H->n_launches;
+  k_b_after_eval<<<(nc + 127) / 128, 128, 0, H->stream>>>(H->d_lm, H->opt, H->d_gate_jac, nc, first ? 1 : 0, H->d_FF, H->d_gf, H->d_cam_sc, H->d_intr[0], H->d_scale_f);
+  CHECK_LAUNCH();
+  return MCBA_OK;
+}
+
+// Config 5: all problems advance together; each takes its own trust-region decisions on the device.
+int mcba_solve_batched(void* h, mcba_params* p, const mcba_options* opt, mcba_summary* summaries) {
   Handle* H = (Handle*)h; if (!H) return MCBA_ERR_INVALID;
-  H->err = "mcba_solve_batched: not built in this round";
-  return MCBA_ERR_INVALID;
+  if (!H->batched) { H->err = "not a batched handle (mcba_problem::cam_problem was NULL)"; return MCBA_ERR_INVALID; }
+  CU(cudaSetDevice(H->device));
+  mcba_options o; if (opt) o = *opt; else mcba_default_options(&o);
+  H->opt = o;
+  int rc;
+  if ((rc = upload_params(H, p))) return rc;
+  const int nc = H->n_cam, np = H->n_pose;
+  ++H->n_launches;
+  k_b_init<<<(nc + 127) / 128, 128, 0, H->stream>>>(H->d_lm, o, nc, H->d_gate_jac, H->d_active);
+  CHECK_LAUNCH();
+  if ((rc = batched_eval(H, true))) return rc;
+  for (int64_t guard = 0; guard < (int64_t)o.max_num_iterations * 8 + 64; ++guard) {
+    CU(cudaMemsetAsync(H->d_n_active, 0, sizeof(int), H->stream));
+    ++H->n_launches;
+    k_b_finalize<<<(nc + 127) / 128, 128, 0, H->stream>>>(H->d_lm, o, nc, H->d_active, H->d_n_active);
+    int n_active = 0;
+    CU(cudaMemcpyAsync(&n_active, H->d_n_active, sizeof(int), cudaMemcpyDeviceToHost, H->stream));
+    CU(cudaStreamSynchronize(H->stream));
+    if (n_active == 0) break;
+    {
+      Timed t(H, KF_EFACTOR);
+      ++H->n_launches;
+      k_b_eblock_factor<<<(np + 127) / 128, 128, 0, H->stream>>>(H->d_bobs, H->d_active, H->d_lm, o, H->d_brec, H->d_scale_e, H->d_scale_f, H->d_diag_e, np, H->d_L, H->d_Z, H->d_cam_fail);
+    }
+    {
+      Timed t(H, KF_SYRK);
+      ++H->n_launches;
+      k_b_schur_solve<<<nc, 64, 0, H->stream>>>(H->d_active, H->d_lm, o, H->d_cam_ptr, H->d_FF, H->d_gf, H->d_Z, H->d_scale_f, H->d_diag_f, H->d_intr[0], H->d_intr[1], H->d_zf, H->d_cam_sc, H->d_cam_fail);
+    }
+    {
+      Timed t(H, KF_BACKSUBST);
+      ++H->n_launches;
+      k_b_backsubst<<<(np + 127) / 128, 128, 0, H->stream>>>(H->d_bobs, H->d_active, H->d_lm, H->d_Z, H->d_L, H->d_zf, H->d_scale_e, H->d_diag_e, H->d_pose[0], np, H->d_pose[1], H->d_part_e);
+    }
+    CHECK_LAUNCH();
+    if ((rc = launch_prep(H, 1))) return rc;
+    H->obs_gate = H->d_active;
+    rc = launch_obs<MODE_COST>(H, 1, o.huber_a);
+    H->obs_gate = nullptr;
+    if (rc) return rc;
+    {
+      Timed t(H, KF_REDUCE);
+      ++H->n_launches;
+      k_b_decide<<<nc, 32, 0, H->stream>>>(H->d_active, H->d_lm, o, H->d_cam_ptr, H->d_part_e, H->d_cost_bobs, H->d_cam_sc, H->d_cam_fail, H->d_gate_jac);
+      ++H->n_launches;
+      k_b_commit<<<(np + nc + 127) / 128, 128, 0, H->stream>>>(H->d_bobs, H->d_gate_jac, np, nc, H->d_pose[1], H->d_pose[0], H->d_intr[1], H->d_intr[0]);
+    }
+    CHECK_LAUNCH();
+    if ((rc = batched_eval(H, false))) return rc;
+  }
+  // per-problem RMS of the unrobustified residuals at the returned parameters
+  if ((rc = launch_prep(H, 0))) return rc;
+  if ((rc = launch_obs<MODE_COST>(H, 0, 0.0))) return rc;
+  ++H->n_launches;
+  k_b_cam_cost<<<(nc + 127) / 128, 128, 0, H->stream>>>(H->d_cam_ptr, H->d_cost_bobs, nc, H->d_cam_cost);
+  CHECK_LAUNCH();
+  std::vector<LmState> lm(nc); std::vector<double> cc(nc);
+  CU(cudaMemcpyAsync(lm.data(), H->d_lm, nc * sizeof(LmState), cudaMemcpyDeviceToHost, H->stream));
+  CU(cudaMemcpyAsync(cc.data(), H->d_cam_cost, nc * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+  H->cur = 0;
+  if (p && (rc = download_params(H, p))) return rc;
+  flush_timers(H);
+  if (summaries) {
+    for (int c = 0; c < nc; ++c) {
+      mcba_summary& S = summaries[c];
+      std::memset(&S, 0, sizeof(S));
+      S.termination = lm[c].termination; S.num_successful_steps = lm[c].num_successful; S.num_unsuccessful_steps = lm[c].num_unsuccessful;
+      S.num_iterations = lm[c].num_recorded; S.initial_cost = lm[c].initial_cost;
+      S.final_cost = lm[c].minimum_cost < DBL_MAX ? lm[c].minimum_cost : lm[c].x_cost;
+      const int64_t n_obs_c = H->h_bobs_ptr[H->h_cam_ptr[c + 1]] - H->h_bobs_ptr[H->h_cam_ptr[c]];
+      S.rms_px = std::sqrt(2.0 * cc[c] / (double)std::max<int64_t>(1, n_obs_c));
+    }
+  }
+  return MCBA_OK;
 }
 
 int mcba_eval(void* h, const mcba_params* p, const mcba_options* opt, double* cost, double* residuals, double* jacobian) {

@@ -24,7 +24,8 @@
 
 namespace mcba {
 
-constexpr int TS = 68;            // row stride (doubles) of the per-warp J^T tile: 64 rows + 4 (bank spread)
+constexpr int OBS_PASS = 32;      // corners per warp pass (64 tile rows = 16 DMMA k-steps); 24 (4 CTAs/SM) measured no faster
+constexpr int TS = 2 * OBS_PASS + 4;   // row stride (doubles) of the per-warp J^T tile: 48 rows + 4 (bank spread: TS mod 16 == 4)
 constexpr int OBS_WARPS = 4;      // warps per CTA in the observation kernels
 enum { MODE_FUSED = 0, MODE_MATERIALIZE = 1, MODE_FROM_J = 2, MODE_COST = 3 };
 
@@ -39,6 +40,7 @@ struct ObsArgs {
   double* cost_bobs;                // [nb]
   double* jmat; double* resmat;     // materialised Jacobian blocks (see BlockSink); resmat unused
   int64_t npad;
+  const uint8_t* gate;              // batched problems: per-camera flag, board observations of gated-off cameras are skipped
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -81,11 +83,12 @@ struct BlockSink {
 };
 
 template <int STAGE, int MODE>
-__global__ void __launch_bounds__(OBS_WARPS * 32) k_observations(ObsArgs a) {
+__global__ void __launch_bounds__(OBS_WARPS * 32, (MODE == MODE_FUSED || MODE == MODE_FROM_J) ? 3 : (MODE == MODE_COST ? 8 : 4)) k_observations(ObsArgs a) {
   typedef Cols<STAGE> C;
   typedef StageTraits<STAGE> ST;
   constexpr bool ACC = (MODE == MODE_FUSED || MODE == MODE_FROM_J);
-  constexpr int TILE_DOUBLES = ACC ? C::NBLK * 8 * TS : 0;
+  constexpr int TILE_DOUBLES = ACC ? C::NC * TS : 0;   // only the NC real columns are stored
+  constexpr int PASS = ACC ? OBS_PASS : 32;
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* ctx = smem + warp * (CTX_SIZE + TILE_DOUBLES);
@@ -99,6 +102,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) k_observations(ObsArgs a) {
     const int4 rec = a.bobs[b];
     const int obs_begin = rec.x, obs_end = a.bobs[b + 1].x;
     const int cam = rec.y;
+    if (a.gate && !a.gate[cam]) continue;
     const bool act_c = ST::CAM && !(a.cam_is_ref && a.cam_is_ref[cam]);
     const bool act_b = ST::BOARD && !(a.board_is_ref && a.board_is_ref[rec.w]);
     const int model = a.cam_model[cam];
@@ -120,9 +124,9 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) k_observations(ObsArgs a) {
 #pragma unroll
     for (int t = 0; t < (ACC ? C::NT : 1); ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
     double cost = 0.0;
-    for (int base = obs_begin; base < obs_end; base += 32) {
+    for (int base = obs_begin; base < obs_end; base += PASS) {
       const int i = base + lane;
-      const bool active = i < obs_end;
+      const bool active = lane < PASS && i < obs_end;
       if (active) {
         if (MODE == MODE_FROM_J) {
           const double* blk = a.jmat + (size_t)2 * C::NC * obs_begin;
@@ -146,19 +150,19 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) k_observations(ObsArgs a) {
             cost += obs_jacobian<STAGE>(ctx, act_c, act_b, model, X0, uu, vv, a.huber_a, sink);
           }
         }
-      } else if (ACC) {
+      } else if (ACC && lane < PASS) {
 #pragma unroll
         for (int col = 0; col < C::NC; ++col)
           *reinterpret_cast<double2*>(T + col * TS + 2 * lane) = make_double2(0.0, 0.0);
       }
       if (ACC) {
         __syncwarp();
-        const int nrows = 2 * min(32, obs_end - base);
+        const int nrows = 2 * min(PASS, obs_end - base);
         const int ksteps = (nrows + 3) >> 2;
         for (int ks = 0; ks < ksteps; ++ks) {
           double f[C::NBLK];
 #pragma unroll
-          for (int c = 0; c < C::NBLK; ++c) f[c] = T[(8 * c + g) * TS + 4 * ks + q];
+          for (int c = 0; c < C::NBLK; ++c) f[c] = (8 * c + g < C::NC) ? T[(8 * c + g) * TS + 4 * ks + q] : 0.0;
           int t = 0;
 #pragma unroll
           for (int bi = 0; bi < C::NBLK; ++bi)

@@ -161,3 +161,52 @@ def test_stage4_then_stage5_on_one_handle(oracle, c1):
     assert (s5.num_successful_steps, s5.num_unsuccessful_steps) == (o5.num_successful_steps, o5.num_unsuccessful_steps)
     assert abs(s5.rms_px - o5.rms_px) <= 1e-6
     assert np.abs(pg.intrinsics - po.intrinsics).max() <= 1e-6 * np.abs(po.intrinsics).max()
+
+
+def _camera_subproblem(prob, params, c):
+    """Stage-1 problem of one camera cut out of a batched problem (what the reference solves per camera)."""
+    sel = np.nonzero(prob.bobs_cam == c)[0]
+    b0, b1 = sel[0], sel[-1] + 1
+    o0, o1 = prob.bobs_ptr[b0], prob.bobs_ptr[b1]
+    sub = mcba.Problem(1, prob.u[o0:o1], prob.v[o0:o1], prob.pt_idx[o0:o1], prob.bobs_ptr[b0:b1 + 1] - o0,
+                       np.zeros(b1 - b0), np.arange(b1 - b0), np.zeros(b1 - b0), prob.pts_xyz, prob.cam_model[c:c + 1],
+                       b1 - b0, 0)
+    p = mcba.Params(np.zeros((1, 6)), params.pose[b0:b1], np.zeros((0, 6)), params.intrinsics[c:c + 1])
+    return sub, p, (b0, b1)
+
+
+def test_batched_intrinsics_matches_per_camera_oracle(oracle):
+    """Config 5 shape: independent per-camera intrinsic refinements solved in one batch; every camera must follow the
+    same trajectory as its own single-problem oracle solve (Camera::refineIntrinsicCalibration per camera)."""
+    prob, init, gt = synth.batched_intrinsics_problem(n_cameras=7, n_frames=40, kannala_every=3)
+    pg = init.copy()
+    h = mcba.Handle(prob)
+    summ = h.solve_batched(pg)
+    h.close()
+    assert len(summ) == 7
+    for c in range(7):
+        sub, p, (b0, b1) = _camera_subproblem(prob, init, c)
+        rc, so, to = oracle.solve(sub, p)
+        assert rc == 0
+        s = summ[c]
+        assert (s.termination, s.num_successful_steps, s.num_unsuccessful_steps, s.num_iterations) == \
+               (so.termination, so.num_successful_steps, so.num_unsuccessful_steps, so.num_iterations), c
+        assert abs(s.final_cost - so.final_cost) <= 1e-9 * so.final_cost
+        assert abs(s.rms_px - so.rms_px) <= 1e-6
+        assert np.abs(pg.intrinsics[c] - p.intrinsics[0]).max() <= 1e-6 * np.abs(p.intrinsics[0]).max()
+        assert np.abs(pg.pose[b0:b1] - p.pose).max() <= 1e-6 * max(1.0, np.abs(p.pose).max())
+
+
+def test_batched_problems_terminate_independently(oracle):
+    """One camera starts at its optimum-ish (ground truth), the others far away: iteration counts differ per problem."""
+    prob, init, gt = synth.batched_intrinsics_problem(n_cameras=4, n_frames=30)
+    p0 = init.copy()
+    p0.intrinsics[0] = gt.intrinsics[0]
+    sel = prob.bobs_cam == 0
+    p0.pose[sel] = gt.pose[sel]
+    h = mcba.Handle(prob)
+    summ = h.solve_batched(p0)
+    h.close()
+    its = [s.num_iterations for s in summ]
+    assert its[0] < max(its[1:])
+    assert all(s.termination == 0 for s in summ)
