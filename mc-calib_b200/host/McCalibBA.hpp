@@ -1,0 +1,145 @@
+// McCalibBA.hpp — host-side mirror of the MC-Calib classes that own the bundle-adjustment state, with the
+// reference's refinement entry points re-implemented on top of libmcba (include/mcba.h).
+//
+// Mirrors (names, members and call order; /root/reference/McCalib/include/*.hpp):
+//   Camera.hpp:43-46 (intrinsics_), Board.hpp:36 (pts_3d_), BoardObs.hpp:33-37 (pose_, pts_2d_, charuco_id_),
+//   Object3D.hpp:43-48 (pts_obj_2_board_, relative_board_pose_), Object3DObs.hpp:40-47 (pose_, pts_2d_, pts_id_),
+//   CameraGroupObs.hpp:29-30 (object_pose_), CameraGroup.hpp:40-41 (relative_camera_pose_), Frame.hpp,
+//   McCalib.hpp (Calibration: refineIntrinsicAndPoseAllCam, refineAllObject3D, refineAllCameraGroup,
+//   refineAllCameraGroupAndObjects, refineAllCameraGroupAndObjectsAndIntrinsic, computeAvgReprojectionError).
+// Only what the refinement path reads or writes is mirrored: detection, initialisation, graphs and file I/O of
+// the reference are out of scope. OpenCV types are replaced by plain structs.
+#pragma once
+#include <array>
+#include <map>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace McCalib {
+
+struct Point2f { float x, y; };
+struct Point3f { float x, y, z; };
+typedef std::array<double, 6> Pose6;   // angle-axis (3) || translation (3)
+
+class Board; class BoardObs; class Camera; class Object3D; class Object3DObs; class CameraGroup; class CameraGroupObs; class Frame;
+
+class Board final {
+public:
+  int board_id_ = 0;
+  std::vector<Point3f> pts_3d_;   // (x*sq, y*sq, 0), Board.cpp:66-72
+};
+
+class Camera final {
+public:
+  int cam_idx_ = 0;
+  int distortion_model_ = 0;              // 0 Brown, 1 Kannala
+  std::array<double, 9> intrinsics_{};    // fx fy u0 v0 d4..d8
+  std::map<int, std::weak_ptr<BoardObs>> board_observations_;
+  void refineIntrinsicCalibration(const int nb_iterations);   // Camera.cpp:268-305
+};
+
+class BoardObs final {
+public:
+  int frame_id_ = 0, camera_id_ = 0, board_id_ = 0;
+  std::vector<Point2f> pts_2d_;
+  std::vector<int> charuco_id_;
+  Pose6 pose_{};          // board pose w.r.t. the camera
+  bool valid_ = true;
+  std::weak_ptr<Camera> cam_;
+  std::weak_ptr<Board> board_3d_;
+};
+
+class Object3D final {
+public:
+  int obj_id_ = 0, ref_board_id_ = 0;
+  std::map<int, std::weak_ptr<Board>> boards_;
+  std::map<int, Pose6> relative_board_pose_;
+  std::vector<Point3f> pts_3d_;                                  // object-frame points (float, regenerated)
+  std::map<std::pair<int, int>, int> pts_board_2_obj_;
+  std::vector<std::pair<int, int>> pts_obj_2_board_;
+  std::map<int, std::weak_ptr<Object3DObs>> object_observations_;
+  void refineObject(const int nb_iterations);   // Object3D.cpp:160-243
+  void updateObjectPts();                       // Object3D.cpp:249-268
+};
+
+class Object3DObs final {
+public:
+  int frame_id_ = 0, camera_id_ = 0, object_3d_id_ = 0;
+  std::vector<Point2f> pts_2d_;
+  std::vector<int> pts_id_;                 // indices into Object3D::pts_3d_
+  Pose6 pose_{};                            // object pose w.r.t. the camera
+  Pose6 group_pose_{};                      // object pose w.r.t. the camera group (setPoseInGroupVec)
+  std::map<int, std::weak_ptr<BoardObs>> board_observations_;
+  std::weak_ptr<Camera> cam_;
+  std::weak_ptr<Object3D> object_3d_;
+};
+
+class CameraGroupObs final {
+public:
+  int cam_group_idx_ = 0;
+  std::map<int, std::weak_ptr<Object3DObs>> object_observations_;
+  std::map<int, Pose6> object_pose_;        // object pose w.r.t. the reference camera of the group
+  void updateObjObsPose();                  // CameraGroupObs.cpp:208-217
+};
+
+class Frame final {
+public:
+  int frame_idx_ = 0;
+  std::map<int, std::weak_ptr<CameraGroupObs>> cam_group_observations_;
+};
+
+class CameraGroup final {
+public:
+  int cam_group_idx_ = 0, id_ref_cam_ = 0;
+  std::map<int, std::weak_ptr<Camera>> cameras_;
+  std::map<int, std::weak_ptr<Frame>> frames_;
+  std::map<int, Pose6> relative_camera_pose_;
+  void refineCameraGroup(const int nb_iterations);                         // CameraGroup.cpp:191-279
+  void refineCameraGroupAndObjects(const int nb_iterations);               // CameraGroup.cpp:366-474
+  void refineCameraGroupAndObjectsAndIntrinsics(const int nb_iterations);  // CameraGroup.cpp:483-583
+  // stage 4 immediately followed by stage 5 on one device-resident copy of the observations
+  // (apps/calibrate/src/calibrate.cpp:60-64 calls the two entry points back to back)
+  void refineCameraGroupAndObjectsThenIntrinsics(const int nb_iterations, bool with_intrinsics);
+private:
+  void refineStage(int stage, int nb_iterations, bool then_intrinsics);
+};
+
+class Calibration final {
+public:
+  int nb_iterations_ = 1000;       // YAML number_iterations (McCalib.cpp:59)
+  int fix_intrinsic_ = 0;          // YAML fix_intrinsic     (McCalib.cpp:77)
+  int distortion_model_ = 0;       // YAML distortion_model  (McCalib.cpp:60)
+  std::vector<int> distortion_per_camera_;
+  int cuda_device_ = 0;
+  std::map<int, std::shared_ptr<Camera>> cams_;
+  std::map<int, std::shared_ptr<Board>> boards_3d_;
+  std::map<int, std::shared_ptr<BoardObs>> board_observations_;
+  std::map<int, std::shared_ptr<Object3D>> object_3d_;
+  std::map<int, std::shared_ptr<Object3DObs>> object_observations_;
+  std::map<int, std::shared_ptr<CameraGroup>> cam_group_;
+  std::map<int, std::shared_ptr<CameraGroupObs>> cams_group_obs_;
+  std::map<int, std::shared_ptr<Frame>> frames_;
+
+  bool loadConfig(const std::string& yaml_path);       // the keys of McCalib.cpp:39-79 that the refinement path uses
+  void refineIntrinsicAndPoseAllCam();                 // McCalib.cpp:713-716
+  void refineAllObject3D();                            // McCalib.cpp:1014-1017
+  void refineAllCameraGroup();                         // McCalib.cpp:1211-1220
+  void refineAllCameraGroupAndObjects();               // McCalib.cpp:1876-1887
+  void refineAllCameraGroupAndObjectsAndIntrinsic();   // McCalib.cpp:2348-2359
+  double computeAvgReprojectionError();                // McCalib.cpp:2168-2245 (mean of per-observation means)
+  bool saveCamerasParams(const std::string& path) const;   // calibrated_cameras_data.yml layout of McCalib.cpp:374-420
+};
+
+// pose helpers (Rodrigues both ways, composition), double precision
+void rotVecToMat(const double* rv, double* R /*9, row-major*/);
+void matToRotVec(const double* R, double* rv);
+Pose6 composePose(const Pose6& outer, const Pose6& inner);   // x -> outer(inner(x))
+Pose6 invertPose(const Pose6& p);
+
+extern int g_verbose;              // 1: per-iteration table on stdout like minimizer_progress_to_stdout (default)
+extern int g_cuda_device;          // device used by the refine* methods (set from Calibration::cuda_device_)
+extern std::string g_last_error;   // text of the last libmcba failure (the reference ignores solver failures)
+
+}  // namespace McCalib
