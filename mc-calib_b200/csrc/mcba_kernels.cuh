@@ -856,48 +856,68 @@ __global__ void __launch_bounds__(CC_THREADS) k_chol_coop(double* __restrict__ S
     grid.sync();
     CC_PROF(4);
   }
-  // ---- backward substitution L^T z = y (y = row n), CTA 0 only
-  if (blockIdx.x != 0) return;
-  __syncthreads();
-  double* y = Pa;   // needs n doubles: n <= 64*68*2 = 8704
-  for (int i = tid; i < n; i += CC_THREADS) y[i] = S[(size_t)n * n + i];
-  __syncthreads();
-  for (int j0 = ((n - 1) / CC_B) * CC_B; j0 >= 0; j0 -= CC_B) {
-    const int jb = min(CC_B, n - j0);
-    for (int e = tid; e < jb * jb; e += CC_THREADS) { const int r = e / jb, c = e % jb; Lm[r * CC_DL + c] = (c <= r) ? S[(size_t)(j0 + r) * n + j0 + c] : 0.0; }
-    __syncthreads();
-    if (tid < jb) invd[tid] = 1.0 / Lm[tid * CC_DL + tid];
-    __syncthreads();
-    if (warp == 0) {
-      double a0 = (lane < jb) ? y[j0 + lane] : 0.0, a1 = (lane + 32 < jb) ? y[j0 + lane + 32] : 0.0;
-      for (int j = jb - 1; j >= 0; --j) {
-        const double zj = __shfl_sync(0xffffffffu, (j < 32) ? a0 : a1, j & 31) * invd[j];
-        if (lane == (j & 31)) { if (j < 32) a0 = zj; else a1 = zj; }
-        if (lane < j) a0 -= zj * Lm[j * CC_DL + lane];
-        if (lane + 32 < j) a1 -= zj * Lm[j * CC_DL + lane + 32];
-      }
-      if (lane < jb) y[j0 + lane] = a0;
-      if (lane + 32 < jb) y[j0 + lane + 32] = a1;
-    }
-    __syncthreads();
-    for (int i = tid; i < j0; i += CC_THREADS) {
-      double v[16], s0 = 0.0, s1 = 0.0;
+  // ---- backward substitution L^T z = y (y = row n of S, in place). Per 64-block, from the last one: CTA 0 solves the
+  // diagonal block and publishes z_b; one grid sync; then the update y[i] -= sum_k L[j0+k][i] z_b[k] of the columns to
+  // the left is spread over CTAs by 64-column chunk. CTA 0 keeps the chunk it needs next for itself, so the critical
+  // path per block is one small update + one 64-step warp solve + one grid sync.
+  double* yrow = S + (size_t)n * n;
+  double* zb = Pa;            // [64] current z block (shared)
+  double* red = Pa + 64;      // [4][64] partial sums
+  const int nblk = (n + CC_B - 1) / CC_B;
+  for (int b = nblk - 1; b >= 0; --b) {
+    const int j0 = b * CC_B, jb = min(CC_B, n - j0);
+    if (blockIdx.x == 0) {
+      __syncthreads();
+      {
+        double v[16];
 #pragma unroll
-      for (int kb = 0; kb < CC_B; kb += 16) {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = (kb + k < jb) ? S[(size_t)(j0 + kb + k) * n + i] : 0.0;
-#pragma unroll
-        for (int k = 0; k < 16; k += 2) {
-          if (kb + k < jb) s0 += v[k] * y[j0 + kb + k];
-          if (kb + k + 1 < jb) s1 += v[k + 1] * y[j0 + kb + k + 1];
+        for (int it = 0; it < 16; ++it) {
+          const int e = tid + it * CC_THREADS, r = e >> 6, c = e & 63;
+          v[it] = (r < jb && c <= r) ? S[(size_t)(j0 + r) * n + j0 + c] : 0.0;
         }
+#pragma unroll
+        for (int it = 0; it < 16; ++it) { const int e = tid + it * CC_THREADS; Lm[(e >> 6) * CC_DL + (e & 63)] = v[it]; }
       }
-      y[i] -= s0 + s1;
+      __syncthreads();
+      if (tid < jb) invd[tid] = 1.0 / Lm[tid * CC_DL + tid];
+      __syncthreads();
+      if (warp == 0) {
+        double a0 = (lane < jb) ? yrow[j0 + lane] : 0.0, a1 = (lane + 32 < jb) ? yrow[j0 + lane + 32] : 0.0;
+        for (int j = jb - 1; j >= 0; --j) {
+          const double zj = __shfl_sync(0xffffffffu, (j < 32) ? a0 : a1, j & 31) * invd[j];
+          if (lane == (j & 31)) { if (j < 32) a0 = zj; else a1 = zj; }
+          if (lane < j) a0 -= zj * Lm[j * CC_DL + lane];
+          if (lane + 32 < j) a1 -= zj * Lm[j * CC_DL + lane + 32];
+        }
+        if (lane < jb) z[j0 + lane] = a0;
+        if (lane + 32 < jb) z[j0 + lane + 32] = a1;
+        __threadfence();
+      }
     }
-    __syncthreads();
+    grid.sync();
+    if (b == 0) break;
+    for (int c = b - 1; c >= 0; --c) {
+      const int owner = (c == b - 1) ? 0 : 1 + (c % (gridDim.x - 1));
+      if ((int)blockIdx.x != owner) continue;
+      __syncthreads();
+      if (tid < CC_B) zb[tid] = (tid < jb) ? z[j0 + tid] : 0.0;
+      __syncthreads();
+      const int i = c * CC_B + (tid & 63), kg = tid >> 6;
+      double v[16], s0 = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) { const int k = kg + 4 * kk; v[kk] = (k < jb) ? S[(size_t)(j0 + k) * n + i] : 0.0; }
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) s0 += v[kk] * zb[kg + 4 * kk];
+      red[kg * 64 + (tid & 63)] = s0;
+      __syncthreads();
+      if (tid < 64) yrow[c * CC_B + tid] -= (red[tid] + red[64 + tid]) + (red[128 + tid] + red[192 + tid]);
+    }
+    __threadfence();
   }
-  const bool failed = *fail != 0;
-  for (int i = tid; i < n; i += CC_THREADS) z[i] = failed ? 0.0 : y[i];
+  if (blockIdx.x == 0 && *fail != 0) {
+    __syncthreads();
+    for (int i = tid; i < n; i += CC_THREADS) z[i] = 0.0;
+  }
   CC_PROF(5);
 #undef CC_PROF
 }
