@@ -12,7 +12,7 @@
 //   k_eblock_factor      K2c (E^T E + D^2) = L L^T, Z = L^-1 [E^T F | E^T r] (Jacobi-scaled)
 //   k_syrk / k_syrk_sum  K2d Schur complement sum_o Z_o^T Z_o with DMMA, split-K with fixed-order sum
 //   k_build_reduced      K2e S = F^T F + D^2 - Z^T Z, rhs
-//   k_chol_*             K3  blocked dense Cholesky + triangular solves of the reduced system
+//   k_chol_coop          K3  cooperative persistent blocked Cholesky + both triangular solves of the reduced system
 //   k_backsubst, k_fstep K4  e-block back-substitution, candidate point, model-cost-change pieces
 // Replaces ProgramEvaluator / SchurEliminator / CHOLMOD of ceres-solver 2.2.0 as used by the reference
 // (SURVEY.md §2.2, §8a rows a12-a15).
@@ -112,8 +112,15 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, (MODE == MODE_FUSED || MODE ==
     const double* in = a.intr + 9 * (size_t)cam;
     __syncwarp();
     if (MODE != MODE_FROM_J) {
-      for (int e = lane; e < CTX_SIZE; e += 32)
-        if (e < CTX_NO || e >= CTX_IN) ctx[e] = ctx_entry_a(e, pc, act_c, po, pb, act_b, in);
+      if (MODE == MODE_COST) {   // residual only: the three (R, t) pairs and the intrinsics
+        for (int e = lane; e < CTX_DRC + 9; e += 32) {
+          const int ee = (e < CTX_DRC) ? e : CTX_IN + (e - CTX_DRC);
+          ctx[ee] = ctx_entry_a(ee, pc, act_c, po, pb, act_b, in);
+        }
+      } else {
+        for (int e = lane; e < CTX_SIZE; e += 32)
+          if (e < CTX_NO || e >= CTX_IN) ctx[e] = ctx_entry_a(e, pc, act_c, po, pb, act_b, in);
+      }
       __syncwarp();
       if (MODE != MODE_COST) {
         for (int e = CTX_NO + lane; e < CTX_IN; e += 32) ctx[e] = ctx_entry_b(e, ctx, po, pb, act_b);
@@ -159,15 +166,20 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, (MODE == MODE_FUSED || MODE ==
         __syncwarp();
         const int nrows = 2 * min(PASS, obs_end - base);
         const int ksteps = (nrows + 3) >> 2;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          double f[C::NBLK];
+        double f[C::NBLK], fn[C::NBLK];   // fragments of the next k-step are fetched while this one's DMMAs issue
 #pragma unroll
-          for (int c = 0; c < C::NBLK; ++c) f[c] = (8 * c + g < C::NC) ? T[(8 * c + g) * TS + 4 * ks + q] : 0.0;
+        for (int c = 0; c < C::NBLK; ++c) f[c] = (8 * c + g < C::NC) ? T[(8 * c + g) * TS + q] : 0.0;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const int kn = min(ks + 1, ksteps - 1);
+#pragma unroll
+          for (int c = 0; c < C::NBLK; ++c) fn[c] = (8 * c + g < C::NC) ? T[(8 * c + g) * TS + 4 * kn + q] : 0.0;
           int t = 0;
 #pragma unroll
           for (int bi = 0; bi < C::NBLK; ++bi)
 #pragma unroll
             for (int bj = bi; bj < C::NBLK; ++bj) { dmma884(acc[t][0], acc[t][1], f[bi], f[bj]); ++t; }
+#pragma unroll
+          for (int c = 0; c < C::NBLK; ++c) f[c] = fn[c];
         }
         __syncwarp();
       }
@@ -539,142 +551,7 @@ __global__ void k_build_reduced(const double* __restrict__ FF, const double* __r
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: blocked right-looking Cholesky of S (lower, in place, row-major ld n). Panel width 32.
-constexpr int CH_B = 32;
-__global__ void __launch_bounds__(32) k_chol_diag(double* __restrict__ S, int n, int j0, int* __restrict__ fail) {
-  __shared__ double A[CH_B][CH_B + 1];
-  const int jb = min(CH_B, n - j0), t = threadIdx.x;
-  for (int r = 0; r < jb; ++r) if (t < jb) A[r][t] = S[(size_t)(j0 + r) * n + j0 + t];
-  __syncwarp();
-  for (int j = 0; j < jb; ++j) {
-    // column j: rows t >= j
-    double s = 0.0;
-    if (t >= j && t < jb) { s = A[t][j]; for (int k = 0; k < j; ++k) s -= A[t][k] * A[j][k]; }
-    const double d = __shfl_sync(0xffffffffu, s, j);
-    if (!(d > 0.0) || !(d < DBL_MAX)) { if (t == 0) atomicExch(fail, 1); return; }
-    const double l = sqrt(d);
-    if (t == j) A[t][j] = l; else if (t > j && t < jb) A[t][j] = s / l;
-    __syncwarp();
-  }
-  for (int r = 0; r < jb; ++r) if (t <= r && t < jb) S[(size_t)(j0 + r) * n + j0 + t] = A[r][t];
-}
-// rows below the panel: L21 = A21 L11^-T, one thread per row
-__global__ void __launch_bounds__(128) k_chol_trsm(double* __restrict__ S, int n, int j0, const int* __restrict__ fail) {
-  __shared__ double L[CH_B][CH_B + 1];
-  __shared__ double X[128][CH_B + 1];
-  if (*fail) return;
-  const int jb = min(CH_B, n - j0), t = threadIdx.x;
-  for (int e = t; e < jb * jb; e += 128) L[e / jb][e % jb] = S[(size_t)(j0 + e / jb) * n + j0 + e % jb];
-  const int i = j0 + jb + blockIdx.x * 128 + t;
-  // coalesced load of the 128 x jb block
-  for (int e = t; e < 128 * jb; e += 128) {
-    const int r = e / jb, c = e % jb, gi = j0 + jb + blockIdx.x * 128 + r;
-    X[r][c] = (gi < n) ? S[(size_t)gi * n + j0 + c] : 0.0;
-  }
-  __syncthreads();
-  if (i < n) {
-    for (int j = 0; j < jb; ++j) {
-      double s = X[t][j];
-      for (int k = 0; k < j; ++k) s -= X[t][k] * L[j][k];
-      X[t][j] = s / L[j][j];
-    }
-  }
-  __syncthreads();
-  for (int e = t; e < 128 * jb; e += 128) {
-    const int r = e / jb, c = e % jb, gi = j0 + jb + blockIdx.x * 128 + r;
-    if (gi < n) S[(size_t)gi * n + j0 + c] = X[r][c];
-  }
-}
-// trailing update A22 -= L21 L21^T on lower-triangle 64x64 tiles; 256 threads, 4x4 per thread
-__global__ void __launch_bounds__(256) k_chol_update(double* __restrict__ S, int n, int j0, const int* __restrict__ fail) {
-  __shared__ double Pi[64][CH_B + 1];
-  __shared__ double Pj[64][CH_B + 1];
-  if (*fail) return;
-  const int jb = min(CH_B, n - j0), base = j0 + jb;
-  // tile pair (ti >= tj) from linear index
-  int tj = 0, rem = blockIdx.x; const int nt = (n - base + 63) / 64;
-  while (rem >= nt - tj) { rem -= nt - tj; ++tj; }
-  const int ti = tj + rem;
-  const int t = threadIdx.x;
-  for (int e = t; e < 64 * jb; e += 256) {
-    const int r = e / jb, c = e % jb;
-    const int gi = base + ti * 64 + r, gj = base + tj * 64 + r;
-    Pi[r][c] = (gi < n) ? S[(size_t)gi * n + j0 + c] : 0.0;
-    Pj[r][c] = (gj < n) ? S[(size_t)gj * n + j0 + c] : 0.0;
-  }
-  __syncthreads();
-  const int tr = (t / 16) * 4, tc = (t % 16) * 4;
-  double acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-  for (int k = 0; k < jb; ++k) {
-    double x[4], y[4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) { x[a] = Pi[tr + a][k]; y[a] = Pj[tc + a][k]; }
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] += x[a] * y[b];
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int gi = base + ti * 64 + tr + a, gj = base + tj * 64 + tc + b;
-      if (gi < n && gj <= gi) S[(size_t)gi * n + gj] -= acc[a][b];
-    }
-}
-// z = L^-T L^-1 rhs, single CTA, blocked by 32 columns
-__global__ void __launch_bounds__(1024) k_chol_solve(const double* __restrict__ S, int n, const double* __restrict__ rhs,
-                                                     double* __restrict__ z, const int* __restrict__ fail) {
-  extern __shared__ double b[];   // [n]
-  const int t = threadIdx.x;
-  if (*fail) { for (int i = t; i < n; i += blockDim.x) z[i] = 0.0; return; }
-  for (int i = t; i < n; i += blockDim.x) b[i] = rhs[i];
-  __syncthreads();
-  for (int j0 = 0; j0 < n; j0 += CH_B) {          // forward: L y = b
-    const int jb = min(CH_B, n - j0);
-    if (t < 32) {
-      for (int j = 0; j < jb; ++j) {
-        if (t == 0) b[j0 + j] /= S[(size_t)(j0 + j) * n + j0 + j];
-        __syncwarp();
-        const int i = j + 1 + t;
-        if (i < jb) b[j0 + i] -= S[(size_t)(j0 + i) * n + j0 + j] * b[j0 + j];
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    for (int i = j0 + jb + t; i < n; i += blockDim.x) {
-      double s = b[i]; const double* Li = S + (size_t)i * n + j0;
-      for (int k = 0; k < jb; ++k) s -= Li[k] * b[j0 + k];
-      b[i] = s;
-    }
-    __syncthreads();
-  }
-  for (int j0 = ((n - 1) / CH_B) * CH_B; j0 >= 0; j0 -= CH_B) {   // backward: L^T z = y
-    const int jb = min(CH_B, n - j0);
-    if (t < 32) {
-      for (int j = jb - 1; j >= 0; --j) {
-        if (t == 0) b[j0 + j] /= S[(size_t)(j0 + j) * n + j0 + j];
-        __syncwarp();
-        if (t < j) b[j0 + t] -= S[(size_t)(j0 + j) * n + j0 + t] * b[j0 + j];
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    for (int i = t; i < j0; i += blockDim.x) {
-      double s = b[i];
-      for (int k = 0; k < jb; ++k) s -= S[(size_t)(j0 + k) * n + i] * b[j0 + k];
-      b[i] = s;
-    }
-    __syncthreads();
-  }
-  for (int i = t; i < n; i += blockDim.x) z[i] = b[i];
-}
-
-// K3 (production): one cooperative persistent kernel for the whole factorisation + both triangular solves.
+// K3: one cooperative persistent kernel for the whole factorisation + both triangular solves.
 // S is (n+1) x n row-major: rows 0..n-1 the symmetric reduced matrix (lower part used), row n the rhs.
 // Right-looking with 64-wide panels. Per panel: every CTA factors the 64x64 diagonal block redundantly in shared
 // memory (no broadcast needed), warps solve one row each of the panel below it (the rhs row included, which

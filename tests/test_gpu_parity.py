@@ -210,3 +210,71 @@ def test_batched_problems_terminate_independently(oracle):
     its = [s.num_iterations for s in summ]
     assert its[0] < max(its[1:])
     assert all(s.termination == 0 for s in summ)
+
+
+@pytest.mark.parametrize("cfgname,frames,stage", [("c3", 40, 5), ("c3", 40, 4), ("c4", 30, 5)])
+def test_solve_large_reduced_systems(cfgname, frames, stage, oracle):
+    """16-camera ring (63-corner boards: three warp passes per board observation, n_f = 270 = 4 panels + 14) and the
+    64-camera dome (n_f = 1020 = 15 panels + 60): multi-panel cooperative Cholesky and the split-K Schur SYRK."""
+    s = synth.make_scene(cfgname, n_frames=frames)
+    o = synth.generate_observations(s)
+    prob, init, gt = synth.make_problem(s, o, stage)
+    g, oo = _solve_both(prob, init, oracle)
+    _assert_same_solution(prob, g, oo)
+
+
+def test_ragged_and_empty_inputs(oracle):
+    """Poses without any observation, single-corner board observations and a camera that is never observed."""
+    s = synth.make_scene("c2", n_frames=30)
+    o = synth.generate_observations(s)
+    prob, init, gt = synth.make_problem(s, o, 5)
+    counts = np.diff(prob.bobs_ptr)
+    keep_bobs = np.ones(prob.n_bobs, bool)
+    keep_bobs[prob.bobs_pose == 7] = False          # frame 7 loses all its observations -> empty e-block
+    keep_bobs[prob.bobs_cam == 3] &= (np.arange(prob.n_bobs) % 2 == 0)[prob.bobs_cam == 3]
+    new_counts = counts.copy()
+    new_counts[prob.bobs_pose == 11] = 1            # frame 11: one corner per board observation
+    obs_keep = np.zeros(prob.n_obs, bool)
+    for b in range(prob.n_bobs):
+        if keep_bobs[b]:
+            obs_keep[prob.bobs_ptr[b]:prob.bobs_ptr[b] + new_counts[b]] = True
+    p2 = mcba.Problem(5, prob.u[obs_keep], prob.v[obs_keep], prob.pt_idx[obs_keep],
+                      np.concatenate([[0], np.cumsum(new_counts[keep_bobs])]), prob.bobs_cam[keep_bobs],
+                      prob.bobs_pose[keep_bobs], prob.bobs_board[keep_bobs], prob.pts_xyz, prob.cam_model, prob.n_pose,
+                      prob.n_board, prob.cam_is_ref, prob.board_is_ref)
+    g, oo = _solve_both(p2, init, oracle)
+    _assert_same_solution(p2, g, oo)
+    assert np.array_equal(g[0].pose[7], init.pose[7])      # untouched: zero gradient, zero step
+
+
+def test_invalid_inputs_are_rejected():
+    s = synth.make_scene("c1", n_frames=5)
+    o = synth.generate_observations(s)
+    prob, init, gt = synth.make_problem(s, o, 4)
+    bad = prob.with_stage(4)
+    bad.pt_idx = prob.pt_idx.copy(); bad.pt_idx[3] = 10 ** 6
+    with pytest.raises(mcba.McbaError):
+        mcba.Handle(bad)
+    bad = prob.with_stage(4)
+    bad.bobs_pose = prob.bobs_pose[::-1].copy()
+    with pytest.raises(mcba.McbaError):
+        mcba.Handle(bad)
+    with pytest.raises(mcba.McbaError):
+        mcba.Handle(prob.with_stage(9))
+    h = mcba.Handle(prob)
+    with pytest.raises(mcba.McbaError):
+        h.solve_batched(init.copy())
+    h.close()
+
+
+def test_non_finite_start_fails_like_ceres():
+    """NaN in the initial point: Ceres reports 'Initial residual and Jacobian evaluation failed' (FAILURE)."""
+    s = synth.make_scene("c1", n_frames=5)
+    o = synth.generate_observations(s)
+    prob, init, gt = synth.make_problem(s, o, 5)
+    p = init.copy(); p.intrinsics[0, 0] = np.nan
+    h = mcba.Handle(prob)
+    with pytest.raises(mcba.McbaError) as e:
+        h.solve(p)
+    assert "rc=-4" in str(e.value)
+    h.close()
