@@ -278,3 +278,35 @@ def test_non_finite_start_fails_like_ceres():
         h.solve(p)
     assert "rc=-4" in str(e.value)
     h.close()
+
+
+def test_solve_is_bit_reproducible(c2):
+    """No floating-point atomics anywhere: two solves from the same start give bit-identical parameters and traces."""
+    prob, init, gt = stage_problem(c2, 5)
+    outs = []
+    for _ in range(2):
+        p = init.copy()
+        h = mcba.Handle(prob)
+        s, t = h.solve(p)
+        h.close()
+        outs.append((p, [(r.cost, r.trust_region_radius, r.gradient_max_norm) for r in t]))
+    assert outs[0][1] == outs[1][1]
+    for name in ("cam_pose", "pose", "board_pose", "intrinsics"):
+        assert np.array_equal(getattr(outs[0][0], name), getattr(outs[1][0], name))
+
+
+def test_empty_problem(oracle):
+    """A problem whose parameter blocks have no residuals: cost 0, zero gradient -> CONVERGENCE at iteration 0."""
+    s = synth.make_scene("c1", n_frames=4)
+    o = synth.generate_observations(s)
+    prob, init, gt = synth.make_problem(s, o, 4)
+    e = mcba.Problem(4, [], [], [], [0], [], [], [], prob.pts_xyz, prob.cam_model, prob.n_pose, prob.n_board,
+                     prob.cam_is_ref, prob.board_is_ref)
+    p = init.copy()
+    h = mcba.Handle(e)
+    summ, tr = h.solve(p)
+    h.close()
+    po = init.copy()
+    rc, so, to = oracle.solve(e, po)
+    assert (summ.termination, summ.num_iterations) == (so.termination, so.num_iterations) == (0, 1)
+    assert summ.final_cost == 0.0 and np.array_equal(p.pose, init.pose)
