@@ -40,6 +40,41 @@ __global__ void __launch_bounds__(256) dmma_kernel(double* out, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// DMMA with a 4x4 outer-product operand pattern (16 accumulator tiles, 4 A and 4 B fragment registers per k-step
+// refreshed every step from shared memory), the operand pattern of k_syrk / k_observations.
+__global__ void __launch_bounds__(128) dmma_outer_kernel(double* out, int iters) {
+  __shared__ double sm[16 * 68];
+  for (int i = threadIdx.x; i < 16 * 68; i += blockDim.x) sm[i] = 1.0 + i * 1e-6;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  double c[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) { c[i][j][0] = 0; c[i][j][1] = 0; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+      double fa[4], fb[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) { fa[i] = sm[(4 * ks + q) * 68 + 8 * i + g]; fb[i] = sm[(4 * ks + q) * 68 + 32 + 8 * i + g]; }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                       : "+d"(c[i][j][0]), "+d"(c[i][j][1]) : "d"(fa[i]), "d"(fb[j]));
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) s += c[i][j][0] + c[i][j][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void copy_kernel(const double2* __restrict__ in, double2* __restrict__ out, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -81,6 +116,14 @@ int main() {
       float ms = time_ms([&] { dmma_kernel<8><<<sms * bps, 256>>>(out, iters); }, 5);
       double flops = 2.0 * 256.0 * 8 * iters * 8.0 * sms * bps;  // 8x8x4 FMAs per warp-instr, 8 warps/CTA
       printf(" \"dmma_tflops_bps%d\": %.3f,\n", bps, flops / ms * 1e-9);
+    }
+  }
+  {
+    const int iters = 2000;
+    for (int bps : {2, 4, 6}) {
+      float ms = time_ms([&] { dmma_outer_kernel<<<sms * bps, 128>>>(out, iters); }, 5);
+      double flops = 2.0 * 256.0 * 64 * iters * 4.0 * sms * bps;   // 64 DMMA per iteration per warp, 4 warps/CTA
+      printf(" \"dmma_outer4x4_tflops_bps%d\": %.3f,\n", bps, flops / ms * 1e-9);
     }
   }
   {
