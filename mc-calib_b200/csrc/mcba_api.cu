@@ -234,7 +234,8 @@ static int setup_stage(Handle* H, int stage) {
   H->syrk_tiles = H->syrk_nt * (H->syrk_nt + 1) / 2;
   const int64_t n_rows = 6 * (int64_t)H->n_pose;
   int syrk_per_sm = 4;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&syrk_per_sm, k_syrk, 128, 0);
+  CU(cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&syrk_per_sm, k_syrk, 128, SY_SMEM);
   int nsplit = std::max(1, (std::max(1, syrk_per_sm) * H->n_sm) / H->syrk_tiles);   // one full wave of CTAs, no tail
   nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(nsplit, (n_rows + 63) / 64));
   H->syrk_rows_per_split = (((n_rows + nsplit - 1) / nsplit + SY_K - 1) / SY_K) * SY_K;
@@ -465,7 +466,7 @@ static int compute_step(Handle* H, LmStep* out) {
     Timed t(H, KF_SYRK);
     dim3 grid(H->syrk_tiles, H->syrk_nsplit);
     ++H->n_launches;
-    k_syrk<<<grid, 128, 0, H->stream>>>(H->d_Z, 6 * (int64_t)H->n_pose, H->ldz, H->syrk_nt, H->syrk_rows_per_split, H->d_syrk_partial);
+    k_syrk<<<grid, 128, SY_SMEM, H->stream>>>(H->d_Z, 6 * (int64_t)H->n_pose, H->ldz, H->syrk_nt, H->syrk_rows_per_split, H->d_syrk_partial);
     ++H->n_launches;
     k_syrk_sum<<<H->syrk_tiles, 256, 0, H->stream>>>(H->d_syrk_partial, H->syrk_tiles, H->syrk_nt, H->syrk_nsplit, H->ldz, H->d_ZtZ);
     CHECK_LAUNCH();

@@ -110,6 +110,11 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, (MODE == MODE_FUSED || MODE ==
     const double* po = a.prep_pose + (size_t)PREP * rec.z;
     const double* pb = ST::BOARD ? a.prep_board + (size_t)PREP * rec.w : nullptr;
     const double* in = a.intr + 9 * (size_t)cam;
+    // observation loads run one pass ahead: the first pass's are issued before the context is built
+    float pf_u = 0.f, pf_v = 0.f; int pf_pt = 0;
+    if (MODE != MODE_FROM_J && lane < PASS && obs_begin + lane < obs_end) {
+      pf_u = a.u[obs_begin + lane]; pf_v = a.v[obs_begin + lane]; pf_pt = a.pt[obs_begin + lane];
+    }
     __syncwarp();
     if (MODE != MODE_FROM_J) {
       if (MODE == MODE_COST) {   // residual only: the three (R, t) pairs and the intrinsics
@@ -134,6 +139,10 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, (MODE == MODE_FUSED || MODE ==
     for (int base = obs_begin; base < obs_end; base += PASS) {
       const int i = base + lane;
       const bool active = lane < PASS && i < obs_end;
+      const float cur_u = pf_u, cur_v = pf_v; const int cur_pt = pf_pt;
+      if (MODE != MODE_FROM_J && lane < PASS && i + PASS < obs_end) {
+        pf_u = a.u[i + PASS]; pf_v = a.v[i + PASS]; pf_pt = a.pt[i + PASS];
+      }
       if (active) {
         if (MODE == MODE_FROM_J) {
           const double* blk = a.jmat + (size_t)2 * C::NC * obs_begin;
@@ -143,9 +152,9 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, (MODE == MODE_FUSED || MODE ==
             *reinterpret_cast<double2*>(T + col * TS + 2 * lane) =
                 *reinterpret_cast<const double2*>(blk + ((size_t)col * nobs + j) * 2);
         } else {
-          const double* p3 = a.pts + 3 * (size_t)a.pt[i];
+          const double* p3 = a.pts + 3 * (size_t)cur_pt;
           const double X0[3] = {p3[0], p3[1], p3[2]};
-          const double uu = (double)a.u[i], vv = (double)a.v[i];
+          const double uu = (double)cur_u, vv = (double)cur_v;
           if (MODE == MODE_COST) {
             double ru, rv;
             cost += obs_cost(ctx, model, X0, uu, vv, a.huber_a, ru, rv);
@@ -446,11 +455,20 @@ __global__ void __launch_bounds__(128) k_eblock_factor(const double* __restrict_
 
 // K2d: C = Z^T Z restricted to upper tile pairs, split over row ranges. 64x64 tile per CTA, 4 warps (2x2),
 // each warp 32x32 = 4x4 DMMA tiles; K chunk of 16 rows staged through shared memory with register prefetch.
-constexpr int SY_T = 64, SY_K = 16, SY_LD = 68;
+constexpr int SY_T = 64, SY_K = 32, SY_LD = 68, SY_STAGES = 3;
+constexpr int SY_SMEM = SY_STAGES * 2 * SY_K * SY_LD * 8;   // dynamic shared memory of k_syrk
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {   // src_bytes 0 -> zero fill
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// 64x64 output tile per CTA, 4 warps (2x2) of 32x32 = 4x4 DMMA tiles each; rows of Z stream through a 3-stage
+// cp.async ring of 32-row chunks (one barrier per 128 DMMAs per warp, loads two chunks ahead of the math).
 __global__ void __launch_bounds__(128) k_syrk(const double* __restrict__ Z, int64_t n_rows, int ldz, int nt,
                                               int64_t rows_per_split, double* __restrict__ partial) {
-  __shared__ double As[SY_K * SY_LD];
-  __shared__ double Bs[SY_K * SY_LD];
+  extern __shared__ __align__(16) double sy_sm[];
   // tile pair from linear index (ti <= tj)
   int ti = 0, rem = blockIdx.x;
   while (rem >= nt - ti) { rem -= nt - ti; ++ti; }
@@ -459,41 +477,43 @@ __global__ void __launch_bounds__(128) k_syrk(const double* __restrict__ Z, int6
   const int64_t r0 = (int64_t)split * rows_per_split, r1 = min(n_rows, r0 + rows_per_split);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const bool diag = (ti == tj);
   double acc[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-  // each thread stages 8 doubles of A and of B per chunk: row = e / 16, col4 = (e % 16) * 4 ... as 4 double2 loads
-  double2 ra[4], rb[4];
-  const bool diag = (ti == tj);
-  auto gload = [&](int64_t rbase) {
+  const int n_chunks = (r1 > r0) ? (int)((r1 - r0 + SY_K - 1) / SY_K) : 0;
+  // per-thread copy slots: SY_K rows x 64 cols = SY_K*32 16-byte pieces per operand, SY_K/4 per thread
+  const int c2 = (tid & 31) * 2, row0 = tid >> 5;            // piece i: row = row0 + 4 i
+  const bool ca_ok = ti * SY_T + c2 < ldz, cb_ok = tj * SY_T + c2 < ldz;
+  const double* ga = Z + (r0 + row0) * ldz + ti * SY_T + c2;
+  const double* gb = Z + (r0 + row0) * ldz + tj * SY_T + c2;
+  auto issue = [&](int chunk) {
+    if (chunk < n_chunks) {
+      double* As = sy_sm + (size_t)(chunk % SY_STAGES) * (2 * SY_K * SY_LD) + row0 * SY_LD + c2;
+      double* Bs = As + SY_K * SY_LD;
+      const int64_t rbase = r0 + (int64_t)chunk * SY_K + row0;
+      const double* pa = ga + (int64_t)chunk * SY_K * ldz;
+      const double* pb = gb + (int64_t)chunk * SY_K * ldz;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int e = tid + i * 128;            // 0..511 double2 slots: 16 rows x 32 double2
-      const int row = e >> 5, c2 = (e & 31) * 2;
-      const int64_t r = rbase + row;
-      const int ca = ti * SY_T + c2, cb = tj * SY_T + c2;
-      ra[i] = (r < r1 && ca < ldz) ? *reinterpret_cast<const double2*>(Z + r * ldz + ca) : make_double2(0.0, 0.0);
-      if (!diag) rb[i] = (r < r1 && cb < ldz) ? *reinterpret_cast<const double2*>(Z + r * ldz + cb) : make_double2(0.0, 0.0);
+      for (int i = 0; i < SY_K / 4; ++i) {
+        const bool rv = rbase + 4 * i < r1;
+        const bool va = rv && ca_ok, vb = rv && cb_ok;
+        cp_async16(As + 4 * i * SY_LD, va ? (const void*)(pa + (int64_t)4 * i * ldz) : (const void*)Z, va ? 16 : 0);
+        if (!diag) cp_async16(Bs + 4 * i * SY_LD, vb ? (const void*)(pb + (int64_t)4 * i * ldz) : (const void*)Z, vb ? 16 : 0);
+      }
     }
+    cp_async_commit();
   };
-  auto sstore = [&]() {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int e = tid + i * 128;
-      const int row = e >> 5, c2 = (e & 31) * 2;
-      *reinterpret_cast<double2*>(As + row * SY_LD + c2) = ra[i];
-      if (!diag) *reinterpret_cast<double2*>(Bs + row * SY_LD + c2) = rb[i];
-    }
-  };
-  const double* Bp = diag ? As : Bs;
-  if (r0 < r1) gload(r0);
-  for (int64_t rbase = r0; rbase < r1; rbase += SY_K) {
+  for (int s = 0; s < SY_STAGES - 1; ++s) issue(s);
+  for (int chunk = 0; chunk < n_chunks; ++chunk) {
+    cp_async_wait<SY_STAGES - 2>();
     __syncthreads();
-    sstore();
-    __syncthreads();
-    if (rbase + SY_K < r1) gload(rbase + SY_K);
+    issue(chunk + SY_STAGES - 1);
+    const double* As = sy_sm + (size_t)(chunk % SY_STAGES) * (2 * SY_K * SY_LD);
+    const double* Bp = diag ? As : As + SY_K * SY_LD;
 #pragma unroll
     for (int ks = 0; ks < SY_K / 4; ++ks) {
       double fa[4], fb[4];
@@ -507,6 +527,7 @@ __global__ void __launch_bounds__(128) k_syrk(const double* __restrict__ Z, int6
         for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
     }
   }
+  cp_async_wait<0>();
   double* out = partial + ((size_t)split * gridDim.x + blockIdx.x) * (SY_T * SY_T);
 #pragma unroll
   for (int i = 0; i < 4; ++i)

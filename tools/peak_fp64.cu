@@ -75,6 +75,45 @@ __global__ void __launch_bounds__(128) dmma_outer_kernel(double* out, int iters)
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// Same, but the fragment loads cannot be hoisted (row offset depends on the iteration), and a variant with a
+// 4x8 warp tile (12 LDS per 32 DMMA instead of 8 per 16).
+template <int NJ>
+__global__ void __launch_bounds__(128) dmma_lds_kernel(double* out, int iters) {
+  __shared__ double sm[64 * 68];
+  for (int i = threadIdx.x; i < 64 * 68; i += blockDim.x) sm[i] = 1.0 + i * 1e-6;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  double c[4][NJ][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < NJ; j++) { c[i][j][0] = 0; c[i][j][1] = 0; }
+  for (int it = 0; it < iters; it++) {
+    const double* base = sm + ((it & 3) * 16) * 68;
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+      double fa[4], fb[NJ];
+#pragma unroll
+      for (int i = 0; i < 4; i++) fa[i] = base[(4 * ks + q) * 68 + 8 * i + g];
+#pragma unroll
+      for (int j = 0; j < NJ; j++) fb[j] = base[(4 * ks + q) * 68 + ((32 + 8 * j) & 63) + g];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < NJ; j++)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                       : "+d"(c[i][j][0]), "+d"(c[i][j][1]) : "d"(fa[i]), "d"(fb[j]));
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < NJ; j++) s += c[i][j][0] + c[i][j][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void copy_kernel(const double2* __restrict__ in, double2* __restrict__ out, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -124,6 +163,15 @@ int main() {
       float ms = time_ms([&] { dmma_outer_kernel<<<sms * bps, 128>>>(out, iters); }, 5);
       double flops = 2.0 * 256.0 * 64 * iters * 4.0 * sms * bps;   // 64 DMMA per iteration per warp, 4 warps/CTA
       printf(" \"dmma_outer4x4_tflops_bps%d\": %.3f,\n", bps, flops / ms * 1e-9);
+    }
+  }
+  {
+    const int iters = 2000;
+    for (int bps : {2, 3, 4}) {
+      float ms = time_ms([&] { dmma_lds_kernel<4><<<sms * bps, 128>>>(out, iters); }, 5);
+      printf(" \"dmma_lds_4x4_tflops_bps%d\": %.3f,\n", bps, 2.0 * 256.0 * 64 * iters * 4.0 * sms * bps / ms * 1e-9);
+      ms = time_ms([&] { dmma_lds_kernel<8><<<sms * bps, 128>>>(out, iters); }, 5);
+      printf(" \"dmma_lds_4x8_tflops_bps%d\": %.3f,\n", bps, 2.0 * 256.0 * 128 * iters * 4.0 * sms * bps / ms * 1e-9);
     }
   }
   {
