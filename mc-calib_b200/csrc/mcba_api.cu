@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <limits>
 #include <string>
 #include <vector>
@@ -617,8 +618,13 @@ void mcba_destroy(void* h) {
   delete H;
 }
 
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 int mcba_create(void** handle, const mcba_problem* P, int device) {
   if (!handle) return MCBA_ERR_INVALID;
+  static const bool prof = getenv("MCBA_CREATE_PROF") != nullptr;
+  const double t_begin = now_ms(); double t_mark = t_begin;
+  auto mark = [&](const char* what) { if (prof) { const double t = now_ms(); std::fprintf(stderr, "[mcba_create] %-28s %8.3f ms\n", what, t - t_mark); t_mark = t; } };
   Handle* H = new Handle();
   *handle = H;
   if (!P || P->n_obs < 0 || P->n_bobs < 0 || P->n_cam <= 0 || P->n_pose < 0) { H->err = "bad problem sizes"; return MCBA_ERR_INVALID; }
@@ -633,14 +639,17 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   }
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { H->err = "no CUDA device: libmcba has no CPU fallback"; return MCBA_ERR_CUDA; }
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10) { H->err = "libmcba is built for sm_100a (B200) only"; return MCBA_ERR_CUDA; }
+  int cc_major = 0, n_sm = 0, coop = 0;   // cudaGetDeviceProperties costs ~6 ms per call: query the three attributes instead
+  CU(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+  CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+  CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+  if (cc_major != 10) { H->err = "libmcba is built for sm_100a (B200) only"; return MCBA_ERR_CUDA; }
   CU(cudaSetDevice(device));
   H->device = device;
   CU(cudaStreamCreate(&H->stream));
   H->n_cam = P->n_cam; H->n_pose = P->n_pose; H->n_board = std::max(0, P->n_board); H->n_pts = P->n_pts;
   H->n_obs = P->n_obs; H->nb = (int)P->n_bobs; H->npad = ((P->n_obs + 31) / 32) * 32; H->n_obs_global = P->n_obs;
+  mark("device + stream");
   // validate + pack
   std::vector<int4> bobs(H->nb + 1);
   std::vector<int> ppt(H->n_pose + 1, 0);
@@ -661,6 +670,7 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   for (int64_t i = 0; i < P->n_obs; ++i) if (P->pt_idx[i] < 0 || P->pt_idx[i] >= P->n_pts) { H->err = "pt_idx out of range"; return MCBA_ERR_INVALID; }
   std::vector<double> pts((size_t)std::max(1, P->n_pts) * 3);
   for (int i = 0; i < P->n_pts * 3; ++i) pts[i] = (double)P->pts_xyz[i];
+  mark("validate + pack (host)");
   if (dalloc(H, &H->d_u, (size_t)H->npad) || dalloc(H, &H->d_v, (size_t)H->npad) || dalloc(H, &H->d_pt, (size_t)H->npad)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_pts, pts.size()) || dalloc(H, &H->d_bobs, bobs.size()) || dalloc(H, &H->d_pose_bobs_ptr, ppt.size())) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_cam_model, (size_t)H->n_cam) || dalloc(H, &H->d_cam_is_ref, (size_t)H->n_cam) || dalloc(H, &H->d_board_is_ref, (size_t)std::max(1, H->n_board))) return MCBA_ERR_CUDA;
@@ -674,6 +684,7 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   std::vector<uint8_t> zc((size_t)std::max(H->n_cam, std::max(1, H->n_board)), 0);
   CU(cudaMemcpy(H->d_cam_is_ref, P->cam_is_ref ? P->cam_is_ref : zc.data(), H->n_cam, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(H->d_board_is_ref, (P->board_is_ref && H->n_board > 0) ? P->board_is_ref : zc.data(), std::max(1, H->n_board), cudaMemcpyHostToDevice));
+  mark("observation alloc + H2D");
   for (int w = 0; w < 2; ++w) {
     if (dalloc(H, &H->d_cam_pose[w], (size_t)H->n_cam * 6) || dalloc(H, &H->d_pose[w], (size_t)H->n_pose * 6) ||
         dalloc(H, &H->d_board[w], (size_t)std::max(1, H->n_board) * 6) || dalloc(H, &H->d_intr[w], (size_t)H->n_cam * 9)) return MCBA_ERR_CUDA;
@@ -683,15 +694,19 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
       dalloc(H, &H->d_prep_board, (size_t)std::max(1, H->n_board) * PREP)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_red_scratch, (size_t)512 * 8) || dalloc(H, &H->d_scalars, (size_t)SC_N) || dalloc(H, &H->d_gather, (size_t)SC_N * 64) || dalloc(H, &H->d_fail, (size_t)1)) return MCBA_ERR_CUDA;
   CU(cudaMemset(H->d_scalars, 0, SC_N * sizeof(double)));
-  H->n_sm = prop.multiProcessorCount;
+  H->n_sm = n_sm;
   CU(cudaFuncSetAttribute(k_chol_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, CC_SMEM));
   { int per_sm = 0; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chol_coop, CC_THREADS, CC_SMEM));
-    if (per_sm < 1 || !prop.cooperativeLaunch) { H->err = "cooperative launch unavailable"; return MCBA_ERR_CUDA; }
+    if (per_sm < 1 || !coop) { H->err = "cooperative launch unavailable"; return MCBA_ERR_CUDA; }
     H->chol_grid = H->n_sm; }
   mcba_default_options(&H->opt);
+  mark("small allocs");
   const int rc = setup_stage(H, P->stage);
   if (rc) return rc;
+  mark("setup_stage (pair lists + allocs)");
   CU(cudaDeviceSynchronize());
+  mark("device sync");
+  if (prof) std::fprintf(stderr, "[mcba_create] total %8.3f ms\n", now_ms() - t_begin);
   return MCBA_OK;
 }
 

@@ -318,16 +318,17 @@ void Calibration::refineAllCameraGroupAndObjectsAndIntrinsic() {
   for (const auto& it : cams_group_obs_) it.second->updateObjObsPose();
 }
 
-// Mean over object observations of the mean corner error (McCalib.cpp:2168-2245). The per-corner errors come from
-// libmcba (mcba_reprojection_errors on the stage-3 packing: Object3D::pts_3d_ -> object pose -> camera pose ->
-// projection), evaluated in fp64; the reference rounds the transformed points to float once more
-// (geometrytools.cpp:346-352), a ~1e-4 px difference.
-double Calibration::computeAvgReprojectionError() {
-  g_cuda_device = cuda_device_;
-  double total = 0.0; long long adds = 0;
-  for (const auto& it : cam_group_) {
+// Per-corner reprojection errors of every object observation of every camera group, through libmcba
+// (mcba_reprojection_errors on the stage-3 packing: Object3D::pts_3d_ -> object pose -> camera pose -> projection),
+// evaluated in fp64; the reference rounds the transformed points to float once more (geometrytools.cpp:346-352), a
+// ~1e-4 px difference. One record per object observation, in the reference's walking order.
+namespace {
+struct ObsErrors { int group, frame, camera; std::vector<double> err; };
+bool collectReprojectionErrors(Calibration& calib, std::vector<ObsErrors>& out) {
+  for (const auto& it : calib.cam_group_) {
     CameraGroup& g = *it.second;
     Packed pk;
+    std::vector<ObsErrors> recs;
     for (const auto& it_frame : g.frames_) {
       auto frame = it_frame.second.lock();
       if (!frame) continue;
@@ -339,7 +340,7 @@ double Calibration::computeAvgReprojectionError() {
           auto oo = it_oo.second.lock();
           if (!oo) continue;
           auto object = oo->object_3d_.lock(); auto cam = oo->cam_.lock();
-          if (!object || !cam) continue;
+          if (!object || !cam || oo->pts_id_.empty()) continue;
           const int cs = pk.camSlot(cam, &g.relative_camera_pose_[oo->camera_id_], false);
           auto ps = pose_slot_of_object.find(oo->object_3d_id_);
           if (ps == pose_slot_of_object.end()) ps = pose_slot_of_object.emplace(oo->object_3d_id_, pk.poseSlot(&cgo->object_pose_[oo->object_3d_id_])).first;
@@ -347,30 +348,119 @@ double Calibration::computeAvgReprojectionError() {
             pk.board_pt_base[-1 - object->obj_id_] = (int)(pk.pts_xyz.size() / 3);
             for (const Point3f& p : object->pts_3d_) { pk.pts_xyz.push_back(p.x); pk.pts_xyz.push_back(p.y); pk.pts_xyz.push_back(p.z); }
           }
-          if (oo->pts_id_.empty()) continue;
-          pk.beginBobs(cs, ps->second, 0);        // one run per object observation = the unit the reference averages over
+          pk.beginBobs(cs, ps->second, (int)recs.size());   // the board slot is unused in stage 3: carry the record id through the sort
           for (size_t i = 0; i < oo->pts_id_.size(); ++i) pk.addObs(oo->pts_2d_[i], pk.board_pt_base[-1 - object->obj_id_] + oo->pts_id_[i]);
+          recs.push_back(ObsErrors{g.cam_group_idx_, frame->frame_idx_, oo->camera_id_, {}});
         }
       }
     }
     if (pk.u.empty()) continue;
     pk.stage = 3;
+    pk.sortByPose();
+    std::vector<int32_t> rec_of_bobs = pk.bobs_board;
+    std::fill(pk.bobs_board.begin(), pk.bobs_board.end(), 0);
     mcba_problem P = pk.problem();
     void* h = nullptr;
     std::vector<double> err(pk.u.size());
     mcba_params X = pk.params();
     int rc = mcba_create(&h, &P, g_cuda_device);
     if (rc == MCBA_OK) rc = mcba_reprojection_errors(h, &X, err.data());
-    if (rc != MCBA_OK) { g_last_error = mcba_last_error(h); mcba_destroy(h); return std::numeric_limits<double>::quiet_NaN(); }
+    if (rc != MCBA_OK) { g_last_error = mcba_last_error(h); mcba_destroy(h); return false; }
     mcba_destroy(h);
-    for (size_t b = 0; b + 1 < pk.bobs_ptr.size(); ++b) {
-      double s = 0.0;
-      for (int64_t i = pk.bobs_ptr[b]; i < pk.bobs_ptr[b + 1]; ++i) s += err[i];
-      total += s / (double)(pk.bobs_ptr[b + 1] - pk.bobs_ptr[b]);
-      ++adds;
-    }
+    for (size_t b = 0; b + 1 < pk.bobs_ptr.size(); ++b)
+      recs[rec_of_bobs[b]].err.assign(err.begin() + pk.bobs_ptr[b], err.begin() + pk.bobs_ptr[b + 1]);
+    for (auto& r : recs) out.push_back(std::move(r));
   }
-  return adds ? total / (double)adds : 0.0;
+  return true;
+}
+}  // namespace
+
+// Mean over object observations of the mean corner error (McCalib.cpp:2168-2245).
+double Calibration::computeAvgReprojectionError() {
+  g_cuda_device = cuda_device_;
+  std::vector<ObsErrors> recs;
+  if (!collectReprojectionErrors(*this, recs)) return std::numeric_limits<double>::quiet_NaN();
+  double total = 0.0;
+  for (const auto& r : recs) { double s = 0.0; for (double e : r.err) s += e; total += s / (double)r.err.size(); }
+  return recs.empty() ? 0.0 : total / (double)recs.size();
+}
+
+// reprojection_error_data.yml (McCalib.cpp:2251-2341): camera_group_G { frame_F { camera_C { nb_pts, error_list },
+// camera_list }, frame_list } with OpenCV-FileStorage matrices.
+bool Calibration::saveReprojectionErrorToFile(const std::string& path) {
+  g_cuda_device = cuda_device_;
+  std::vector<ObsErrors> recs;
+  if (!collectReprojectionErrors(*this, recs)) return false;
+  std::ofstream f(path);
+  if (!f) return false;
+  f.precision(9);
+  f << "%YAML:1.0\n---\nnb_camera_group: " << cam_group_.size() << "\n";
+  auto mat = [&](const char* indent, const char* name, const char* dt, const std::vector<double>& v) {
+    f << indent << name << ": !!opencv-matrix\n" << indent << "   rows: " << v.size() << "\n" << indent << "   cols: 1\n" << indent
+      << "   dt: " << dt << "\n" << indent << "   data: [ ";
+    for (size_t i = 0; i < v.size(); ++i) f << v[i] << (i + 1 < v.size() ? ", " : "");
+    f << " ]\n";
+  };
+  std::vector<double> frame_list;   // the reference never clears it between groups (McCalib.cpp:2255): kept
+  size_t k = 0;
+  for (const auto& it : cam_group_) {
+    f << "camera_group_" << it.second->cam_group_idx_ << ":\n";
+    while (k < recs.size() && recs[k].group == it.second->cam_group_idx_) {
+      const int frame = recs[k].frame;
+      f << "   frame_" << frame << ":\n";
+      frame_list.push_back(frame);
+      std::vector<double> camera_list;
+      for (; k < recs.size() && recs[k].group == it.second->cam_group_idx_ && recs[k].frame == frame; ++k) {
+        camera_list.push_back(recs[k].camera);
+        f << "      camera_" << recs[k].camera << ":\n         nb_pts: " << recs[k].err.size() << "\n";
+        mat("         ", "error_list", "f", recs[k].err);
+      }
+      mat("      ", "camera_list", "i", camera_list);
+    }
+    mat("   ", "frame_list", "i", frame_list);
+  }
+  return true;
+}
+
+// calibrated_objects_data.yml (McCalib.cpp:406-446): per object a 5 x N float matrix [X; Y; Z; board_id; pts_id].
+bool Calibration::save3DObj(const std::string& path) const {
+  std::ofstream f(path);
+  if (!f) return false;
+  f.precision(9);
+  f << "%YAML:1.0\n---\n";
+  for (const auto& it_obj : object_3d_) {
+    const Object3D& obj = *it_obj.second;
+    std::vector<std::array<float, 5>> cols;
+    for (const auto& it_board : obj.boards_) {
+      auto board = it_board.second.lock();
+      if (!board) continue;
+      for (size_t i = 0; i < board->pts_3d_.size(); ++i) {
+        const Point3f& p = obj.pts_3d_[obj.pts_board_2_obj_.at(std::make_pair(board->board_id_, (int)i))];
+        cols.push_back({p.x, p.y, p.z, (float)board->board_id_, (float)i});
+      }
+    }
+    f << "object_" << obj.obj_id_ << ":\n   points: !!opencv-matrix\n      rows: 5\n      cols: " << cols.size() << "\n      dt: f\n      data: [ ";
+    for (int r = 0; r < 5; ++r) for (size_t c = 0; c < cols.size(); ++c) f << cols[c][r] << ((r == 4 && c + 1 == cols.size()) ? "" : ", ");
+    f << " ]\n";
+  }
+  return true;
+}
+
+// calibrated_objects_pose_data.yml (McCalib.cpp:452-483): per object a 6 x N double matrix of Object3DObs::pose_.
+bool Calibration::save3DObjPose(const std::string& path) const {
+  std::ofstream f(path);
+  if (!f) return false;
+  f.precision(17);
+  f << "%YAML:1.0\n---\n";
+  for (const auto& it_obj : object_3d_) {
+    const Object3D& obj = *it_obj.second;
+    std::vector<Pose6> poses;
+    for (const auto& it_oo : obj.object_observations_) { auto oo = it_oo.second.lock(); if (oo) poses.push_back(oo->pose_); }
+    f << "object_" << obj.obj_id_ << ":\n   poses: !!opencv-matrix\n      rows: 6\n      cols: " << poses.size() << "\n      dt: d\n      data: [ ";
+    for (int r = 0; r < 6; ++r) for (size_t c = 0; c < poses.size(); ++c) f << poses[c][r] << ((r == 5 && c + 1 == poses.size()) ? "" : ", ");
+    f << " ]\n";
+  }
+  return true;
 }
 
 // The handful of keys of the reference's OpenCV-FileStorage YAML that the refinement path reads (McCalib.cpp:39-79):

@@ -129,7 +129,10 @@ public:
   void refineAllCameraGroupAndObjects();               // McCalib.cpp:1876-1887
   void refineAllCameraGroupAndObjectsAndIntrinsic();   // McCalib.cpp:2348-2359
   double computeAvgReprojectionError();                // McCalib.cpp:2168-2245 (mean of per-observation means)
-  bool saveCamerasParams(const std::string& path) const;   // calibrated_cameras_data.yml layout of McCalib.cpp:374-420
+  bool saveCamerasParams(const std::string& path) const;   // calibrated_cameras_data.yml layout of McCalib.cpp:374-404
+  bool save3DObj(const std::string& path) const;           // calibrated_objects_data.yml, McCalib.cpp:406-446
+  bool save3DObjPose(const std::string& path) const;       // calibrated_objects_pose_data.yml, McCalib.cpp:452-483
+  bool saveReprojectionErrorToFile(const std::string& path);   // reprojection_error_data.yml, McCalib.cpp:2251-2341
 };
 
 // pose helpers (Rodrigues both ways, composition), double precision

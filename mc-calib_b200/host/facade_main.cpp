@@ -113,5 +113,8 @@ int main(int argc, char** argv) {
   for (int k = 0; k < n_bo; ++k) { for (double x : calib.board_observations_[k]->pose_) out << x << " "; out << "\n"; }
   for (int k = 0; k < n_oo; ++k) { for (double x : calib.object_observations_[k]->pose_) out << x << " "; out << "\n"; }
   calib.saveCamerasParams(std::string(argv[3]) + ".cameras.yml");
+  calib.save3DObj(std::string(argv[3]) + ".objects.yml");
+  calib.save3DObjPose(std::string(argv[3]) + ".objects_pose.yml");
+  calib.saveReprojectionErrorToFile(std::string(argv[3]) + ".reprojection_error.yml");
   return 0;
 }

@@ -83,8 +83,42 @@ def test_final_bundle_adjustment_flow(tmp_path, scene):
     per_obs_key = np.repeat(key, np.diff(o.bobs_ptr))
     means = [err[per_obs_key == k].mean() for k in np.unique(per_obs_key)]
     assert abs(got["avg"] - np.mean(means)) <= 1e-3
-    txt = open(got["cameras_yml"]).read()
-    assert "camera_pose_matrix" in txt and "distortion_vector" in txt and txt.count("camera_") >= s.n_cam
+    # the output files are OpenCV-FileStorage YAML like the reference's savers: read them back with OpenCV itself
+    import cv2
+    base = got["cameras_yml"][:-len(".cameras.yml")]
+    fs = cv2.FileStorage(base + ".cameras.yml", cv2.FILE_STORAGE_READ)
+    assert int(fs.getNode("nb_camera").real()) == s.n_cam
+    for c in range(s.n_cam):
+        node = fs.getNode(f"camera_{c}")
+        K = node.getNode("camera_matrix").mat()
+        assert np.allclose([K[0, 0], K[1, 1], K[0, 2], K[1, 2]], p.intrinsics[c, :4], rtol=1e-8)
+        assert int(node.getNode("distortion_type").real()) == int(s.cam_model[c])
+        nd = 5 if s.cam_model[c] == 0 else 4
+        assert np.allclose(node.getNode("distortion_vector").mat().ravel(), p.intrinsics[c, 4:4 + nd], rtol=1e-7, atol=1e-12)
+        T = node.getNode("camera_pose_matrix").mat()       # inverse of relative_camera_pose_ (McCalib.cpp:398-399)
+        R = synth.Rot.from_rotvec(p.cam_pose[c, :3]).as_matrix()
+        Tf = np.eye(4); Tf[:3, :3] = R; Tf[:3, 3] = p.cam_pose[c, 3:]
+        assert np.allclose(T @ Tf, np.eye(4), atol=1e-9)
+    fs.release()
+    fs = cv2.FileStorage(base + ".objects.yml", cv2.FILE_STORAGE_READ)
+    pts = fs.getNode("object_0").getNode("points").mat()
+    assert pts.shape == (5, s.n_board * s.P) and set(np.unique(pts[3]).astype(int)) == set(range(s.n_board))
+    fs.release()
+    fs = cv2.FileStorage(base + ".objects_pose.yml", cv2.FILE_STORAGE_READ)
+    poses = fs.getNode("object_0").getNode("poses").mat()
+    assert poses.shape[0] == 6 and poses.shape[1] == len(np.unique(key))
+    fs.release()
+    fs = cv2.FileStorage(base + ".reprojection_error.yml", cv2.FILE_STORAGE_READ)
+    grp = fs.getNode("camera_group_0")
+    frames = grp.getNode("frame_list").mat().ravel()
+    assert len(frames) == len(np.unique(o.bobs_frame))
+    f0 = int(frames[0])
+    cams0 = grp.getNode(f"frame_{f0}").getNode("camera_list").mat().ravel()
+    c0 = int(cams0[0])
+    el = grp.getNode(f"frame_{f0}").getNode(f"camera_{c0}").getNode("error_list").mat().ravel()
+    want = err[per_obs_key == f0 * s.n_cam + c0]
+    assert len(el) == len(want) and np.abs(el - want).max() <= 1e-3
+    fs.release()
 
 
 def test_intrinsics_flow(tmp_path, scene, oracle):
