@@ -34,6 +34,10 @@ STAGE = 5
 BYTES_PER_OBS = {1: 277, 2: 229, 3: 229, 4: 325, 5: 469}       # materialising resid+Jac kernel
 FLOPS_PER_OBS = {4: 500 + 756, 5: 500 + 1620}                  # resid+Jac ~0.5 kFLOP + J^T J / J^T r
 FP64_PEAK_TFLOPS = 36.9    # measured on this pool's B200 with tools/peak_fp64.cu (DMMA m8n8k4), profiles/r01_peak_fp64.json
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the ncu --set full captures of this workload,
+# profiles/r01b_ncu_full_step_kernels.txt and profiles/r01b_ncu_full_materialize.txt (6.18 M observations per launch)
+NCU_TRAFFIC_FUSED = 77.2e6 + 604.3e6
+NCU_TRAFFIC_MATERIALIZE = 77.7e6 + 2716.7e6
 
 
 def bench_options(mcba, **kw):
@@ -334,13 +338,14 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
             "roofline": {"kernel": "k_observations<5,MODE_FUSED> (resid + Jacobian + J^T J/J^T r, DMMA)", "bound": "tensor",
                          "achieved": achieved_tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                         "frac": (achieved_tf / FP64_PEAK_TFLOPS) if achieved_tf else None, "traffic": None,
+                         "frac": (achieved_tf / FP64_PEAK_TFLOPS) if achieved_tf else None,
+                         "traffic": NCU_TRAFFIC_FUSED if fpg == FRAMES_PER_GPU else None,
                          "ms_per_launch": fused_avg_ms, "launches": fused_n,
                          "peak_source": "fp64 DMMA m8n8k4 peak measured with tools/peak_fp64.cu on this pool (profiles/r01_peak_fp64.json); MEASURED_PEAKS.json has no fp64 figure",
                          "algorithmic": f"{FLOPS_PER_OBS[STAGE]} FLOP/obs x {n_obs_local} obs per launch (SURVEY.md 8d)"},
             "roofline_hbm": {"kernel": "k_observations<5,MODE_MATERIALIZE> (resid + Jacobian written to HBM)", "bound": "hbm",
                              "achieved": mat_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": (mat_gbs / hbm_peak) if mat_gbs else None,
-                             "traffic": None, "ms_per_launch": mat_avg_ms, "launches": mat_n, "peak_source": hbm_src,
+                             "traffic": NCU_TRAFFIC_MATERIALIZE if fpg == FRAMES_PER_GPU else None, "ms_per_launch": mat_avg_ms, "launches": mat_n, "peak_source": hbm_src,
                              "algorithmic": f"{BYTES_PER_OBS[STAGE]} B/obs x {n_obs_local} obs per launch (SURVEY.md 8d)",
                              "readback_ms_per_launch": fromj_ms / max(1, fromj_n)},
             "kernel_ms_per_step": {k: v[1] / args.steps for k, v in stats.items() if v[0]},
