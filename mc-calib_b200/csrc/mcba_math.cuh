@@ -22,6 +22,15 @@
 
 namespace mcba {
 
+// IEEE-rounded reciprocal without the slow path of the generic fp64 division (device); plain division on the host
+MCBA_HD double rcp(double x) {
+#ifdef __CUDA_ARCH__
+  return __drcp_rn(x);
+#else
+  return 1.0 / x;
+#endif
+}
+
 // Local column order of a board observation's Jacobian: [cam pose 6][intrinsics 9][board 6] | [e-block 6] | [residual]
 template <int STAGE> struct StageTraits;
 template <> struct StageTraits<1> { static constexpr bool CAM = false, INTR = true,  BOARD = false; };
@@ -215,7 +224,11 @@ MCBA_HD void huber_weight(double a, double s, double& w, double& half_rho) {
   if (a > 0.0 && s > a * a) {
     const double r = sqrt(s);
     half_rho = 0.5 * (2.0 * a * r - a * a);
+#ifdef __CUDA_ARCH__
+    w = sqrt(a) * rsqrt(r);          // sqrt(a / r) with one dependent special-function op instead of div + sqrt
+#else
     w = sqrt(fmax(DBL_MIN, a / r));
+#endif
   } else {
     half_rho = 0.5 * s;
     w = 1.0;
@@ -229,7 +242,7 @@ MCBA_HD double obs_cost(const double* ctx, int model, const double* X0, double u
   mat3_vec_add(ctx + CTX_RB, X0, ctx + CTX_TB, X1);
   mat3_vec_add(ctx + CTX_RO, X1, ctx + CTX_TO, X2);
   mat3_vec_add(ctx + CTX_RC, X2, ctx + CTX_TC, X3);
-  const double iz = 1.0 / X3[2];
+  const double iz = rcp(X3[2]);
   Distort d;
   distort<false>(model, ctx + CTX_IN, X3[0] * iz, X3[1] * iz, d);
   const double* in = ctx + CTX_IN;
@@ -251,7 +264,7 @@ MCBA_HD double obs_jacobian(const double* ctx, bool act_c, bool act_b, int model
   mat3_vec_add(ctx + CTX_RB, X0, ctx + CTX_TB, X1);
   mat3_vec_add(ctx + CTX_RO, X1, ctx + CTX_TO, X2);
   mat3_vec_add(ctx + CTX_RC, X2, ctx + CTX_TC, X3);
-  const double iz = 1.0 / X3[2];
+  const double iz = rcp(X3[2]);
   const double a = X3[0] * iz, b = X3[1] * iz;
   Distort d;
   distort<true>(model, ctx + CTX_IN, a, b, d);
