@@ -76,7 +76,7 @@ struct Handle {
   // stage-dependent
   int Wc = 0, Wb = 0, n_f = 0, ldz = 0, n_pair = 0, n_chunks = 0, NT = 0, NE = 0, K = 0;
   int* d_pair_bobs = nullptr; PairChunk* d_chunks = nullptr; int* d_pair_chunk_ptr = nullptr;
-  double *d_brec = nullptr, *d_cost_bobs = nullptr, *d_Hoo = nullptr, *d_Wt = nullptr, *d_Z = nullptr, *d_L = nullptr;
+  double *d_brec = nullptr, *d_brec_alt = nullptr, *brec_target = nullptr, *d_cost_bobs = nullptr, *d_Hoo = nullptr, *d_Wt = nullptr, *d_Z = nullptr, *d_L = nullptr;
   double *d_scale_e = nullptr, *d_diag_e = nullptr, *d_scale_f = nullptr, *d_diag_f = nullptr;
   double *d_FF = nullptr, *d_gf = nullptr, *d_S = nullptr, *d_rhs = nullptr, *d_zf = nullptr, *d_ZtZ = nullptr, *d_hz = nullptr;
   double *d_syrk_partial = nullptr, *d_pair_partial = nullptr, *d_pair_rec = nullptr, *d_part_e = nullptr;
@@ -101,7 +101,7 @@ struct Handle {
   int rank = 0, n_ranks = 1; nccl_comm_t comm = nullptr;
   // LM state
   mcba_options opt;
-  bool solving = false, have_scale = false;
+  bool solving = false, have_scale = false, cand_has_jac = false;
   LmState lm;
   double ev_cost = 0, ev_x_norm = 0, ev_grad_max = 0;   // outputs of the last eval_jacobian
   mcba_summary summ;
@@ -223,7 +223,7 @@ static int setup_stage(Handle* H, int stage) {
   if (!chunks.empty()) CU(cudaMemcpy(H->d_chunks, chunks.data(), chunks.size() * sizeof(PairChunk), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(H->d_pair_chunk_ptr, pcp.data(), pcp.size() * sizeof(int), cudaMemcpyHostToDevice));
   const size_t np = H->n_pose, nf = H->n_f, ldz = H->ldz;
-  if (dalloc(H, &H->d_brec, (size_t)H->nb * H->NT * 64)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_brec, (size_t)H->nb * H->NT * 64) || dalloc(H, &H->d_brec_alt, (size_t)H->nb * H->NT * 64)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_cost_bobs, (size_t)H->nb)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_Hoo, np * 36) || dalloc(H, &H->d_L, np * 36)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_Wt, np * 6 * ldz) || dalloc(H, &H->d_Z, np * 6 * ldz)) return MCBA_ERR_CUDA;
@@ -281,7 +281,7 @@ static ObsArgs obs_args(Handle* H, int which, double huber_a) {
   a.u = H->d_u; a.v = H->d_v; a.pt = H->d_pt; a.pts = H->d_pts; a.bobs = H->d_bobs;
   a.prep_cam = H->d_prep_cam; a.prep_pose = H->d_prep_pose; a.prep_board = H->d_prep_board; a.intr = H->d_intr[which];
   a.cam_model = H->d_cam_model; a.cam_is_ref = H->d_cam_is_ref; a.board_is_ref = H->d_board_is_ref;
-  a.huber_a = huber_a; a.nb = H->nb; a.brec = H->d_brec; a.cost_bobs = H->d_cost_bobs;
+  a.huber_a = huber_a; a.nb = H->nb; a.brec = H->brec_target ? H->brec_target : H->d_brec; a.cost_bobs = H->d_cost_bobs;
   a.jmat = H->d_jmat; a.resmat = H->d_resmat; a.npad = H->npad; a.gate = H->obs_gate;
   return a;
 }
@@ -348,20 +348,30 @@ enum { SC_COST = 0, SC_XE2 = 1, SC_GMAX_E = 2, SC_F0 = 3 /*..6*/, SC_PE0 = 7 /*.
 
 static FState fstate(Handle* H, int which) { return FState{H->d_cam_pose[which], H->d_intr[which], H->d_board[which]}; }
 
-// Evaluate cost, gradient pieces and the normal-equation blocks at the current point (ProgramEvaluator::Evaluate
-// with Jacobian + what SchurEliminator needs from it).
-static int eval_jacobian(Handle* H, bool first) {
+// ProgramEvaluator::Evaluate with Jacobian, in two halves. eval_observations: residual + Jacobian + per-bobs J^T J
+// tiles at parameter copy `which`, written to `target` (the current tile set or the alternate one), and the cost.
+// eval_assemble: everything SchurEliminator and the trust-region loop need from the tiles of the *current* set.
+// The split lets the candidate point be evaluated with its Jacobian straight away (the cost comes with it): when
+// the step is accepted - the usual case - the tiles are simply swapped in instead of running a cost-only pass
+// followed by a second, full pass at the same point as Ceres does; a rejected step leaves the current set untouched.
+static int eval_observations(Handle* H, int which, double* target) {
+  int rc;
+  if ((rc = launch_prep(H, which))) return rc;
+  H->brec_target = target;
+  if (H->opt.materialize_jacobian) {
+    if (!(rc = ensure_jmat(H)) && !(rc = launch_obs<MODE_MATERIALIZE>(H, which, H->opt.huber_a)))
+      rc = launch_obs<MODE_FROM_J>(H, which, H->opt.huber_a);
+  } else {
+    rc = launch_obs<MODE_FUSED>(H, which, H->opt.huber_a);
+  }
+  H->brec_target = nullptr;
+  if (rc) return rc;
+  return reduce_rows(H, H->d_cost_bobs, H->nb, 1, 1, H->d_scalars + SC_COST);
+}
+
+static int eval_assemble(Handle* H, bool first) {
   int rc;
   const StageDims sd = stage_dims(H->stage);
-  if ((rc = launch_prep(H, H->cur))) return rc;
-  if (H->opt.materialize_jacobian) {
-    if ((rc = ensure_jmat(H))) return rc;
-    if ((rc = launch_obs<MODE_MATERIALIZE>(H, H->cur, H->opt.huber_a))) return rc;
-    if ((rc = launch_obs<MODE_FROM_J>(H, H->cur, H->opt.huber_a))) return rc;
-  } else {
-    if ((rc = launch_obs<MODE_FUSED>(H, H->cur, H->opt.huber_a))) return rc;
-  }
-  if ((rc = reduce_rows(H, H->d_cost_bobs, H->nb, 1, 1, H->d_scalars + SC_COST))) return rc;
   if (H->n_pose > 0) {
     Timed t(H, KF_EASSEMBLE);
     ++H->n_launches;
@@ -427,6 +437,11 @@ static int eval_jacobian(Handle* H, bool first) {
   H->ev_grad_max = gmax;
   if (!std::isfinite(cost)) return MCBA_ERR_NUMERIC;
   return MCBA_OK;
+}
+
+static int eval_jacobian(Handle* H, bool first) {
+  const int rc = eval_observations(H, H->cur, H->d_brec);
+  return rc ? rc : eval_assemble(H, first);
 }
 
 static int cholesky_reduced(Handle* H) {
@@ -495,10 +510,9 @@ static int compute_step(Handle* H, LmStep* out) {
     CHECK_LAUNCH();
   }
   if ((rc = reduce_rows(H, H->d_part_e, H->n_pose, 4, 4, H->d_scalars + SC_PE0))) return rc;
-  // candidate cost
-  if ((rc = launch_prep(H, cand))) return rc;
-  if ((rc = launch_obs<MODE_COST>(H, cand, H->opt.huber_a))) return rc;
-  if ((rc = reduce_rows(H, H->d_cost_bobs, H->nb, 1, 1, H->d_scalars + SC_COST))) return rc;
+  // candidate point: residual + Jacobian tiles into the alternate set (the cost comes with them), see eval_observations
+  if ((rc = eval_observations(H, cand, H->d_brec_alt))) return rc;
+  H->cand_has_jac = true;
   std::vector<double> hs;
   ++H->n_launches;
   k_flag_to_scalar<<<1, 1, 0, H->stream>>>(H->d_fail, H->d_scalars + SC_FAIL);
@@ -604,7 +618,7 @@ void mcba_destroy(void* h) {
   dfree(&H->d_u); dfree(&H->d_v); dfree(&H->d_pt); dfree(&H->d_pts); dfree(&H->d_bobs); dfree(&H->d_pose_bobs_ptr);
   dfree(&H->d_cam_model); dfree(&H->d_cam_is_ref); dfree(&H->d_board_is_ref);
   dfree(&H->d_pair_bobs); dfree(&H->d_chunks); dfree(&H->d_pair_chunk_ptr);
-  dfree(&H->d_brec); dfree(&H->d_cost_bobs); dfree(&H->d_Hoo); dfree(&H->d_Wt); dfree(&H->d_Z); dfree(&H->d_L);
+  dfree(&H->d_brec); dfree(&H->d_brec_alt); dfree(&H->d_cost_bobs); dfree(&H->d_Hoo); dfree(&H->d_Wt); dfree(&H->d_Z); dfree(&H->d_L);
   dfree(&H->d_scale_e); dfree(&H->d_diag_e); dfree(&H->d_scale_f); dfree(&H->d_diag_f);
   dfree(&H->d_FF); dfree(&H->d_gf); dfree(&H->d_S); dfree(&H->d_rhs); dfree(&H->d_zf); dfree(&H->d_ZtZ); dfree(&H->d_hz);
   dfree(&H->d_syrk_partial); dfree(&H->d_pair_partial); dfree(&H->d_pair_rec); dfree(&H->d_part_e);
@@ -783,13 +797,15 @@ int mcba_solve_step(void* h) {
                 row.step_norm, row.relative_decrease, row.trust_region_radius);
   if (!cont) return 0;
   LmStep so;
+  H->cand_has_jac = false;
   int rc = compute_step(H, &so);
   if (rc) return rc;
   const int d = lm_decide(H->lm, H->opt, so);
   if (d == LM_TERMINATED) return 0;
   if (d == LM_ACCEPT) {   // HandleSuccessfulStep
     H->cur = 1 - H->cur;
-    rc = eval_jacobian(H, false);
+    if (H->cand_has_jac) { std::swap(H->d_brec, H->d_brec_alt); rc = eval_assemble(H, false); }
+    else rc = eval_jacobian(H, false);
     if (rc == MCBA_ERR_NUMERIC) { H->lm.termination = MCBA_FAILURE; H->lm.done = 1; return 0; }
     if (rc) return rc;
     lm_accepted_eval(H->lm, H->opt, H->ev_cost, H->ev_grad_max);
