@@ -231,13 +231,14 @@ static int setup_stage(Handle* H, int stage) {
   if (dalloc(H, &H->d_scale_f, nf) || dalloc(H, &H->d_diag_f, nf)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_FF, nf * nf) || dalloc(H, &H->d_gf, nf) || dalloc(H, &H->d_S, (nf + 1) * nf)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_hz, nf) || dalloc(H, &H->d_rhs, nf) || dalloc(H, &H->d_zf, nf) || dalloc(H, &H->d_ZtZ, ldz * ldz)) return MCBA_ERR_CUDA;
+  CU(cudaMemset(H->d_ZtZ, 0, ldz * ldz * sizeof(double)));   // the lower triangle is never written
   H->syrk_nt = (H->ldz + SY_T - 1) / SY_T;
   H->syrk_tiles = H->syrk_nt * (H->syrk_nt + 1) / 2;
   const int64_t n_rows = 6 * (int64_t)H->n_pose;
-  int syrk_per_sm = 4;
+  int syrk_per_sm = 1;
   CU(cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM));
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&syrk_per_sm, k_syrk, 128, SY_SMEM);
-  int nsplit = std::max(1, (std::max(1, syrk_per_sm) * H->n_sm) / H->syrk_tiles);   // one full wave of CTAs, no tail
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&syrk_per_sm, k_syrk, SY_THREADS, SY_SMEM);
+  int nsplit = std::max(1, (2 * std::max(1, syrk_per_sm) * H->n_sm) / H->syrk_tiles);   // about two full waves of equal CTAs
   nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(nsplit, (n_rows + 63) / 64));
   H->syrk_rows_per_split = (((n_rows + nsplit - 1) / nsplit + SY_K - 1) / SY_K) * SY_K;
   if (H->syrk_rows_per_split == 0) H->syrk_rows_per_split = SY_K;
@@ -482,9 +483,9 @@ static int compute_step(Handle* H, LmStep* out) {
     Timed t(H, KF_SYRK);
     dim3 grid(H->syrk_tiles, H->syrk_nsplit);
     ++H->n_launches;
-    k_syrk<<<grid, 128, SY_SMEM, H->stream>>>(H->d_Z, 6 * (int64_t)H->n_pose, H->ldz, H->syrk_nt, H->syrk_rows_per_split, H->d_syrk_partial);
+    k_syrk<<<grid, SY_THREADS, SY_SMEM, H->stream>>>(H->d_Z, 6 * (int64_t)H->n_pose, H->ldz, H->syrk_nt, H->syrk_rows_per_split, H->d_syrk_partial);
     ++H->n_launches;
-    k_syrk_sum<<<H->syrk_tiles, 256, 0, H->stream>>>(H->d_syrk_partial, H->syrk_tiles, H->syrk_nt, H->syrk_nsplit, H->ldz, H->d_ZtZ);
+    k_syrk_sum<<<dim3(H->syrk_tiles, 8), 256, 0, H->stream>>>(H->d_syrk_partial, H->syrk_tiles, H->syrk_nt, H->syrk_nsplit, H->ldz, H->d_ZtZ);
     CHECK_LAUNCH();
   }
   if ((rc = allreduce_sum(H, H->d_ZtZ, (size_t)H->ldz * H->ldz))) return rc;

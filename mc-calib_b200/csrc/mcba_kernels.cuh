@@ -455,8 +455,8 @@ __global__ void __launch_bounds__(128) k_eblock_factor(const double* __restrict_
 
 // K2d: C = Z^T Z restricted to upper tile pairs, split over row ranges. 64x64 tile per CTA, 4 warps (2x2),
 // each warp 32x32 = 4x4 DMMA tiles; K chunk of 16 rows staged through shared memory with register prefetch.
-constexpr int SY_T = 64, SY_K = 32, SY_LD = 68, SY_STAGES = 3;
-constexpr int SY_SMEM = SY_STAGES * 2 * SY_K * SY_LD * 8;   // dynamic shared memory of k_syrk
+constexpr int SY_T = 128, SY_K = 32, SY_LD = SY_T + 4, SY_STAGES = 3, SY_THREADS = 256;
+constexpr int SY_SMEM = SY_STAGES * 2 * SY_K * SY_LD * 8;   // dynamic shared memory of k_syrk (202,752 B: one CTA per SM)
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {   // src_bytes 0 -> zero fill
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
@@ -464,28 +464,30 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// 64x64 output tile per CTA, 4 warps (2x2) of 32x32 = 4x4 DMMA tiles each; rows of Z stream through a 3-stage
-// cp.async ring of 32-row chunks (one barrier per 128 DMMAs per warp, loads two chunks ahead of the math).
-__global__ void __launch_bounds__(128) k_syrk(const double* __restrict__ Z, int64_t n_rows, int ldz, int nt,
-                                              int64_t rows_per_split, double* __restrict__ partial) {
+// 128x128 output tile per CTA (halves the L2 traffic of a 64x64 tiling: every CTA streams its two 128-column strips
+// of Z), 8 warps (4x2) of 32x64 = 4x8 DMMA tiles each; rows of Z stream through a 3-stage cp.async ring of 32-row
+// chunks (one barrier per 256 DMMAs per warp, loads two chunks ahead of the math). On diagonal tiles the B strip is
+// the A strip and warps entirely below the diagonal skip the math.
+__global__ void __launch_bounds__(SY_THREADS) k_syrk(const double* __restrict__ Z, int64_t n_rows, int ldz, int nt,
+                                                     int64_t rows_per_split, double* __restrict__ partial) {
   extern __shared__ __align__(16) double sy_sm[];
-  // tile pair from linear index (ti <= tj)
-  int ti = 0, rem = blockIdx.x;
+  int ti = 0, rem = blockIdx.x;   // tile pair from linear index (ti <= tj)
   while (rem >= nt - ti) { rem -= nt - ti; ++ti; }
   const int tj = ti + rem;
   const int split = blockIdx.y;
   const int64_t r0 = (int64_t)split * rows_per_split, r1 = min(n_rows, r0 + rows_per_split);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
-  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 64;
   const bool diag = (ti == tj);
-  double acc[4][4][2];
+  const bool skip = diag && (wm >= wn + 64);   // warp tile strictly below the diagonal of a diagonal tile
+  double acc[4][8][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
   const int n_chunks = (r1 > r0) ? (int)((r1 - r0 + SY_K - 1) / SY_K) : 0;
-  // per-thread copy slots: SY_K rows x 64 cols = SY_K*32 16-byte pieces per operand, SY_K/4 per thread
-  const int c2 = (tid & 31) * 2, row0 = tid >> 5;            // piece i: row = row0 + 4 i
+  // per-thread copy slots: SY_K rows x 128 cols = SY_K*64 16-byte pieces per operand, SY_K/4 per thread
+  const int c2 = (tid & 63) * 2, row0 = tid >> 6;            // piece i: row = row0 + 4 i
   const bool ca_ok = ti * SY_T + c2 < ldz, cb_ok = tj * SY_T + c2 < ldz;
   const double* ga = Z + (r0 + row0) * ldz + ti * SY_T + c2;
   const double* gb = Z + (r0 + row0) * ldz + tj * SY_T + c2;
@@ -512,19 +514,20 @@ __global__ void __launch_bounds__(128) k_syrk(const double* __restrict__ Z, int6
     cp_async_wait<SY_STAGES - 2>();
     __syncthreads();
     issue(chunk + SY_STAGES - 1);
+    if (skip) continue;
     const double* As = sy_sm + (size_t)(chunk % SY_STAGES) * (2 * SY_K * SY_LD);
     const double* Bp = diag ? As : As + SY_K * SY_LD;
 #pragma unroll
     for (int ks = 0; ks < SY_K / 4; ++ks) {
-      double fa[4], fb[4];
+      double fa[4], fb[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) fa[i] = As[(4 * ks + q) * SY_LD + wm + 8 * i + g];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) fb[j] = Bp[(4 * ks + q) * SY_LD + wn + 8 * j + g];
+      for (int j = 0; j < 8; ++j) fb[j] = Bp[(4 * ks + q) * SY_LD + wn + 8 * j + g];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+        for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
     }
   }
   cp_async_wait<0>();
@@ -532,7 +535,7 @@ __global__ void __launch_bounds__(128) k_syrk(const double* __restrict__ Z, int6
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 8; ++j)
       *reinterpret_cast<double2*>(out + (wm + 8 * i + g) * SY_T + wn + 8 * j + 2 * q) = make_double2(acc[i][j][0], acc[i][j][1]);
 }
 // Fixed-order sum of the split-K partials into the dense upper part of ZtZ (ldz x ldz).
@@ -542,9 +545,9 @@ __global__ void k_syrk_sum(const double* __restrict__ partial, int n_tiles, int 
   int ti = 0, rem = tile;
   while (rem >= nt - ti) { rem -= nt - ti; ++ti; }
   const int tj = ti + rem;
-  for (int e = threadIdx.x; e < SY_T * SY_T; e += blockDim.x) {
+  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < SY_T * SY_T; e += gridDim.y * blockDim.x) {
     const int i = ti * SY_T + e / SY_T, j = tj * SY_T + e % SY_T;
-    if (i >= ldz || j >= ldz) continue;
+    if (i >= ldz || j >= ldz || j < i) continue;   // only the upper triangle is consumed
     double s = 0.0;
     for (int sp = 0; sp < nsplit; ++sp) s += partial[((size_t)sp * n_tiles + tile) * (SY_T * SY_T) + e];
     ZtZ[(size_t)i * ldz + j] = s;
