@@ -146,16 +146,16 @@ template <typename T> static int dalloc(Handle* H, T** p, size_t n) {
 }
 template <typename T> static void dfree(T** p) { if (*p) { cudaFree(*p); *p = nullptr; } }
 
-struct StageDims { bool cam, intr, board; int K, NT, NE, WF; };
+struct StageDims { bool cam, intr, board; int K, NT, NE, WF, NCOMP; };
 static StageDims stage_dims(int stage) {
   switch (stage) {
-    case 1: return {false, true, false, Cols<1>::K, Cols<1>::NT, PairRec<1>::NE, Cols<1>::WF};
-    case 2: return {false, false, true, Cols<2>::K, Cols<2>::NT, PairRec<2>::NE, Cols<2>::WF};
-    case 3: return {true, false, false, Cols<3>::K, Cols<3>::NT, PairRec<3>::NE, Cols<3>::WF};
-    case 4: return {true, false, true, Cols<4>::K, Cols<4>::NT, PairRec<4>::NE, Cols<4>::WF};
-    case 5: return {true, true, true, Cols<5>::K, Cols<5>::NT, PairRec<5>::NE, Cols<5>::WF};
+    case 1: return {false, true, false, Cols<1>::K, Cols<1>::NT, PairRec<1>::NE, Cols<1>::WF, Cols<1>::NCOMP};
+    case 2: return {false, false, true, Cols<2>::K, Cols<2>::NT, PairRec<2>::NE, Cols<2>::WF, Cols<2>::NCOMP};
+    case 3: return {true, false, false, Cols<3>::K, Cols<3>::NT, PairRec<3>::NE, Cols<3>::WF, Cols<3>::NCOMP};
+    case 4: return {true, false, true, Cols<4>::K, Cols<4>::NT, PairRec<4>::NE, Cols<4>::WF, Cols<4>::NCOMP};
+    case 5: return {true, true, true, Cols<5>::K, Cols<5>::NT, PairRec<5>::NE, Cols<5>::WF, Cols<5>::NCOMP};
   }
-  return {false, false, false, 0, 0, 0, 0};
+  return {false, false, false, 0, 0, 0, 0, 0};
 }
 
 #define DISPATCH_STAGE(stage, ...)                    \
@@ -223,7 +223,7 @@ static int setup_stage(Handle* H, int stage) {
   if (!chunks.empty()) CU(cudaMemcpy(H->d_chunks, chunks.data(), chunks.size() * sizeof(PairChunk), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(H->d_pair_chunk_ptr, pcp.data(), pcp.size() * sizeof(int), cudaMemcpyHostToDevice));
   const size_t np = H->n_pose, nf = H->n_f, ldz = H->ldz;
-  if (dalloc(H, &H->d_brec, (size_t)H->nb * H->NT * 64) || dalloc(H, &H->d_brec_alt, (size_t)H->nb * H->NT * 64)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_brec, (size_t)H->nb * sd.NCOMP) || dalloc(H, &H->d_brec_alt, (size_t)H->nb * sd.NCOMP)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_cost_bobs, (size_t)H->nb)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_Hoo, np * 36) || dalloc(H, &H->d_L, np * 36)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_Wt, np * 6 * ldz) || dalloc(H, &H->d_Z, np * 6 * ldz)) return MCBA_ERR_CUDA;
@@ -1020,7 +1020,7 @@ int mcba_debug_fetch(void* h, const char* name, double* out, int64_t cap, int64_
   else if (s == "S") { src = H->d_S; n = nf * nf; } else if (s == "rhs") { src = H->d_rhs; n = nf; }
   else if (s == "zf") { src = H->d_zf; n = nf; } else if (s == "ZtZ") { src = H->d_ZtZ; n = ldz * ldz; }
   else if (s == "Hoo") { src = H->d_Hoo; n = np * 36; } else if (s == "Wt") { src = H->d_Wt; n = np * 6 * ldz; }
-  else if (s == "Z") { src = H->d_Z; n = np * 6 * ldz; } else if (s == "brec") { src = H->d_brec; n = (int64_t)H->nb * H->NT * 64; }
+  else if (s == "Z") { src = H->d_Z; n = np * 6 * ldz; } else if (s == "brec") { src = H->d_brec; n = (int64_t)H->nb * stage_dims(H->stage).NCOMP; }
   else if (s == "scale_e") { src = H->d_scale_e; n = np * 6; } else if (s == "scale_f") { src = H->d_scale_f; n = nf; }
   else if (s == "diag_e") { src = H->d_diag_e; n = np * 6; } else if (s == "diag_f") { src = H->d_diag_f; n = nf; }
   else { H->err = "unknown buffer"; return MCBA_ERR_INVALID; }

@@ -13,11 +13,9 @@
 
 namespace mcba {
 
-typedef Cols<1> C1;   // local columns: intrinsics 0..8 | e-block 9..14 | residual 15 ; 2 column blocks, 3 tiles
-constexpr int B_REC = C1::NT * 64;
-__device__ __forceinline__ int b_off(int a, int b) {   // a <= b
-  return tile_index(a >> 3, b >> 3, C1::NBLK) * 64 + (a & 7) * 8 + (b & 7);
-}
+typedef Cols<1> C1;   // local columns: intrinsics 0..8 | e-block 9..14 | residual 15
+constexpr int B_REC = C1::NCOMP;
+__device__ __forceinline__ int b_off(int a, int b) { return C1::cidx(a, b); }   // a <= b, index in the compact record
 // per-camera scalar slots
 enum { BC_COST = 0, BC_XE2, BC_GMAX, BC_ZG, BC_ZHZ, BC_SN, BC_XN, BC_FAIL, BC_N };
 

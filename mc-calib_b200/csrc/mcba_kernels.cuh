@@ -36,7 +36,7 @@ struct ObsArgs {
   const int32_t* cam_model; const uint8_t* cam_is_ref; const uint8_t* board_is_ref;
   double huber_a;
   int nb;
-  double* brec;                     // [nb][NT*64] per-bobs J^T J tiles
+  double* brec;                     // [nb][NCOMP] per-bobs J~^T J~, compact (Cols<STAGE>::cidx)
   double* cost_bobs;                // [nb]
   double* jmat; double* resmat;     // materialised Jacobian blocks (see BlockSink); resmat unused
   int64_t npad;
@@ -194,10 +194,19 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, (MODE == MODE_FUSED || MODE ==
       }
     }
     if (ACC) {
-      double* out = a.brec + (size_t)b * (C::NT * 64);
+      double* out = a.brec + (size_t)b * C::NCOMP;
+      int t = 0;
 #pragma unroll
-      for (int t = 0; t < C::NT; ++t)
-        *reinterpret_cast<double2*>(out + t * 64 + lane * 2) = make_double2(acc[t][0], acc[t][1]);
+      for (int bi = 0; bi < C::NBLK; ++bi)
+#pragma unroll
+        for (int bj = bi; bj < C::NBLK; ++bj) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int ea = 8 * bi + g, eb = 8 * bj + 2 * q + h;
+            if (ea <= eb && eb < C::NC) { const int ci = C::cidx(ea, eb); if (ci >= 0) out[ci] = acc[t][h]; }
+          }
+          ++t;
+        }
     }
     if (MODE != MODE_FROM_J) {
 #pragma unroll
@@ -279,26 +288,23 @@ __global__ void __launch_bounds__(192) k_eblock_assemble(const int4* __restrict_
   const int b0 = pose_bobs_ptr[o], b1 = pose_bobs_ptr[o + 1];
   if (tid < 6 * C::WF) {
     const int k = tid / C::WF, j = tid % C::WF;           // e-row k, local f column j
-    const int ecol = C::E0 + k;
-    const int off = tile_index(j >> 3, ecol >> 3, C::NBLK) * 64 + (j & 7) * 8 + (ecol & 7);
+    const int off = C::cidx(j, C::E0 + k);
     for (int b = b0; b < b1; ++b) {
       const int4 rec = bobs[b];
       const int gcol = (j < C::B0) ? rec.y * Wc + j : n_cam * Wc + rec.w * Wb + (j - C::B0);
-      W[k * ldz + gcol] += brec[(size_t)b * (C::NT * 64) + off];
+      W[k * ldz + gcol] += brec[(size_t)b * C::NCOMP + off];
     }
   } else if (tid < 6 * C::WF + 36) {
     const int e = tid - 6 * C::WF, p = e / 6, r = e % 6;
-    const int lo = C::E0 + min(p, r), hi = C::E0 + max(p, r);
-    const int off = tile_index(lo >> 3, hi >> 3, C::NBLK) * 64 + (lo & 7) * 8 + (hi & 7);
+    const int off = C::cidx(C::E0 + min(p, r), C::E0 + max(p, r));
     double s = 0.0;
-    for (int b = b0; b < b1; ++b) s += brec[(size_t)b * (C::NT * 64) + off];
+    for (int b = b0; b < b1; ++b) s += brec[(size_t)b * C::NCOMP + off];
     Hoo[(size_t)o * 36 + e] = s;
   } else if (tid < 6 * C::WF + 42) {
     const int k = tid - 6 * C::WF - 36;
-    const int ecol = C::E0 + k;
-    const int off = tile_index(ecol >> 3, C::R0 >> 3, C::NBLK) * 64 + (ecol & 7) * 8 + (C::R0 & 7);
+    const int off = C::cidx(C::E0 + k, C::R0);
     double s = 0.0;
-    for (int b = b0; b < b1; ++b) s += brec[(size_t)b * (C::NT * 64) + off];
+    for (int b = b0; b < b1; ++b) s += brec[(size_t)b * C::NCOMP + off];
     W[k * ldz + n_f] = s;
   }
   __syncthreads();
@@ -324,16 +330,10 @@ __global__ void __launch_bounds__(256) k_pair_reduce(const PairChunk* __restrict
   typedef PairRec<STAGE> PR;
   const int t = threadIdx.x;
   if (t >= PR::NE) return;
-  int a, b;
-  if (t < PR::NFF) {   // invert the triangular index
-    a = 0; int rem = t;
-    while (rem >= C::WF - a) { rem -= C::WF - a; ++a; }
-    b = a + rem;
-  } else { a = t - PR::NFF; b = C::R0; }
-  const int off = tile_index(a >> 3, b >> 3, C::NBLK) * 64 + (a & 7) * 8 + (b & 7);
+  // entry t of a pair record is entry t of the compact per-bobs record (f x f upper, then f x r): contiguous reads
   const PairChunk ch = chunks[blockIdx.x];
   double s = 0.0;
-  for (int i = ch.begin; i < ch.end; ++i) s += brec[(size_t)pair_bobs[i] * (C::NT * 64) + off];
+  for (int i = ch.begin; i < ch.end; ++i) s += brec[(size_t)pair_bobs[i] * C::NCOMP + t];
   partial[(size_t)blockIdx.x * PR::NE + t] = s;
 }
 template <int STAGE>

@@ -50,6 +50,18 @@ template <int STAGE> struct Cols {
   static constexpr int NBLK = (NC + 7) / 8;                 // 8-wide column blocks
   static constexpr int NT = NBLK * (NBLK + 1) / 2;          // upper-triangle 8x8 tiles
   static constexpr int K = WF + 6;                          // Jacobian width (reference: 15,12,12,18,27)
+  // Compact per-bobs record of J~^T J~ (only what is consumed, in the order the consumers read it):
+  //   [ f x f upper (NFF) | f x r (WF) | f x e (6 WF) | e x e upper (21) | e x r (6) ]
+  // The per-pair reduction reads the first NFF + WF doubles contiguously, the e-block assembly the rest.
+  static constexpr int NFF = WF * (WF + 1) / 2;
+  static constexpr int CI_FR = NFF, CI_FE = NFF + WF, CI_EE = CI_FE + 6 * WF, CI_ER = CI_EE + 21, NCOMP = CI_ER + 6;
+  MCBA_HD static int cidx(int a, int b) {                   // entry (a <= b) -> index in the compact record, -1 if unused
+    if (b < WF) return a * WF - a * (a - 1) / 2 + (b - a);
+    if (b == R0) return a < WF ? CI_FR + a : (a < R0 ? CI_ER + (a - E0) : -1);
+    if (a < WF) return CI_FE + a * 6 + (b - E0);
+    const int p = a - E0, r = b - E0;
+    return CI_EE + p * 6 - p * (p - 1) / 2 + (r - p);
+  }
   // reference parameter-block order at the call sites (Camera.cpp:290, Object3D.cpp:208-209,
   // CameraGroup.cpp:253-256, :445-451, :553-560): [cam][pose][board][intr] with absent blocks removed
   static constexpr int REF_C = 0;
