@@ -35,9 +35,9 @@ BYTES_PER_OBS = {1: 277, 2: 229, 3: 229, 4: 325, 5: 469}       # SURVEY.md §8(d
 FLOPS_PER_OBS = {4: 500 + 756, 5: 500 + 1620}                  # resid+Jac ~0.5 kFLOP + J^T J / J^T r
 FP64_PEAK_TFLOPS = 36.9    # measured on this pool's B200 with tools/peak_fp64.cu (DMMA m8n8k4), profiles/r01_peak_fp64.json
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the ncu --set full captures of this workload,
-# profiles/r01b_ncu_full_step_kernels.txt and profiles/r01b_ncu_full_materialize.txt (6.18 M observations per launch)
-NCU_TRAFFIC_FUSED = 77.2e6 + 604.3e6
-NCU_TRAFFIC_MATERIALIZE = 77.7e6 + 2716.7e6
+# profiles/r01c_ncu_full_step_kernels.txt and profiles/r01c_ncu_full_materialize.txt (6.18 M observations per launch)
+NCU_TRAFFIC_FUSED = 77.2e6 + 361.6e6
+NCU_TRAFFIC_MATERIALIZE = 77.6e6 + 2712.9e6
 
 
 def bench_options(mcba, **kw):
