@@ -762,6 +762,19 @@ int mcba_comm_init(void* h, int rank, int n_ranks, const void* uid) {
   CU(cudaMemcpyAsync(&n_glob, H->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, H->stream));
   CU(cudaStreamSynchronize(H->stream));
   H->n_obs_global = (int64_t)(n_glob + 0.5);
+  // NCCL sets up its channels for a message size on first use (~100 ms for the 8 MB reduced-system allreduce):
+  // pay that here, once per communicator, not inside the first LM iteration.
+  if (!H->batched) {
+    CU(cudaMemsetAsync(H->d_ZtZ, 0, (size_t)H->ldz * H->ldz * sizeof(double), H->stream));
+    CU(cudaMemsetAsync(H->d_pair_rec, 0, (size_t)H->n_pair * H->NE * sizeof(double), H->stream));
+    int rc;
+    if ((rc = allreduce_sum(H, H->d_ZtZ, (size_t)H->ldz * H->ldz))) return rc;
+    if ((rc = allreduce_sum(H, H->d_pair_rec, (size_t)H->n_pair * H->NE))) return rc;
+    std::vector<double> hs;
+    if ((rc = gather_scalars(H, H->d_scalars, SC_N, hs))) return rc;
+    flush_timers(H);
+    for (int k = 0; k < KF_COUNT; ++k) { H->kf_launches[k] = 0; H->kf_ms[k] = 0; }
+  }
   return MCBA_OK;
 }
 
