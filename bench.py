@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 0)
+    args.warmup = max(args.warmup, 3)   # timing hygiene: never fewer than 3 untimed iterations (the JSON reports the count actually run)
     if args.impl == "reference":
         run_reference(args)
         return
