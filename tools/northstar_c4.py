@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--frames", type=int, default=20000)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--out", required=True)
+    ap.add_argument("--warm", action="store_true", help="solve every stage once untimed first (kernel modules, NCCL channels)")
     args = ap.parse_args()
     import mcba
     from mcba import synth
@@ -46,7 +47,7 @@ def main():
     prob, init, gt = synth.make_problem(s, o, 4)
     p = init.copy()
     p.intrinsics[:] = s.intr_init
-    doc = dict(impl=args.impl, frames=args.frames, world=world, gen_s=t_gen, stages=[])
+    doc = dict(impl=args.impl, frames=args.frames, world=world, gen_s=t_gen, warm=bool(args.warm), stages=[])
     if args.impl == "mcba":
         import torch
         import torch.distributed as dist
@@ -71,6 +72,8 @@ def main():
         for stage in (4, 5):
             if stage == 5:
                 h.set_stage(5)
+            if args.warm:
+                h.solve(p.copy())
             h.reset_kernel_stats()
             torch.cuda.synchronize()
             if world > 1:
