@@ -99,6 +99,12 @@ struct Handle {
   int cur = 0;
   // comm
   int rank = 0, n_ranks = 1; nccl_comm_t comm = nullptr;
+  // peer-memory path of the Schur reduction (k_syrk_sum_p2p)
+  bool p2p = false; unsigned long long p2p_epoch = 0;
+  unsigned long long* d_p2p_flags = nullptr; unsigned int* d_p2p_counter = nullptr; int* d_p2p_err = nullptr;
+  double* d_p2p_stage = nullptr;
+  double* peer_stage[P2P_MAX_RANKS] = {nullptr}; double* peer_ZtZ[P2P_MAX_RANKS] = {nullptr}; unsigned long long* peer_flags[P2P_MAX_RANKS] = {nullptr};
+  std::vector<void*> ipc_opened;
   // LM state
   mcba_options opt;
   bool solving = false, have_scale = false, cand_has_jac = false;
@@ -485,10 +491,19 @@ static int compute_step(Handle* H, LmStep* out) {
     ++H->n_launches;
     k_syrk<<<grid, SY_THREADS, SY_SMEM, H->stream>>>(H->d_Z, 6 * (int64_t)H->n_pose, H->ldz, H->syrk_nt, H->syrk_rows_per_split, H->d_syrk_partial);
     ++H->n_launches;
-    k_syrk_sum<<<dim3(H->syrk_tiles, 8), 256, 0, H->stream>>>(H->d_syrk_partial, H->syrk_tiles, H->syrk_nt, H->syrk_nsplit, H->ldz, H->d_ZtZ);
+    if (H->p2p) {   // split-K sum + cross-GPU reduction in one kernel over NVLink peer memory
+      P2PArgs pa;
+      for (int r = 0; r < P2P_MAX_RANKS; ++r) { pa.stage[r] = H->peer_stage[r]; pa.ZtZ[r] = H->peer_ZtZ[r]; pa.flags[r] = H->peer_flags[r]; }
+      pa.partial = H->d_syrk_partial; pa.nsplit = H->syrk_nsplit;
+      pa.rank = H->rank; pa.n_ranks = H->n_ranks; pa.epoch = ++H->p2p_epoch; pa.n_tiles = H->syrk_tiles; pa.nt = H->syrk_nt; pa.ldz = H->ldz;
+      pa.counter = H->d_p2p_counter; pa.err = H->d_p2p_err;
+      k_syrk_sum_p2p<<<2 * H->n_sm, 256, 0, H->stream>>>(pa);   // co-resident by construction: 2 CTAs of 256 threads per SM
+    } else {
+      k_syrk_sum<<<dim3(H->syrk_tiles, 8), 256, 0, H->stream>>>(H->d_syrk_partial, H->syrk_tiles, H->syrk_nt, H->syrk_nsplit, H->ldz, H->d_ZtZ);
+    }
     CHECK_LAUNCH();
   }
-  if ((rc = allreduce_sum(H, H->d_ZtZ, (size_t)H->ldz * H->ldz))) return rc;
+  if (!H->p2p && (rc = allreduce_sum(H, H->d_ZtZ, (size_t)H->ldz * H->ldz))) return rc;
   {
     Timed t(H, KF_REDUCED);
     const int n = H->n_f * H->n_f + H->n_f;
@@ -516,7 +531,7 @@ static int compute_step(Handle* H, LmStep* out) {
   H->cand_has_jac = true;
   std::vector<double> hs;
   ++H->n_launches;
-  k_flag_to_scalar<<<1, 1, 0, H->stream>>>(H->d_fail, H->d_scalars + SC_FAIL);
+  k_flag_to_scalar<<<1, 1, 0, H->stream>>>(H->d_fail, H->p2p ? H->d_p2p_err : nullptr, H->d_scalars + SC_FAIL);
   CHECK_LAUNCH();
   if ((rc = gather_scalars(H, H->d_scalars, SC_N, hs))) return rc;
   double py = 0, he = 0, sn = 0, xn = 0, cost = 0, h_fail = 0;
@@ -525,6 +540,7 @@ static int compute_step(Handle* H, LmStep* out) {
     cost += s[SC_COST]; h_fail += s[SC_FAIL];
     if (H->n_pose > 0 || H->n_ranks > 1) { py += s[SC_PE0]; he += s[SC_PE0 + 1]; sn += s[SC_PE0 + 2]; xn += s[SC_PE0 + 3]; }
   }
+  if (h_fail >= P2P_ERR_UNIT) { H->err = "peer-memory Schur reduction timed out waiting for another rank"; return MCBA_ERR_NCCL; }
   const double* f = &hs[SC_F0];
   const double zg = py + f[0], zhz = he + f[1];
   out->mcc = zg - 0.5 * zhz;
@@ -556,6 +572,78 @@ static int download_params(Handle* H, mcba_params* p) {
   if (sd.board) CU(cudaMemcpyAsync(p->board_pose, H->d_board[w], (size_t)H->n_board * 6 * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
   if (sd.intr) CU(cudaMemcpyAsync(p->intrinsics, H->d_intr[w], (size_t)H->n_cam * 9 * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
   CU(cudaStreamSynchronize(H->stream));
+  return MCBA_OK;
+}
+
+// Peer-memory setup for k_syrk_sum_p2p: exchange CUDA IPC handles of the staging buffer, ZtZ and the flag array
+// (through the NCCL communicator), open the peers' handles and keep the pointer tables. Collective: every rank calls it
+// (mcba_comm_init, and mcba_set_stage after the buffers were reallocated). Falls back to the NCCL allreduce
+// (p2p = false) if anything is refused on any rank; MCBA_P2P=0 disables it.
+struct IpcRecord { cudaIpcMemHandle_t h[3]; long long off[3]; int ok; int pad; };
+static int close_p2p(Handle* H) {
+  for (void* p : H->ipc_opened) cudaIpcCloseMemHandle(p);
+  H->ipc_opened.clear(); H->p2p = false;
+  return MCBA_OK;
+}
+static int setup_p2p(Handle* H) {
+  close_p2p(H);
+  if (H->n_ranks < 2 || H->n_ranks > P2P_MAX_RANKS || H->batched) return MCBA_OK;
+  const char* env = getenv("MCBA_P2P");
+  if (env && atoi(env) == 0) return MCBA_OK;
+  typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+  static range_fn get_range = []() -> range_fn { void* l = dlopen("libcuda.so.1", RTLD_NOW); return l ? (range_fn)dlsym(l, "cuMemGetAddressRange_v2") : nullptr; }();
+  const int N = H->n_ranks;
+  if (!H->d_p2p_flags) {
+    if (dalloc(H, &H->d_p2p_flags, (size_t)1 << 18) || dalloc(H, &H->d_p2p_counter, (size_t)2) || dalloc(H, &H->d_p2p_err, (size_t)1)) return MCBA_ERR_CUDA;   // flags: 2 MB, an allocation of their own
+    CU(cudaMemset(H->d_p2p_flags, 0, ((size_t)1 << 18) * sizeof(unsigned long long)));
+    CU(cudaMemset(H->d_p2p_counter, 0, 2 * sizeof(unsigned int))); CU(cudaMemset(H->d_p2p_err, 0, sizeof(int)));
+  }
+  const size_t stage_n = std::max<size_t>((size_t)H->syrk_tiles * SY_T * SY_T, (size_t)1 << 18);
+  if (dalloc(H, &H->d_p2p_stage, stage_n)) return MCBA_ERR_CUDA;
+  IpcRecord mine; std::memset(&mine, 0, sizeof(mine));
+  void* ptrs[3] = {H->d_p2p_stage, H->d_ZtZ, H->d_p2p_flags};
+  mine.ok = get_range ? 1 : 0;
+  for (int k = 0; k < 3 && mine.ok; ++k) {
+    unsigned long long base = 0; size_t size = 0;
+    if (get_range(&base, &size, (unsigned long long)ptrs[k]) != 0) { mine.ok = 0; break; }
+    mine.off[k] = (long long)((unsigned long long)ptrs[k] - base);
+    if (cudaIpcGetMemHandle(&mine.h[k], (void*)base) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+  }
+  // allgather the records (as bytes) through NCCL
+  char *d_send = nullptr, *d_recv = nullptr;
+  if (dalloc(H, &d_send, sizeof(IpcRecord)) || dalloc(H, &d_recv, sizeof(IpcRecord) * (size_t)N)) return MCBA_ERR_CUDA;
+  CU(cudaMemcpy(d_send, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+  if (g_nccl.AllGather(d_send, d_recv, sizeof(IpcRecord), /*ncclChar*/ 0, H->comm, H->stream) != 0) { cudaFree(d_send); cudaFree(d_recv); H->err = "ncclAllGather(ipc handles)"; return MCBA_ERR_NCCL; }
+  std::vector<IpcRecord> all(N);
+  CU(cudaMemcpyAsync(all.data(), d_recv, sizeof(IpcRecord) * (size_t)N, cudaMemcpyDeviceToHost, H->stream));
+  CU(cudaStreamSynchronize(H->stream));
+  cudaFree(d_send); cudaFree(d_recv);
+  bool ok = true;
+  for (int r = 0; r < N; ++r) ok = ok && all[r].ok;
+  for (int r = 0; r < P2P_MAX_RANKS; ++r) { H->peer_stage[r] = nullptr; H->peer_ZtZ[r] = nullptr; H->peer_flags[r] = nullptr; }
+  for (int r = 0; r < N && ok; ++r) {
+    if (r == H->rank) { H->peer_stage[r] = H->d_p2p_stage; H->peer_ZtZ[r] = H->d_ZtZ; H->peer_flags[r] = H->d_p2p_flags; continue; }
+    void* opened[3] = {nullptr, nullptr, nullptr};
+    for (int k = 0; k < 3 && ok; ++k) {
+      bool dup = false;   // two buffers may live in the same underlying allocation
+      for (int q = 0; q < k; ++q) if (std::memcmp(&all[r].h[q], &all[r].h[k], sizeof(cudaIpcMemHandle_t)) == 0) { opened[k] = opened[q]; dup = true; }
+      if (dup) continue;
+      if (cudaIpcOpenMemHandle(&opened[k], all[r].h[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+      H->ipc_opened.push_back(opened[k]);
+    }
+    if (!ok) break;
+    H->peer_stage[r] = (double*)((char*)opened[0] + all[r].off[0]);
+    H->peer_ZtZ[r] = (double*)((char*)opened[1] + all[r].off[1]);
+    H->peer_flags[r] = (unsigned long long*)((char*)opened[2] + all[r].off[2]);
+  }
+  // every rank must take the same path: agree through a sum over ranks of the local verdict
+  double verdict = ok ? 1.0 : 0.0;
+  CU(cudaMemcpy(H->d_scalars, &verdict, sizeof(double), cudaMemcpyHostToDevice));
+  if (g_nccl.AllReduce(H->d_scalars, H->d_scalars, 1, NCCL_DOUBLE, NCCL_SUM, H->comm, H->stream) != 0) { H->err = "ncclAllReduce(p2p verdict)"; return MCBA_ERR_NCCL; }
+  CU(cudaMemcpyAsync(&verdict, H->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+  CU(cudaStreamSynchronize(H->stream));
+  if (verdict < N - 0.5) { close_p2p(H); return MCBA_OK; }
+  H->p2p = true;
   return MCBA_OK;
 }
 
@@ -612,7 +700,9 @@ void mcba_destroy(void* h) {
     std::fprintf(stderr, "[mcba chol prof, CTA0 cycles] diag %lld trsm %lld sync1 %lld update %lld sync2 %lld backsolve %lld\n", p[0], p[1], p[2], p[3], p[4], p[5]);
     cudaFree(H->d_chol_prof);
   }
+  close_p2p(H);
   if (H->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(H->comm);
+  dfree(&H->d_p2p_flags); dfree(&H->d_p2p_counter); dfree(&H->d_p2p_err); dfree(&H->d_p2p_stage);
   for (auto& p : H->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : H->free_events) cudaEventDestroy(e);
   if (H->tm_a) { cudaEventDestroy(H->tm_a); cudaEventDestroy(H->tm_b); }
@@ -730,9 +820,16 @@ int mcba_set_stage(void* h, int stage) {
   if (H->batched) { H->err = "batched handles are stage 1 only"; return MCBA_ERR_INVALID; }
   CU(cudaSetDevice(H->device));
   if (stage == H->stage) return MCBA_OK;
-  const int rc = setup_stage(H, stage);
+  int rc;
+  if (H->n_ranks > 1) {   // every rank unmaps its peers' buffers before anybody frees them
+    close_p2p(H);
+    if ((rc = allreduce_sum(H, H->d_scalars, 1))) return rc;
+    CU(cudaStreamSynchronize(H->stream));
+  }
+  rc = setup_stage(H, stage);
   if (rc) return rc;
   CU(cudaDeviceSynchronize());
+  if (H->n_ranks > 1 && (rc = setup_p2p(H))) return rc;   // collective: every rank changes stage
   return MCBA_OK;
 }
 
@@ -774,6 +871,7 @@ int mcba_comm_init(void* h, int rank, int n_ranks, const void* uid) {
     if ((rc = gather_scalars(H, H->d_scalars, SC_N, hs))) return rc;
     flush_timers(H);
     for (int k = 0; k < KF_COUNT; ++k) { H->kf_launches[k] = 0; H->kf_ms[k] = 0; }
+    if ((rc = setup_p2p(H))) return rc;
   }
   return MCBA_OK;
 }

@@ -245,7 +245,11 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) k_reproj_err(ObsArgs a, double
   }
 }
 
-__global__ void k_flag_to_scalar(const int* __restrict__ flag, double* __restrict__ out) { *out = (double)*flag; }
+// SC_FAIL scalar: numerical-failure flag of this rank, plus P2P_ERR_UNIT if the peer-memory reduction timed out
+constexpr double P2P_ERR_UNIT = 1048576.0;
+__global__ void k_flag_to_scalar(const int* __restrict__ flag, const int* __restrict__ p2p_err, double* __restrict__ out) {
+  *out = (double)*flag + ((p2p_err && *p2p_err) ? P2P_ERR_UNIT : 0.0);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Deterministic reductions: out[c] = op_c over rows of in[n][m]; columns < m_sum are summed, the others maxed.
@@ -551,6 +555,102 @@ __global__ void k_syrk_sum(const double* __restrict__ partial, int n_tiles, int 
     double s = 0.0;
     for (int sp = 0; sp < nsplit; ++sp) s += partial[((size_t)sp * n_tiles + tile) * (SY_T * SY_T) + e];
     ZtZ[(size_t)i * ldz + j] = s;
+  }
+}
+
+// K2d, multi-GPU: the fixed-order split-K sum fused with the cross-GPU reduction of the Schur complement, over
+// NVLink peer memory instead of an NCCL allreduce - one kernel, three phases:
+//   1. every CTA sums this rank's split-K partials (fixed order) into this rank's staging buffer (tile layout
+//      [tile][SY_T*SY_T]); the last CTA to finish publishes "staged" (epoch) into every rank's flag array;
+//   2. rank r owns the contiguous slice [r, r+1) * ceil(n_tiles*SY_T^2 / n_ranks) of the staging layout: it loads that
+//      slice from EVERY rank's staging buffer (independent peer loads, all in flight together), sums in rank order - so
+//      all ranks end up with bit-identical sums - and stores the result into every rank's ZtZ (peer stores): a
+//      reduce-scatter and an all-gather in one pass;
+//   3. the last CTA publishes "written" and waits until every rank has written its slice into this rank's ZtZ, so
+//      that the next kernel in the stream may consume ZtZ and the next iteration may overwrite the staging buffer.
+// Spins are bounded (P2P_TIMEOUT cycles -> *err, reported through the SC_FAIL scalar). All CTAs must be co-resident
+// (grid = 2 CTAs per SM).
+constexpr long long P2P_TIMEOUT = 6000000000LL;
+constexpr int P2P_MAX_RANKS = 8;
+struct P2PArgs {
+  double* stage[P2P_MAX_RANKS];                // staging buffers (peer-mapped), [n_tiles][SY_T*SY_T]
+  double* ZtZ[P2P_MAX_RANKS];                  // [ldz][ldz]
+  unsigned long long* flags[P2P_MAX_RANKS];    // each [2][P2P_MAX_RANKS]: "staged" and "written" epochs per source rank
+  const double* partial;                       // this rank's split-K partials
+  int nsplit, rank, n_ranks;
+  unsigned long long epoch;
+  int n_tiles, nt, ldz;
+  unsigned int* counter;                       // [2], zero between launches
+  int* err;
+};
+__device__ __forceinline__ bool p2p_wait(const volatile unsigned long long* flags, int n, unsigned long long epoch, int* err) {
+  const long long t0 = clock64();
+  for (int p = 0; p < n; ++p)
+    while (flags[p] < epoch) {
+      if (clock64() - t0 > P2P_TIMEOUT) { *err = 1; return false; }
+      __nanosleep(32);
+    }
+  __threadfence_system();
+  return true;
+}
+__device__ __forceinline__ void p2p_publish(const P2PArgs& a, int slot) {
+  __threadfence_system();
+  for (int p = 0; p < a.n_ranks; ++p) ((volatile unsigned long long*)a.flags[p])[slot * P2P_MAX_RANKS + a.rank] = a.epoch;
+}
+// (row, column) in ZtZ of element idx of the staging layout; false for entries nobody consumes
+__device__ __forceinline__ bool p2p_locate(int64_t idx, int nt, int ldz, int* i, int* j) {
+  const int tile = (int)(idx / (SY_T * SY_T)), e = (int)(idx % (SY_T * SY_T));
+  int ti = 0, rem = tile;
+  while (rem >= nt - ti) { rem -= nt - ti; ++ti; }
+  *i = ti * SY_T + e / SY_T; *j = (ti + rem) * SY_T + e % SY_T;
+  return *i < ldz && *j < ldz && *j >= *i;
+}
+__global__ void __launch_bounds__(256) k_syrk_sum_p2p(P2PArgs a) {
+  __shared__ int ok_s;
+  const int64_t total = (int64_t)a.n_tiles * SY_T * SY_T;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gstride = (int64_t)gridDim.x * blockDim.x;
+  // phase 1
+  double* my_stage = a.stage[a.rank];
+  for (int64_t idx = gtid; idx < total; idx += gstride) {
+    int i, j;
+    if (!p2p_locate(idx, a.nt, a.ldz, &i, &j)) continue;
+    double s = 0.0;
+    for (int sp = 0; sp < a.nsplit; ++sp) s += a.partial[(size_t)sp * total + idx];
+    my_stage[idx] = s;
+  }
+  __threadfence_system();
+  __syncthreads();
+  volatile unsigned long long* my_flags = a.flags[a.rank];
+  if (threadIdx.x == 0) {
+    if (atomicAdd(a.counter, 1u) == gridDim.x - 1) { a.counter[0] = 0; p2p_publish(a, 0); }
+    ok_s = p2p_wait(my_flags, a.n_ranks, a.epoch, a.err) ? 1 : 0;
+  }
+  __syncthreads();
+  // phase 2
+  if (ok_s) {
+    const int64_t slice = (total + a.n_ranks - 1) / a.n_ranks;
+    const int64_t lo = slice * a.rank, hi = (lo + slice < total) ? lo + slice : total;
+    for (int64_t idx = lo + gtid; idx < hi; idx += gstride) {
+      int i, j;
+      if (!p2p_locate(idx, a.nt, a.ldz, &i, &j)) continue;
+      double v[P2P_MAX_RANKS];
+#pragma unroll
+      for (int p = 0; p < P2P_MAX_RANKS; ++p) v[p] = (p < a.n_ranks) ? __ldcg(a.stage[p] + idx) : 0.0;
+      double s = v[0];
+#pragma unroll
+      for (int p = 1; p < P2P_MAX_RANKS; ++p) if (p < a.n_ranks) s += v[p];
+      const size_t o = (size_t)i * a.ldz + j;
+#pragma unroll
+      for (int p = 0; p < P2P_MAX_RANKS; ++p) if (p < a.n_ranks) a.ZtZ[p][o] = s;
+    }
+  }
+  // phase 3
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(a.counter + 1, 1u) == gridDim.x - 1) {
+    a.counter[1] = 0;
+    p2p_publish(a, 1);
+    p2p_wait(my_flags + P2P_MAX_RANKS, a.n_ranks, a.epoch, a.err);
   }
 }
 

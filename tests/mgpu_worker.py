@@ -60,6 +60,36 @@ def main():
             assert np.abs(p.board_pose - po.board_pose).max() <= 1e-6
             assert np.abs(p.intrinsics - po.intrinsics).max() <= 1e-6 * np.abs(po.intrinsics).max()
             print(f"MGPU_OK stage {stage} world {world} iterations {summ.num_iterations} rms {summ.rms_px:.6f}", flush=True)
+    # stage 4 then stage 5 on ONE handle (mcba_set_stage re-exchanges the peer-memory handles)
+    o = synth.generate_observations(s, rank * per, (rank + 1) * per)
+    prob, init, gt = synth.make_problem(s, o, 4)
+    h = mcba.Handle(prob, device=local)
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = ctypes.create_string_buffer(128)
+        assert h.lib.mcba_nccl_unique_id(buf) == 0
+        uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+    uid = uid.cuda()
+    dist.broadcast(uid, 0)
+    h.comm_init(rank, world, uid.cpu().numpy().tobytes())
+    p = init.copy()
+    p.intrinsics[:] = s.intr_init
+    s4, _ = h.solve(p)
+    h.set_stage(5)
+    s5, _ = h.solve(p)
+    h.close()
+    if rank == 0:
+        import oracle_py
+        of = synth.generate_observations(s)
+        pf, initf, _ = synth.make_problem(s, of, 4)
+        po = initf.copy()
+        po.intrinsics[:] = s.intr_init
+        rc, o4, _ = oracle_py.solve(pf, po)
+        rc, o5, _ = oracle_py.solve(pf.with_stage(5), po)
+        assert (s4.num_iterations, s5.num_iterations) == (o4.num_iterations, o5.num_iterations)
+        assert abs(s5.rms_px - o5.rms_px) <= 1e-6
+        assert np.abs(p.intrinsics - po.intrinsics).max() <= 1e-6 * np.abs(po.intrinsics).max()
+        print(f"MGPU_OK set_stage world {world} iterations {s4.num_iterations}+{s5.num_iterations}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
