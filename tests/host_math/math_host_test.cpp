@@ -1,5 +1,6 @@
 // Host-side harness around csrc/mcba_math.cuh (the arithmetic the CUDA kernels run), so that it can be
 // checked against the oracle on a box without a GPU. TEST CODE: never linked into libmcba.
+#include <vector>
 #include "../../mc-calib_b200/csrc/mcba_math.cuh"
 using namespace mcba;
 
@@ -48,4 +49,139 @@ extern "C" double mathtest_obs(int stage, int model, int flags, const double* ca
 extern "C" int mathtest_chol6(double* A, double* b) {
   if (!chol6(A)) return 0;
   chol6_fwd(A, b); chol6_bwd(A, b); return 1;
+}
+
+// ---- pose initialisation arithmetic (csrc/mcba_pnp_math.cuh) ----
+#include "../../mc-calib_b200/csrc/mcba_pnp_math.cuh"
+extern "C" int pnptest_undistort(int model, const double* intr, double u, double v, double* ab) {
+  return undistort_pixel(model, intr, u, v, ab[0], ab[1]) ? 1 : 0;
+}
+// f: 3 unit bearings (row-major 3x3), P: 3 points; out R [4][9], t [4][3]; returns the number of solutions
+extern "C" int pnptest_p3p(const double* f, const double* P, double* R, double* t) {
+  double ff[3][3], PP[3][3];
+  for (int i = 0; i < 3; ++i) for (int k = 0; k < 3; ++k) { ff[i][k] = f[i * 3 + k]; PP[i][k] = P[i * 3 + k]; }
+  P3PSolutions s;
+  p3p_solve(ff, PP, s);
+  for (int i = 0; i < s.n; ++i) { for (int k = 0; k < 9; ++k) R[i * 9 + k] = s.R[i][k]; for (int k = 0; k < 3; ++k) t[i * 3 + k] = s.t[i][k]; }
+  return s.n;
+}
+extern "C" int pnptest_hypothesis(const double* ab, const double* X, const double* intr, const double* w4, double* rvec, double* t) {
+  double a[4][2], x[4][3], R[9];
+  for (int i = 0; i < 4; ++i) { a[i][0] = ab[2 * i]; a[i][1] = ab[2 * i + 1]; for (int k = 0; k < 3; ++k) x[i][k] = X[3 * i + k]; }
+  if (!p3p_hypothesis(a, x, intr, w4, R, t)) return 0;
+  rot_to_rvec(R, rvec);
+  return 1;
+}
+extern "C" void pnptest_rvec(const double* R, double* rv) { rot_to_rvec(R, rv); }
+extern "C" void pnptest_sample4(unsigned long long seed, unsigned long long b, unsigned long long h, int n, int* idx) {
+  ransac_sample4(seed, b, h, n, idx);
+}
+// replays the stopping rule over a list of inlier counts; returns the index of the chosen hypothesis (-1: none),
+// *n_used = hypotheses consumed
+extern "C" int pnptest_replay(const int* counts, int n_counts, int total, int it, double p, int* n_used) {
+  RansacState s; ransac_init(s, it);
+  int h = 0;
+  while (ransac_continue(s, it) && h < n_counts) { ransac_update(s, h, counts[h], total, p); ++h; }
+  *n_used = h;
+  return s.best_h;
+}
+extern "C" int pnptest_residual_jac(const double* pose, const double* intr, const double* X0, double u, double v,
+                                    double* r, double* J) {
+  double prep[PREP];
+  prep_block(pose, prep);
+  return pnp_residual_jac(prep, intr, X0, u, v, r, J, J + 6) ? 1 : 0;
+}
+
+// Sequential restatement of k_pnp_prepare + k_pnp_ransac (csrc/mcba_pnp.cu) for ONE observation run, on the same
+// header arithmetic: lets the CPU-only suite compare the algorithm with the OpenCV-backed checker before a GPU is
+// involved. Sums of the refinement run in corner order instead of the kernel's shuffle tree (rounding-level difference).
+extern "C" int pnptest_ransac(int n, const float* u, const float* v, const float* xyz /*[n][3]*/, int model,
+                              const double* intr, double thresh, int it, double p, int refine, int refine_it,
+                              unsigned long long seed, unsigned long long b, double* pose, double* pose0,
+                              unsigned char* mask, int* best_h, int* n_hyp) {
+  std::vector<double> ab(2 * n), w(2 * n); std::vector<unsigned char> okv(n);
+  double in[9];
+  for (int k = 0; k < 9; ++k) in[k] = (k < 4 || model == 0) ? intr[k] : 0.0;
+  for (int i = 0; i < n; ++i) {
+    double x = 0, y = 0;
+    okv[i] = undistort_pixel(model, intr, (double)u[i], (double)v[i], x, y) ? 1 : 0;
+    ab[2 * i] = x; ab[2 * i + 1] = y;
+    w[2 * i] = model == 0 ? (double)u[i] : x * intr[0] + intr[2];
+    w[2 * i + 1] = model == 0 ? (double)v[i] : y * intr[1] + intr[3];
+  }
+  const double thr2 = thresh * thresh;
+  auto inlier = [&](const double* R, const double* t, int i) {
+    const double X0[3] = {(double)xyz[3 * i], (double)xyz[3 * i + 1], (double)xyz[3 * i + 2]};
+    double X[3], pu, pv;
+    mat3_vec_add(R, X0, t, X);
+    if (!project_brown(in, X, pu, pv)) return false;
+    const double du = pu - w[2 * i], dv = pv - w[2 * i + 1];
+    return du * du + dv * dv < thr2;
+  };
+  RansacState st; ransac_init(st, it);
+  double bR[9] = {0}, bt[3] = {0};
+  if (n >= 4) {
+    for (int h = 0; ransac_continue(st, it); ++h) {
+      int idx[4];
+      ransac_sample4(seed, b, (unsigned long long)h, n, idx);
+      double ab4[4][2], X4[4][3], R[9], t[3];
+      bool ok = true;
+      for (int k = 0; k < 4; ++k) {
+        ab4[k][0] = ab[2 * idx[k]]; ab4[k][1] = ab[2 * idx[k] + 1]; ok = ok && okv[idx[k]];
+        for (int c = 0; c < 3; ++c) X4[k][c] = (double)xyz[3 * idx[k] + c];
+      }
+      const double w4[2] = {w[2 * idx[3]], w[2 * idx[3] + 1]};
+      ok = ok && p3p_hypothesis(ab4, X4, in, w4, R, t);
+      int count = 0;
+      if (ok) for (int i = 0; i < n; ++i) count += (okv[i] && inlier(R, t, i)) ? 1 : 0;
+      const int prev = st.best_h;
+      ransac_update(st, h, count, n, p);
+      if (st.best_h != prev) { for (int k = 0; k < 9; ++k) bR[k] = R[k]; for (int k = 0; k < 3; ++k) bt[k] = t[k]; }
+    }
+  }
+  int cnt = 0;
+  for (int i = 0; i < n; ++i) { mask[i] = (st.best_h >= 0 && okv[i] && inlier(bR, bt, i)) ? 1 : 0; cnt += mask[i]; }
+  double x[6] = {0, 0, 0, 0, 0, 0};
+  if (st.best_h >= 0) { rot_to_rvec(bR, x); x[3] = bt[0]; x[4] = bt[1]; x[5] = bt[2]; }
+  for (int k = 0; k < 6; ++k) pose0[k] = x[k];
+  auto normal_eq = [&](const double* q, double* H, double* g, double& cost) {
+    double prep[PREP]; prep_block(q, prep);
+    for (int k = 0; k < 21; ++k) H[k] = 0; for (int k = 0; k < 6; ++k) g[k] = 0; cost = 0;
+    for (int i = 0; i < n; ++i) {
+      if (!mask[i]) continue;
+      const double X0[3] = {(double)xyz[3 * i], (double)xyz[3 * i + 1], (double)xyz[3 * i + 2]};
+      double r[2], Ju[6], Jv[6];
+      if (!pnp_residual_jac(prep, in, X0, w[2 * i], w[2 * i + 1], r, Ju, Jv)) { cost += 1e12; continue; }
+      cost += r[0] * r[0] + r[1] * r[1];
+      int k = 0;
+      for (int a = 0; a < 6; ++a) { for (int c = a; c < 6; ++c) H[k++] += Ju[a] * Ju[c] + Jv[a] * Jv[c]; g[a] += Ju[a] * r[0] + Jv[a] * r[1]; }
+    }
+  };
+  if (refine && st.best_h >= 0 && cnt >= 4) {
+    double H[21], g[6], cost; normal_eq(x, H, g, cost);
+    double lambda = 1e-3;
+    for (int iter = 0; iter < refine_it; ++iter) {
+      double A[36], d[6]; int k = 0;
+      for (int a = 0; a < 6; ++a) for (int c = a; c < 6; ++c) { A[c * 6 + a] = H[k]; A[a * 6 + c] = H[k]; ++k; }
+      for (int a = 0; a < 6; ++a) { A[a * 6 + a] *= (1.0 + lambda); d[a] = -g[a]; }
+      if (!chol6(A)) { lambda *= 10.0; if (lambda > 1e16) break; continue; }
+      chol6_fwd(A, d); chol6_bwd(A, d);
+      double cand[6], dn = 0, xn = 0;
+      for (int a = 0; a < 6; ++a) { cand[a] = x[a] + d[a]; dn += d[a] * d[a]; xn += x[a] * x[a]; }
+      double H2[21], g2[6], cost2; normal_eq(cand, H2, g2, cost2);
+      if (cost2 < cost) {
+        for (int a = 0; a < 6; ++a) { x[a] = cand[a]; g[a] = g2[a]; }
+        for (int a = 0; a < 21; ++a) H[a] = H2[a];
+        const bool small = (cost - cost2) <= 1e-14 * cost || dn <= 1e-24 * (xn + 1e-24);
+        cost = cost2; lambda = fmax(lambda * 0.1, 1e-16);
+        if (small) break;
+      } else {
+        if (!(dn > 1e-30 * (xn + 1e-30))) break;
+        lambda *= 10.0; if (lambda > 1e16) break;
+      }
+    }
+  }
+  for (int k = 0; k < 6; ++k) pose[k] = x[k];
+  *best_h = st.best_h; *n_hyp = st.countit;
+  return cnt;
 }

@@ -1,0 +1,70 @@
+"""Pose initialisation on the GPU (mcba_pnp_ransac through the C ABI) against the committed OpenCV golden outputs and,
+when cv2 is importable, against the OpenCV-backed checker run on the same inputs."""
+import numpy as np
+import pytest
+
+import pnp_util
+from mcba import pnp
+
+pytestmark = pytest.mark.gpu
+
+
+def as_dict(r):
+    return dict(pose=r.pose, pose0=r.unrefined_pose, n_inliers=r.n_inliers, inlier_mask=r.inlier_mask,
+                best_h=r.best_hypothesis, n_hyp=r.n_hypotheses)
+
+
+@pytest.mark.parametrize("name", list(pnp_util.CASES))
+def test_gpu_matches_opencv_golden(name):
+    P, opt, gt_pose = pnp_util.make_case(name)
+    r = pnp.ransac(P, opt)
+    assert r.kernel_launches == 3 and r.kernel_ms > 0
+    pnp_util.compare(as_dict(r), pnp_util.golden_case(name), P)
+
+
+def test_gpu_matches_checker_live():
+    pytest.importorskip("cv2")
+    import oracle_pnp
+    P, opt, _ = pnp_util.make_case("c2_t1")
+    opt.seed = 777                                  # a seed the golden file does not hold
+    r = pnp.ransac(P, opt)
+    pnp_util.compare(as_dict(r), oracle_pnp.ransac_all(P, opt), P)
+
+
+def test_gpu_reproducible_and_seed_dependent():
+    P, opt, _ = pnp_util.make_case("c2_t1")
+    a, b = pnp.ransac(P, opt), pnp.ransac(P, opt)
+    assert np.array_equal(a.pose, b.pose) and np.array_equal(a.inlier_mask, b.inlier_mask)
+    opt.seed = 43
+    c = pnp.ransac(P, opt)
+    assert not np.array_equal(a.best_hypothesis, c.best_hypothesis)
+
+
+def test_gpu_matches_host_restatement_bitwise_on_integers():
+    L = pnp_util.host_lib()
+    P, opt, _ = pnp_util.make_case("c3_t3")
+    r = pnp.ransac(P, opt)
+    h = pnp_util.host_ransac_all(L, P, opt)
+    pnp_util.compare(as_dict(r), h, P, tol_refined=1e-9, tol_unrefined=1e-10)
+
+
+def test_gpu_edge_cases():
+    P, opt, _ = pnp_util.make_case("c1_t2")
+    empty = pnp.PnpProblem.__new__(pnp.PnpProblem)
+    empty.__dict__.update(P.__dict__)
+    empty.bobs_ptr, empty.bobs_cam = np.zeros(1, np.int64), np.zeros(0, np.int32)
+    empty.u, empty.v, empty.pt_idx = np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros(0, np.int32)
+    r = pnp.ransac(empty, opt)
+    assert r.pose.shape == (0, 6)
+    short = pnp.PnpProblem.__new__(pnp.PnpProblem)
+    short.__dict__.update(P.__dict__)
+    short.bobs_ptr, short.bobs_cam = np.array([0, 3, 19], np.int64), P.bobs_cam[:2].copy()
+    short.u, short.v, short.pt_idx = P.u[:19].copy(), P.v[:19].copy(), P.pt_idx[:19].copy()
+    r = pnp.ransac(short, opt)
+    assert r.best_hypothesis[0] == -1 and r.n_inliers[0] == 0 and not r.pose[0].any()
+    bad = pnp.PnpProblem.__new__(pnp.PnpProblem)
+    bad.__dict__.update(P.__dict__)
+    bad.pt_idx = P.pt_idx.copy()
+    bad.pt_idx[5] = 10 ** 6
+    with pytest.raises(Exception):
+        pnp.ransac(bad, opt)
