@@ -481,6 +481,7 @@ bool Calibration::loadConfig(const std::string& yaml_path) {
     std::istringstream vs(val);
     if (key == "number_iterations") vs >> nb_iterations_;
     else if (key == "fix_intrinsic") vs >> fix_intrinsic_;
+    else if (key == "ransac_threshold") vs >> ransac_thresh_;
     else if (key == "distortion_model") vs >> distortion_model_;
     else if (key == "distortion_per_camera") { distortion_per_camera_.clear(); int d; while (vs >> d) distortion_per_camera_.push_back(d); }
   }

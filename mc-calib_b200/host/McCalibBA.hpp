@@ -35,6 +35,7 @@ class Camera final {
 public:
   int cam_idx_ = 0;
   int distortion_model_ = 0;              // 0 Brown, 1 Kannala
+  int im_cols_ = 0, im_rows_ = 0;         // Camera.hpp (img_width / img_height of the keypoint file)
   std::array<double, 9> intrinsics_{};    // fx fy u0 v0 d4..d8
   std::map<int, std::weak_ptr<BoardObs>> board_observations_;
   void refineIntrinsicCalibration(const int nb_iterations);   // Camera.cpp:268-305
@@ -49,6 +50,7 @@ public:
   bool valid_ = true;
   std::weak_ptr<Camera> cam_;
   std::weak_ptr<Board> board_3d_;
+  void estimatePose(const float ransac_thresh, const int ransac_iterations);   // BoardObs.cpp:121-163 (GPU, one observation)
 };
 
 class Object3D final {
@@ -74,19 +76,27 @@ public:
   std::map<int, std::weak_ptr<BoardObs>> board_observations_;
   std::weak_ptr<Camera> cam_;
   std::weak_ptr<Object3D> object_3d_;
+  void estimatePose(const float ransac_thresh, const int ransac_iterations);   // Object3DObs.cpp:222-262
 };
 
 class CameraGroupObs final {
 public:
   int cam_group_idx_ = 0;
+  bool quaternion_averaging_ = true;        // CameraGroupObs.hpp
+  std::weak_ptr<CameraGroup> cam_group_;
+  std::vector<int> object_idx_;             // object id of object_observations_[k] (insertObjectObservation order)
   std::map<int, std::weak_ptr<Object3DObs>> object_observations_;
   std::map<int, Pose6> object_pose_;        // object pose w.r.t. the reference camera of the group
+  void insertObjectObservation(const std::shared_ptr<Object3DObs>& obs);   // CameraGroupObs.cpp:26-33
+  void computeObjectsPose();                // CameraGroupObs.cpp:42-108
   void updateObjObsPose();                  // CameraGroupObs.cpp:208-217
 };
 
 class Frame final {
 public:
   int frame_idx_ = 0;
+  std::map<int, std::string> frame_path_;   // per camera (Frame.hpp)
+  std::map<int, std::weak_ptr<BoardObs>> board_observations_;
   std::map<int, std::weak_ptr<CameraGroupObs>> cam_group_observations_;
 };
 
@@ -96,6 +106,7 @@ public:
   std::map<int, std::weak_ptr<Camera>> cameras_;
   std::map<int, std::weak_ptr<Frame>> frames_;
   std::map<int, Pose6> relative_camera_pose_;
+  void computeObjPoseInCameraGroup();                                      // CameraGroup.cpp:153-183
   void refineCameraGroup(const int nb_iterations);                         // CameraGroup.cpp:191-279
   void refineCameraGroupAndObjects(const int nb_iterations);               // CameraGroup.cpp:366-474
   void refineCameraGroupAndObjectsAndIntrinsics(const int nb_iterations);  // CameraGroup.cpp:483-583
@@ -113,6 +124,8 @@ public:
   int distortion_model_ = 0;       // YAML distortion_model  (McCalib.cpp:60)
   std::vector<int> distortion_per_camera_;
   int cuda_device_ = 0;
+  float ransac_thresh_ = 10.f;     // YAML ransac_threshold  (McCalib.cpp:58)
+  unsigned long long ransac_seed_ = 0;   // the reference draws from std::random_device; here the draws are seeded
   std::map<int, std::shared_ptr<Camera>> cams_;
   std::map<int, std::shared_ptr<Board>> boards_3d_;
   std::map<int, std::shared_ptr<BoardObs>> board_observations_;
@@ -123,6 +136,17 @@ public:
   std::map<int, std::shared_ptr<Frame>> frames_;
 
   bool loadConfig(const std::string& yaml_path);       // the keys of McCalib.cpp:39-79 that the refinement path uses
+  // on-disk formats either side of the path (cv::FileStorage YAML)
+  void insertNewBoard(const int cam_idx, const int frame_idx, const int board_idx, const std::vector<Point2f>& pts_2d,
+                      const std::vector<int>& charuco_idx, const std::string& frame_path);   // McCalib.cpp:594-642
+  bool loadDetectedKeypoints(const std::string& path);          // McCalib.cpp:172-213 (detected_keypoints_data.yml)
+  bool saveDetectedKeypoints(const std::string& path) const;    // McCalib.cpp:493-548
+  bool loadInitialIntrinsics(const std::string& path);          // McCalib.cpp:662-688 (file branch of initializeCalibrationAllCam)
+  // pose initialisation feeding the refinement: every observation in one GPU launch (include/mcba_pnp.h)
+  void estimatePoseAllBoards();                        // McCalib.cpp:703-706
+  void estimatePoseAllObjects();                       // McCalib.cpp:990-993
+  void computeAllObjPoseInCameraGroup();               // McCalib.cpp:1198-1205: per group computeObjPoseInCameraGroup, per
+                                                       // group observation computeObjectsPose
   void refineIntrinsicAndPoseAllCam();                 // McCalib.cpp:713-716
   void refineAllObject3D();                            // McCalib.cpp:1014-1017
   void refineAllCameraGroup();                         // McCalib.cpp:1211-1220
@@ -140,6 +164,10 @@ void rotVecToMat(const double* rv, double* R /*9, row-major*/);
 void matToRotVec(const double* R, double* rv);
 Pose6 composePose(const Pose6& outer, const Pose6& inner);   // x -> outer(inner(x))
 Pose6 invertPose(const Pose6& p);
+// geometrytools.cpp:832-893: Markley quaternion averaging (largest eigenvector of the mean outer product, antipodal
+// quaternions flipped to w >= 0) or the per-component median of the rotation vectors
+std::array<double, 3> getAverageRotation(std::vector<double>& r1, std::vector<double>& r2, std::vector<double>& r3,
+                                         const bool use_quaternion_averaging = true);
 
 extern int g_verbose;              // 1: per-iteration table on stdout like minimizer_progress_to_stdout (default)
 extern int g_cuda_device;          // device used by the refine* methods (set from Calibration::cuda_device_)

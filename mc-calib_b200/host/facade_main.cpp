@@ -3,8 +3,12 @@
 // the final refinement, runs the requested refine* entry points of Calibration, and prints the refined blocks.
 //   usage: facade_main <scene.txt> <flow> <out.txt>     flow: "final" (apps/calibrate/src/calibrate.cpp:60-64),
 //                                                             "intrinsics" (refineIntrinsicAndPoseAllCam),
-//                                                             "objects" (refineAllObject3D), "group" (refineAllCameraGroup)
+//                                                             "objects" (refineAllObject3D), "group" (refineAllCameraGroup),
+//                                                             "init" (no pose is taken from the file: estimatePoseAllBoards,
+//                                                             estimatePoseAllObjects, computeAllObjPoseInCameraGroup on the
+//                                                             GPU / host), "init_final" ("init" followed by "final")
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <iostream>
 #include <string>
@@ -22,6 +26,9 @@ int main(int argc, char** argv) {
   g_verbose = 0;
   int n_cam, n_board, n_frames, n_bobs;
   in >> n_cam >> n_board >> n_frames >> n_bobs >> calib.nb_iterations_ >> calib.fix_intrinsic_;
+  const bool do_init = flow == "init" || flow == "init_final";
+  if (argc > 4) calib.ransac_thresh_ = (float)std::atof(argv[4]);
+  if (argc > 5) calib.ransac_seed_ = std::strtoull(argv[5], nullptr, 10);
   auto group = std::make_shared<CameraGroup>();
   group->cam_group_idx_ = 0; group->id_ref_cam_ = 0;
   calib.cam_group_[0] = group;
@@ -55,15 +62,15 @@ int main(int argc, char** argv) {
     auto frame = std::make_shared<Frame>();
     frame->frame_idx_ = f;
     auto cgo = std::make_shared<CameraGroupObs>();
-    cgo->cam_group_idx_ = 0;
+    cgo->cam_group_idx_ = 0; cgo->cam_group_ = group;
     Pose6 p; for (double& x : p) in >> x;
+    if (do_init) p = Pose6{};                 // to be computed from the observations
     cgo->object_pose_[0] = p;
     calib.frames_[f] = frame; calib.cams_group_obs_[f] = cgo;
     frame->cam_group_observations_[0] = cgo; group->frames_[f] = frame;
   }
   // board observations: frame cam board npts (charuco_id u v)*, sorted by (frame, cam, board)
   int n_bo = 0, n_oo = 0, last_frame = -1, last_cam = -1;
-  std::shared_ptr<Object3DObs> oo;
   for (int k = 0; k < n_bobs; ++k) {
     auto bo = std::make_shared<BoardObs>();
     int npts;
@@ -71,35 +78,55 @@ int main(int argc, char** argv) {
     bo->pts_2d_.resize(npts); bo->charuco_id_.resize(npts);
     for (int i = 0; i < npts; ++i) in >> bo->charuco_id_[i] >> bo->pts_2d_[i].x >> bo->pts_2d_[i].y;
     bo->cam_ = calib.cams_[bo->camera_id_]; bo->board_3d_ = calib.boards_3d_[bo->board_id_];
-    auto cgo = calib.cams_group_obs_[bo->frame_id_];
-    // BoardObs::pose_ = camera o object o board, Object3DObs::pose_ = camera o object (what estimatePose* would leave)
-    const Pose6 cam_obj = composePose(group->relative_camera_pose_[bo->camera_id_], cgo->object_pose_[0]);
-    bo->pose_ = composePose(cam_obj, object->relative_board_pose_[bo->board_id_]);
     calib.board_observations_[n_bo] = bo;
     calib.cams_[bo->camera_id_]->board_observations_[n_bo] = bo;
+    ++n_bo;
+  }
+  if (do_init) calib.estimatePoseAllBoards();   // McCalib.cpp:703-706: BoardObs::pose_, valid_, inlier corners only
+  // object observations, from the (valid) board observations of one (frame, camera) (Object3DObs.cpp:31-52)
+  std::shared_ptr<Object3DObs> oo;
+  for (int k = 0; k < n_bo; ++k) {
+    auto bo = calib.board_observations_[k];
+    if (!bo->valid_) continue;
+    auto cgo = calib.cams_group_obs_[bo->frame_id_];
+    if (!do_init) {
+      // BoardObs::pose_ = camera o object o board, Object3DObs::pose_ = camera o object (what estimatePose* would leave)
+      const Pose6 cam_obj = composePose(group->relative_camera_pose_[bo->camera_id_], cgo->object_pose_[0]);
+      bo->pose_ = composePose(cam_obj, object->relative_board_pose_[bo->board_id_]);
+    }
     if (bo->frame_id_ != last_frame || bo->camera_id_ != last_cam) {
       oo = std::make_shared<Object3DObs>();
       oo->frame_id_ = bo->frame_id_; oo->camera_id_ = bo->camera_id_; oo->object_3d_id_ = 0;
-      oo->cam_ = calib.cams_[bo->camera_id_]; oo->object_3d_ = object; oo->pose_ = cam_obj;
+      oo->cam_ = calib.cams_[bo->camera_id_]; oo->object_3d_ = object;
+      if (!do_init) oo->pose_ = composePose(group->relative_camera_pose_[bo->camera_id_], cgo->object_pose_[0]);
       calib.object_observations_[n_oo] = oo; object->object_observations_[n_oo] = oo;
-      cgo->object_observations_[n_oo] = oo;
+      cgo->insertObjectObservation(oo);
       ++n_oo; last_frame = bo->frame_id_; last_cam = bo->camera_id_;
     }
-    oo->board_observations_[n_bo] = bo;
-    for (int i = 0; i < npts; ++i) {   // Object3DObs.cpp:38-51: corners appended board after board
+    oo->board_observations_[k] = bo;
+    for (size_t i = 0; i < bo->charuco_id_.size(); ++i) {   // corners appended board after board
       oo->pts_2d_.push_back(bo->pts_2d_[i]);
       oo->pts_id_.push_back(object->pts_board_2_obj_[std::make_pair(bo->board_id_, bo->charuco_id_[i])]);
     }
-    ++n_bo;
   }
   if (!in) { std::fprintf(stderr, "scene file truncated\n"); return 2; }
 
-  if (flow == "final") {                      // apps/calibrate/src/calibrate.cpp:60-64
+  if (do_init) {
+    calib.estimatePoseAllObjects();             // McCalib.cpp:990-993
+    calib.computeAllObjPoseInCameraGroup();     // McCalib.cpp:1635-1641
+    if (!g_last_error.empty()) { std::fprintf(stderr, "libmcba failed: %s\n", g_last_error.c_str()); return 1; }
+    std::ofstream io(std::string(argv[3]) + ".init.txt");
+    io.precision(17);
+    for (int k = 0; k < n_bo; ++k) io << (calib.board_observations_[k]->valid_ ? 1 : 0) << " " << calib.board_observations_[k]->charuco_id_.size() << "\n";
+    for (int k = 0; k < n_oo; ++k) { io << calib.object_observations_[k]->pts_id_.size(); for (double x : calib.object_observations_[k]->group_pose_) io << " " << x; io << "\n"; }
+  }
+  if (flow == "final" || flow == "init_final") {   // apps/calibrate/src/calibrate.cpp:60-64
     calib.refineAllCameraGroupAndObjects();
     if (calib.fix_intrinsic_ == 0) calib.refineAllCameraGroupAndObjectsAndIntrinsic();
   } else if (flow == "intrinsics") calib.refineIntrinsicAndPoseAllCam();
   else if (flow == "objects") calib.refineAllObject3D();
   else if (flow == "group") calib.refineAllCameraGroup();
+  else if (flow == "init") {}
   else { std::fprintf(stderr, "unknown flow %s\n", flow.c_str()); return 2; }
   if (!g_last_error.empty()) { std::fprintf(stderr, "libmcba failed: %s\n", g_last_error.c_str()); return 1; }
   const double avg_err = calib.computeAvgReprojectionError();

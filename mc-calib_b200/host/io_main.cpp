@@ -1,0 +1,97 @@
+// io_main.cpp — CPU-only driver of the host pieces around the refinement path (tests/test_host_io.py):
+//   io_main keypoints <boards.txt> <keypoints_in.yml> <cam_params.yml|None> <keypoints_out.yml> <dump.txt>
+//       Calibration::loadDetectedKeypoints + loadInitialIntrinsics + saveDetectedKeypoints
+//   io_main avgrot <in.txt> <out.txt>          getAverageRotation on lists of rotation vectors
+//   io_main grouppose <in.txt> <out.txt>       CameraGroup::computeObjPoseInCameraGroup + CameraGroupObs::computeObjectsPose
+#include <cstdio>
+#include <fstream>
+#include <string>
+
+#include "McCalibBA.hpp"
+
+using namespace McCalib;
+
+static int keypoints(int argc, char** argv) {
+  if (argc < 7) return 2;
+  Calibration calib;
+  std::ifstream bf(argv[2]);
+  int n_board; bf >> n_board;
+  for (int b = 0; b < n_board; ++b) {                       // Board.cpp:64-72: (nx-1)(ny-1) corners at (x sq, y sq, 0)
+    int nx, ny; float sq; bf >> nx >> ny >> sq;
+    auto board = std::make_shared<Board>();
+    board->board_id_ = b;
+    for (int y = 0; y < ny; ++y) for (int x = 0; x < nx; ++x) board->pts_3d_.push_back(Point3f{x * sq, y * sq, 0.f});
+    calib.boards_3d_[b] = board;
+  }
+  if (!calib.loadDetectedKeypoints(argv[3])) { std::fprintf(stderr, "loadDetectedKeypoints: %s\n", g_last_error.c_str()); return 1; }
+  if (std::string(argv[4]) != "None" && !calib.loadInitialIntrinsics(argv[4])) { std::fprintf(stderr, "loadInitialIntrinsics: %s\n", g_last_error.c_str()); return 1; }
+  if (!calib.saveDetectedKeypoints(argv[5])) return 1;
+  std::ofstream out(argv[6]);
+  out.precision(17);
+  out << calib.cams_.size() << " " << calib.frames_.size() << " " << calib.board_observations_.size() << "\n";
+  for (const auto& c : calib.cams_) {
+    out << c.first << " " << c.second->im_cols_ << " " << c.second->im_rows_ << " " << c.second->distortion_model_ << " " << c.second->board_observations_.size();
+    for (double x : c.second->intrinsics_) out << " " << x;
+    out << "\n";
+  }
+  for (const auto& it : calib.board_observations_) {
+    const BoardObs& bo = *it.second;
+    out << bo.camera_id_ << " " << bo.frame_id_ << " " << bo.board_id_ << " " << bo.pts_2d_.size() << " " << (bo.board_3d_.lock() ? 1 : 0);
+    for (size_t i = 0; i < bo.pts_2d_.size(); ++i) out << " " << bo.charuco_id_[i] << " " << bo.pts_2d_[i].x << " " << bo.pts_2d_[i].y;
+    out << "\n";
+  }
+  return 0;
+}
+
+static int avgrot(char** argv) {
+  std::ifstream in(argv[2]); std::ofstream out(argv[3]);
+  out.precision(17);
+  int n_cases; in >> n_cases;
+  for (int c = 0; c < n_cases; ++c) {
+    int quat, n; in >> quat >> n;
+    std::vector<double> r1(n), r2(n), r3(n);
+    for (int i = 0; i < n; ++i) in >> r1[i] >> r2[i] >> r3[i];
+    const auto r = getAverageRotation(r1, r2, r3, quat != 0);
+    out << r[0] << " " << r[1] << " " << r[2] << "\n";
+  }
+  return 0;
+}
+
+static int grouppose(char** argv) {
+  std::ifstream in(argv[2]); std::ofstream out(argv[3]);
+  out.precision(17);
+  int n_cases; in >> n_cases;
+  for (int c = 0; c < n_cases; ++c) {
+    int ref_cam, n_cam, n_obs, quat; in >> ref_cam >> n_cam >> n_obs >> quat;
+    auto group = std::make_shared<CameraGroup>();
+    group->cam_group_idx_ = 0; group->id_ref_cam_ = ref_cam;
+    for (int k = 0; k < n_cam; ++k) { Pose6 p; for (double& x : p) in >> x; group->relative_camera_pose_[k] = p; }
+    auto frame = std::make_shared<Frame>();
+    auto cgo = std::make_shared<CameraGroupObs>();
+    cgo->cam_group_idx_ = 0; cgo->cam_group_ = group; cgo->quaternion_averaging_ = quat != 0;
+    frame->cam_group_observations_[0] = cgo; group->frames_[0] = frame;
+    std::vector<std::shared_ptr<Object3DObs>> keep;
+    for (int k = 0; k < n_obs; ++k) {
+      auto oo = std::make_shared<Object3DObs>();
+      in >> oo->camera_id_ >> oo->object_3d_id_;
+      for (double& x : oo->pose_) in >> x;
+      keep.push_back(oo); cgo->insertObjectObservation(oo);
+    }
+    group->computeObjPoseInCameraGroup();
+    cgo->computeObjectsPose();
+    out << cgo->object_pose_.size();
+    for (const auto& it : cgo->object_pose_) { out << " " << it.first; for (double x : it.second) out << " " << x; }
+    out << "\n";
+    for (const auto& oo : keep) { for (double x : oo->group_pose_) out << x << " "; out << "\n"; }
+  }
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 4) { std::fprintf(stderr, "usage: %s keypoints|avgrot|grouppose ...\n", argv[0]); return 2; }
+  const std::string mode = argv[1];
+  if (mode == "keypoints") return keypoints(argc, argv);
+  if (mode == "avgrot") return avgrot(argv);
+  if (mode == "grouppose") return grouppose(argv);
+  return 2;
+}

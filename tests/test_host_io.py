@@ -1,0 +1,239 @@
+"""Host pieces either side of the refinement path, CPU only:
+ - detected_keypoints_data.yml / camera-parameter YAML in cv::FileStorage's dialect: files written by OpenCV itself
+   (cv2.FileStorage, the library the reference uses) are read by the C++ facade, and the facade's writer is read back by
+   OpenCV (McCalib.cpp:172-213, :493-548, :662-688);
+ - getAverageRotation (geometrytools.cpp:832-893) against scipy's Markley mean and numpy medians;
+ - CameraGroup::computeObjPoseInCameraGroup + CameraGroupObs::computeObjectsPose (CameraGroup.cpp:153-183,
+   CameraGroupObs.cpp:42-108) against a numpy restatement."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from scipy.spatial.transform import Rotation as Rot
+
+from mcba import synth
+
+cv2 = pytest.importorskip("cv2")
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(REPO, "mc-calib_b200", "host")
+
+
+@pytest.fixture(scope="module")
+def io_main():
+    if not os.path.exists(os.path.join(REPO, "mc-calib_b200", "csrc", "libmcba.so")):
+        pytest.skip("libmcba.so not built")
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    return os.path.join(HOST, "io_main")
+
+
+def write_keypoints_with_opencv(path, s, o, frame_path=lambda c, f: f"/data/Cam_{c:03d}/{f:06d}.png"):
+    """What Calibration::saveDetectedKeypoints emits, through OpenCV's own emitter."""
+    fs = cv2.FileStorage(path, cv2.FILE_STORAGE_WRITE)
+    fs.write("nb_camera", int(s.n_cam))
+    for c in range(s.n_cam):
+        sel = np.nonzero(o.bobs_cam == c)[0]
+        fs.startWriteStruct(f"camera_{c}", cv2.FileNode_MAP)
+        fs.write("img_width", 1920)
+        fs.write("img_height", 1080)
+        fs.startWriteStruct("frame_idxs", cv2.FileNode_SEQ | cv2.FileNode_FLOW)
+        for b in sel:
+            fs.write("", int(o.bobs_frame[b]))
+        fs.endWriteStruct()
+        fs.startWriteStruct("frame_paths", cv2.FileNode_SEQ)
+        for b in sel:
+            fs.write("", frame_path(c, int(o.bobs_frame[b])))
+        fs.endWriteStruct()
+        fs.startWriteStruct("board_idxs", cv2.FileNode_SEQ | cv2.FileNode_FLOW)
+        for b in sel:
+            fs.write("", int(o.bobs_board[b]))
+        fs.endWriteStruct()
+        fs.startWriteStruct("pts_2d", cv2.FileNode_SEQ)
+        for b in sel:
+            fs.startWriteStruct("", cv2.FileNode_SEQ | cv2.FileNode_FLOW)
+            for i in range(o.bobs_ptr[b], o.bobs_ptr[b + 1]):
+                fs.write("", float(o.u[i]))
+                fs.write("", float(o.v[i]))
+            fs.endWriteStruct()
+        fs.endWriteStruct()
+        fs.startWriteStruct("charuco_idxs", cv2.FileNode_SEQ)
+        for b in sel:
+            fs.startWriteStruct("", cv2.FileNode_SEQ | cv2.FileNode_FLOW)
+            for i in range(o.bobs_ptr[b], o.bobs_ptr[b + 1]):
+                fs.write("", int(o.pt_idx[i] - o.bobs_board[b] * s.P))
+            fs.endWriteStruct()
+        fs.endWriteStruct()
+        fs.endWriteStruct()
+    fs.release()
+
+
+def write_camera_params_with_opencv(path, s, intr):
+    fs = cv2.FileStorage(path, cv2.FILE_STORAGE_WRITE)
+    fs.write("nb_camera", int(s.n_cam))
+    for c in range(s.n_cam):
+        fs.startWriteStruct(f"camera_{c}", cv2.FileNode_MAP)
+        K = np.array([[intr[c, 0], 0, intr[c, 2]], [0, intr[c, 1], intr[c, 3]], [0, 0, 1.0]])
+        fs.write("camera_matrix", K)
+        nd = 5 if s.cam_model[c] == 0 else 4
+        fs.write("distortion_vector", intr[c, 4:4 + nd].reshape(1, nd))
+        fs.write("distortion_type", int(s.cam_model[c]))
+        fs.endWriteStruct()
+    fs.release()
+
+
+def write_boards(path, s):
+    nx, ny = s.cfg["grid"]
+    with open(path, "w") as f:
+        f.write(f"{s.n_board}\n" + "".join(f"{nx} {ny} {s.cfg['square']!r}\n" for _ in range(s.n_board)))
+
+
+def read_keypoints_with_opencv(path, n_cam):
+    fs = cv2.FileStorage(path, cv2.FILE_STORAGE_READ)
+    assert int(fs.getNode("nb_camera").real()) == n_cam
+    out = {}
+    for c in range(n_cam):
+        n = fs.getNode(f"camera_{c}")
+        seq = lambda node: [node.at(i) for i in range(node.size())]
+        out[c] = dict(
+            w=int(n.getNode("img_width").real()), h=int(n.getNode("img_height").real()),
+            frames=[int(x.real()) for x in seq(n.getNode("frame_idxs"))],
+            paths=[x.string() for x in seq(n.getNode("frame_paths"))],
+            boards=[int(x.real()) for x in seq(n.getNode("board_idxs"))],
+            pts=[np.array([y.real() for y in seq(x)], np.float32) for x in seq(n.getNode("pts_2d"))],
+            ids=[[int(y.real()) for y in seq(x)] for x in seq(n.getNode("charuco_idxs"))])
+    fs.release()
+    return out
+
+
+def test_keypoint_and_intrinsics_files_round_trip_with_opencv(io_main, tmp_path):
+    s = synth.make_scene("c2", n_frames=12)
+    o = synth.generate_observations(s)
+    kin, kout, cp, dump, boards = (str(tmp_path / n) for n in ("kp_in.yml", "kp_out.yml", "cams.yml", "dump.txt", "boards.txt"))
+    write_keypoints_with_opencv(kin, s, o)
+    write_camera_params_with_opencv(cp, s, s.intr_init)
+    write_boards(boards, s)
+    r = subprocess.run([io_main, "keypoints", boards, kin, cp, kout, dump], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = [l.split() for l in open(dump)]
+    n_cam, n_frames, n_bo = map(int, rows[0])
+    assert (n_cam, n_bo) == (s.n_cam, len(o.bobs_cam)) and n_frames == len(np.unique(o.bobs_frame))
+    for c in range(s.n_cam):                          # intrinsics file -> Camera::intrinsics_
+        row = rows[1 + c]
+        assert [int(x) for x in row[:4]] == [c, 1920, 1080, int(s.cam_model[c])]
+        assert int(row[4]) == int((o.bobs_cam == c).sum())
+        want = s.intr_init[c].copy()
+        if s.cam_model[c] == 1:
+            want[8] = 0.0
+        assert np.array_equal(np.array(row[5:], float), want)
+    # board observations arrive camera by camera, in file order, bit-exact floats
+    order = np.concatenate([np.nonzero(o.bobs_cam == c)[0] for c in range(s.n_cam)])
+    for k, b in enumerate(order):
+        row = rows[1 + s.n_cam + k]
+        npts = int(o.bobs_ptr[b + 1] - o.bobs_ptr[b])
+        assert [int(x) for x in row[:5]] == [int(o.bobs_cam[b]), int(o.bobs_frame[b]), int(o.bobs_board[b]), npts, 1]
+        vals = np.array(row[5:], float).reshape(npts, 3)
+        sl = slice(o.bobs_ptr[b], o.bobs_ptr[b + 1])
+        assert np.array_equal(vals[:, 0].astype(int), o.pt_idx[sl] - o.bobs_board[b] * s.P)
+        assert np.array_equal(vals[:, 1].astype(np.float32), o.u[sl]) and np.array_equal(vals[:, 2].astype(np.float32), o.v[sl])
+    # the facade's writer, read by OpenCV: identical content (frame-major order inside a camera, like the reference)
+    a, b_ = read_keypoints_with_opencv(kin, s.n_cam), read_keypoints_with_opencv(kout, s.n_cam)
+    for c in range(s.n_cam):
+        assert (a[c]["w"], a[c]["h"]) == (b_[c]["w"], b_[c]["h"])
+        key = lambda d: sorted(zip(d["frames"], d["boards"], d["paths"], [tuple(p) for p in d["pts"]], [tuple(i) for i in d["ids"]]))
+        assert key(a[c]) == key(b_[c])
+        assert b_[c]["frames"] == sorted(b_[c]["frames"])
+
+
+def test_keypoint_loader_rejects_inconsistent_file(io_main, tmp_path):
+    bad = tmp_path / "bad.yml"
+    bad.write_text('%YAML:1.0\n---\nnb_camera: 1\ncamera_0:\n   img_width: 10\n   img_height: 10\n   frame_idxs: [ 0, 1 ]\n'
+                   '   frame_paths:\n      - "a"\n      - "b"\n   board_idxs: [ 0 ]\n   pts_2d:\n      - [ 1., 2. ]\n   charuco_idxs:\n      - [ 0 ]\n')
+    boards = tmp_path / "boards.txt"
+    boards.write_text("1\n4 4 0.1\n")
+    r = subprocess.run([io_main, "keypoints", str(boards), str(bad), "None", str(tmp_path / "o.yml"), str(tmp_path / "d.txt")],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "inconsistent" in r.stderr
+
+
+def test_average_rotation(io_main, tmp_path):
+    rng = np.random.default_rng(0)
+    cases = []
+    for k in range(40):
+        quat = k % 2
+        n = int(rng.integers(1, 9))
+        base = Rot.random(random_state=int(rng.integers(1 << 30)))
+        spread = 0.3 if k % 4 < 2 else 1e-3
+        rv = (base * Rot.from_rotvec(spread * rng.standard_normal((n, 3)))).as_rotvec()
+        cases.append((quat, rv))
+    fin, fout = tmp_path / "in.txt", tmp_path / "out.txt"
+    with open(fin, "w") as f:
+        f.write(f"{len(cases)}\n")
+        for quat, rv in cases:
+            f.write(f"{quat} {len(rv)}\n" + "".join(" ".join(repr(float(x)) for x in r) + "\n" for r in rv))
+    subprocess.check_call([io_main, "avgrot", str(fin), str(fout)])
+    got = np.loadtxt(fout).reshape(-1, 3)
+    for (quat, rv), g in zip(cases, got):
+        if quat:
+            want = Rot.from_rotvec(rv).mean()          # Markley et al.: largest eigenvector of sum q q^T
+            assert np.abs(Rot.from_rotvec(g).as_matrix() - want.as_matrix()).max() < 1e-9
+        else:
+            assert np.allclose(g, np.median(rv, axis=0), atol=1e-15)
+
+
+def test_group_pose_initialisation(io_main, tmp_path):
+    rng = np.random.default_rng(1)
+    cases = []
+    for k in range(30):
+        n_cam = int(rng.integers(2, 6))
+        ref = 0
+        cams = np.concatenate([Rot.random(n_cam, random_state=int(rng.integers(1 << 30))).as_rotvec() * 0.3, rng.normal(size=(n_cam, 3))], 1)
+        cams[ref] = 0
+        n_obj = int(rng.integers(1, 3))
+        obj_gt = np.concatenate([Rot.random(n_obj, random_state=int(rng.integers(1 << 30))).as_rotvec(), rng.normal(size=(n_obj, 3)) + [0, 0, 3]], 1)
+        obs = []
+        for c in rng.permutation(n_cam)[:int(rng.integers(1, n_cam + 1))]:
+            if k % 3 == 0 and c == ref:
+                continue                              # no observation from the reference camera: the average is used
+            for ob in range(n_obj):
+                if rng.random() < 0.8:
+                    rv, t = synth.compose(cams[c, :3], cams[c, 3:], obj_gt[ob, :3], obj_gt[ob, 3:])
+                    rv = (Rot.from_rotvec(rv) * Rot.from_rotvec(0.01 * rng.standard_normal(3))).as_rotvec()
+                    obs.append((int(c), ob, np.concatenate([rv, t + 0.01 * rng.standard_normal(3)])))
+        if obs:
+            cases.append((ref, cams, obs, k % 2))
+    fin, fout = tmp_path / "in.txt", tmp_path / "out.txt"
+    with open(fin, "w") as f:
+        f.write(f"{len(cases)}\n")
+        for ref, cams, obs, quat in cases:
+            f.write(f"{ref} {len(cams)} {len(obs)} {quat}\n")
+            for c in cams:
+                f.write(" ".join(repr(float(x)) for x in c) + "\n")
+            for c, ob, p in obs:
+                f.write(f"{c} {ob} " + " ".join(repr(float(x)) for x in p) + "\n")
+    subprocess.check_call([io_main, "grouppose", str(fin), str(fout)])
+    lines = [l.split() for l in open(fout)]
+    li = 0
+    for ref, cams, obs, quat in cases:
+        head = lines[li]; li += 1
+        n_obj = int(head[0])
+        got = {int(head[1 + 7 * j]): np.array(head[2 + 7 * j:8 + 7 * j], float) for j in range(n_obj)}
+        group_pose = np.array([lines[li + j] for j in range(len(obs))], float); li += len(obs)
+        # numpy restatement
+        ing = []
+        for c, ob, p in obs:
+            Rc = Rot.from_rotvec(cams[c, :3])
+            inv = (Rc.inv().as_rotvec(), -Rc.inv().apply(cams[c, 3:]))
+            ing.append(np.concatenate(synth.compose(inv[0], inv[1], p[:3], p[3:])))
+        ing = np.array(ing)
+        for ob in sorted({ob for _, ob, _ in obs}):
+            idx = [j for j, (_, o2, _) in enumerate(obs) if o2 == ob]
+            refs = [j for j in idx if obs[j][0] == ref]
+            if refs:
+                want = ing[refs[-1]]
+            else:
+                r = Rot.from_rotvec(ing[idx, :3]).mean().as_rotvec() if quat else np.median(ing[idx, :3], axis=0)
+                want = np.concatenate([r, ing[idx, 3:].mean(0)])
+            assert np.abs(Rot.from_rotvec(got[ob][:3]).as_matrix() - Rot.from_rotvec(want[:3]).as_matrix()).max() < 1e-9
+            assert np.abs(got[ob][3:] - want[3:]).max() < 1e-12
+            for j in idx:                                 # every observation of the object carries the group pose
+                assert np.allclose(group_pose[j], got[ob], atol=0, rtol=0)
