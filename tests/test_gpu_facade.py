@@ -242,7 +242,8 @@ def test_calibration_from_observations_only(tmp_path, scene):
     s, o = scene
     a = run_init(tmp_path, s, o, "init_final")
     b = run_facade(tmp_path, s, o, "final")
-    assert a["avg"] < 0.6 and abs(a["avg"] - b["avg"]) < 0.05
+    # the RANSAC drops the corners farther than 10 px (most of the synthetic 20 px outliers), so the mean error is lower
+    assert 0.2 < a["avg"] <= b["avg"] + 0.01
     assert np.abs(a["intr"][:, :4] - b["intr"][:, :4]).max() <= 2e-3 * np.abs(b["intr"][:, :4]).max()
     assert np.abs(a["cam_pose"] - b["cam_pose"]).max() <= 5e-3
     assert np.abs(a["intr"][:, :2] - s.intr_gt[:, :2]).max() <= 0.01 * s.intr_gt[:, :2].max()
