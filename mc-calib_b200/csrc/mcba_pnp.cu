@@ -3,16 +3,18 @@
 //   k_pnp_prepare   one thread per corner: pixel -> normalised ray (a, b) and the "working" pixel the inlier test is
 //                   made in (Brown: the detection itself; Kannala: the pinhole re-projection of the undistorted ray,
 //                   geometrytools.cpp:728-742), plus the per-camera working intrinsics (Kannala: zero distortion)
-//   k_pnp_ransac    one warp per observation: lanes evaluate 32 hypotheses at a time (draw 4 corners, three-point pose +
-//                   fourth-point disambiguation, inlier count over all corners of the observation); the sequential
-//                   stopping rule of ransacP3P (geometrytools.cpp:243-300) is then replayed over the 32 counts in draw
-//                   order, so the outcome is the one a sequential run over the same draws would produce. Then the inlier
-//                   mask of the winner and a Levenberg-Marquardt refinement of the pose on the inliers (lanes stride
-//                   over corners, 6x6 normal equations reduced by shuffles in a fixed order).
+//   k_pnp_ransac<G> G lanes per observation (32/G observations per warp): the lanes evaluate G hypotheses at a time (draw 4
+//                   corners, three-point pose + fourth-point disambiguation, inlier count over all corners of the
+//                   observation); the sequential stopping rule of ransacP3P (geometrytools.cpp:243-300) is then replayed
+//                   over the G counts in draw order, so the outcome is the one a sequential run over the same draws
+//                   would produce. Then the inlier mask of the winner.
+//   k_pnp_refine<G> Levenberg-Marquardt refinement of the pose on the inliers (lanes stride over corners, 6x6 normal
+//                   equations reduced over the group by shuffles in a fixed order, driver PnpLm).
 // fp64 throughout; latency/compute bound (a few hundred bytes per observation are read once).
 #include <cuda_runtime.h>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -64,142 +66,177 @@ __device__ __forceinline__ bool pnp_is_inlier(const double* R, const double* t, 
   return du * du + dv * dv < thr2;
 }
 
-// H (upper 21) / g (6) / cost of the pose-only problem at `pose`, over the inliers of the run; all lanes get the sums
-__device__ void pnp_normal_eq(const PnpArgs& a, long long o0, int n, const double* in, const double* pose, int lane,
-                              double* H, double* g, double& cost) {
-  double prep[PREP];
-  prep_block(pose, prep);
-  for (int k = 0; k < 21; ++k) H[k] = 0.0;
-  for (int k = 0; k < 6; ++k) g[k] = 0.0;
-  cost = 0.0;
-  for (int i = lane; i < n; i += 32) {
-    if (!a.mask[o0 + i]) continue;
-    const float* p3 = a.pts + 3 * (size_t)a.pt[o0 + i];
-    const double X0[3] = {(double)p3[0], (double)p3[1], (double)p3[2]};
-    const double2 w = a.w[o0 + i];
-    double r[2], Ju[6], Jv[6];
-    if (!pnp_residual_jac(prep, in, X0, w.x, w.y, r, Ju, Jv)) { cost += 1e12; continue; }   // behind the camera: reject the step
-    cost += r[0] * r[0] + r[1] * r[1];
-    int k = 0;
+// Sub-warp groups: G lanes (a power of two <= 32) work on one observation run, 32/G runs per warp, so that a warp
+// instruction is shared by several runs: a run of 48 corners needs 1-2 draws and 6 pose parameters, far too little to
+// occupy 32 lanes. Shuffles use the full mask with width G; loops are made warp-uniform with __any_sync.
+template <int G> __device__ __forceinline__ double group_sum(double x) {
 #pragma unroll
-    for (int p = 0; p < 6; ++p) {
-#pragma unroll
-      for (int q = p; q < 6; ++q) H[k++] += Ju[p] * Ju[q] + Jv[p] * Jv[q];
-      g[p] += Ju[p] * r[0] + Jv[p] * r[1];
-    }
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    for (int k = 0; k < 21; ++k) H[k] += __shfl_xor_sync(0xffffffffu, H[k], off);
-    for (int k = 0; k < 6; ++k) g[k] += __shfl_xor_sync(0xffffffffu, g[k], off);
-    cost += __shfl_xor_sync(0xffffffffu, cost, off);
-  }
+  for (int off = G / 2; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off, G);
+  return x;
 }
 
-constexpr int PNP_WARPS = 4;
-__global__ void __launch_bounds__(PNP_WARPS * 32) k_pnp_ransac(PnpArgs a) {
-  const int b = blockIdx.x * PNP_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (b >= a.n_bobs) return;
-  const long long o0 = a.bobs_ptr[b];
-  const int n = (int)(a.bobs_ptr[b + 1] - o0);
-  const int cam = a.bobs_cam[b];
+constexpr int PNP_THREADS = 128;
+
+// P3P RANSAC: selected hypothesis, its inlier mask and its (unrefined) pose.
+template <int G>
+__global__ void __launch_bounds__(PNP_THREADS) k_pnp_ransac(PnpArgs a) {
+  const int gtid = blockIdx.x * PNP_THREADS + threadIdx.x;
+  const int b = gtid / G, gl = threadIdx.x & (G - 1);
+  const bool has = b < a.n_bobs;
+  const long long o0 = has ? a.bobs_ptr[b] : 0;
+  const int n = has ? (int)(a.bobs_ptr[b + 1] - o0) : 0;
+  const int cam = has ? a.bobs_cam[b] : 0;
   double in[9];
+#pragma unroll
   for (int k = 0; k < 9; ++k) in[k] = a.wintr[9 * cam + k];
   RansacState st;
   ransac_init(st, a.it);
   double bR[9], bt[3];
+#pragma unroll
   for (int k = 0; k < 9; ++k) bR[k] = 0.0;
+#pragma unroll
   for (int k = 0; k < 3; ++k) bt[k] = 0.0;
-  if (n >= 4) {
-    for (int round = 0; ransac_continue(st, a.it); ++round) {
-      const int h = round * 32 + lane;
-      double R[9], t[3];
-      bool ok = h < a.it;
-      if (ok) {
-        int idx[4];
-        ransac_sample4(a.seed, (unsigned long long)b, (unsigned long long)h, n, idx);
-        double ab4[4][2], X4[4][3];
-        for (int k = 0; k < 4; ++k) {
-          const double2 q = a.ab[o0 + idx[k]];
-          ab4[k][0] = q.x; ab4[k][1] = q.y;
-          ok = ok && a.ok[o0 + idx[k]];
-          const float* p3 = a.pts + 3 * (size_t)a.pt[o0 + idx[k]];
-          X4[k][0] = (double)p3[0]; X4[k][1] = (double)p3[1]; X4[k][2] = (double)p3[2];
-        }
-        const double2 w4 = a.w[o0 + idx[3]];
-        const double w4a[2] = {w4.x, w4.y};
-        ok = ok && p3p_hypothesis(ab4, X4, in, w4a, R, t);
+  const bool live = has && n >= 4;
+#pragma unroll 1
+  for (int round = 0;; ++round) {
+    const bool go = live && ransac_continue(st, a.it);
+    if (!__any_sync(0xffffffffu, go)) break;
+    const int h = round * G + gl;
+    double R[9], t[3];
+    bool ok = go && h < a.it;
+    if (ok) {
+      int idx[4];
+      ransac_sample4(a.seed, (unsigned long long)b, (unsigned long long)h, n, idx);
+      double ab4[4][2], X4[4][3];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double2 q = a.ab[o0 + idx[k]];
+        ab4[k][0] = q.x; ab4[k][1] = q.y;
+        ok = ok && a.ok[o0 + idx[k]];
+        const float* p3 = a.pts + 3 * (size_t)a.pt[o0 + idx[k]];
+        X4[k][0] = (double)p3[0]; X4[k][1] = (double)p3[1]; X4[k][2] = (double)p3[2];
       }
-      int count = 0;
-      if (ok)
-        for (int i = 0; i < n; ++i)
-          count += (a.ok[o0 + i] && pnp_is_inlier(R, t, in, a.pts + 3 * (size_t)a.pt[o0 + i], a.w[o0 + i], a.thr2)) ? 1 : 0;
-      // replay the sequential rule over this round's 32 counts, in draw order (identical on every lane)
-      int new_best_lane = -1;
-      for (int l = 0; l < 32; ++l) {
-        const int cl = __shfl_sync(0xffffffffu, count, l);
-        if (!ransac_continue(st, a.it)) continue;
-        const int prev = st.best_h;
-        ransac_update(st, round * 32 + l, cl, n, a.p);
-        if (st.best_h != prev) new_best_lane = l;
-      }
-      if (new_best_lane >= 0) {
-        for (int k = 0; k < 9; ++k) bR[k] = __shfl_sync(0xffffffffu, R[k], new_best_lane);
-        for (int k = 0; k < 3; ++k) bt[k] = __shfl_sync(0xffffffffu, t[k], new_best_lane);
-      }
+      const double2 w4 = a.w[o0 + idx[3]];
+      const double w4a[2] = {w4.x, w4.y};
+      ok = ok && p3p_hypothesis(ab4, X4, in, w4a, R, t);
     }
+    int count = 0;
+    if (ok) {
+#pragma unroll 1
+      for (int i = 0; i < n; ++i)
+        count += (a.ok[o0 + i] && pnp_is_inlier(R, t, in, a.pts + 3 * (size_t)a.pt[o0 + i], a.w[o0 + i], a.thr2)) ? 1 : 0;
+    }
+    // replay the sequential rule over this round's G counts, in draw order (identical on every lane of the group)
+    int new_best_lane = -1;
+#pragma unroll 1
+    for (int l = 0; l < G; ++l) {
+      const int cl = __shfl_sync(0xffffffffu, count, l, G);
+      if (!go || !ransac_continue(st, a.it)) continue;
+      const int prev = st.best_h;
+      ransac_update(st, round * G + l, cl, n, a.p);
+      if (st.best_h != prev) new_best_lane = l;
+    }
+    const int src = new_best_lane >= 0 ? new_best_lane : 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { const double x = __shfl_sync(0xffffffffu, R[k], src, G); if (new_best_lane >= 0) bR[k] = x; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { const double x = __shfl_sync(0xffffffffu, t[k], src, G); if (new_best_lane >= 0) bt[k] = x; }
   }
-  // inlier mask of the selected hypothesis
+  // inlier mask of the selected hypothesis: lanes of the group stride over the corners
   int cnt = 0;
-  for (int i0 = 0; i0 < n; i0 += 32) {
-    const int i = i0 + lane;
-    bool inl = false;
-    if (i < n && st.best_h >= 0)
-      inl = a.ok[o0 + i] && pnp_is_inlier(bR, bt, in, a.pts + 3 * (size_t)a.pt[o0 + i], a.w[o0 + i], a.thr2);
-    if (i < n) a.mask[o0 + i] = inl ? 1 : 0;
-    cnt += __popc(__ballot_sync(0xffffffffu, inl));
+  for (int i = gl; i < n; i += G) {
+    const bool inl = st.best_h >= 0 && a.ok[o0 + i] &&
+                     pnp_is_inlier(bR, bt, in, a.pts + 3 * (size_t)a.pt[o0 + i], a.w[o0 + i], a.thr2);
+    a.mask[o0 + i] = inl ? 1 : 0;
+    cnt += inl ? 1 : 0;
   }
-  __syncwarp();
-  double pose[6] = {0, 0, 0, 0, 0, 0};
-  if (st.best_h >= 0) { rot_to_rvec(bR, pose); pose[3] = bt[0]; pose[4] = bt[1]; pose[5] = bt[2]; }
-  if (a.pose0 && lane < 6) a.pose0[6 * (size_t)b + lane] = pose[lane];
-  if (a.refine && st.best_h >= 0 && cnt >= 4) {
-    // Levenberg-Marquardt on the 6 pose parameters, damping H + lambda diag(H) as cv::solvePnP's iterative solver
-    double H[21], g[6], cost;
-    pnp_normal_eq(a, o0, n, in, pose, lane, H, g, cost);
-    double lambda = 1e-3;
-    for (int iter = 0; iter < a.refine_it; ++iter) {
-      double A[36], d[6];
-      int k = 0;
-      for (int p = 0; p < 6; ++p)
-        for (int q = p; q < 6; ++q) { A[q * 6 + p] = H[k]; A[p * 6 + q] = H[k]; ++k; }
-      for (int p = 0; p < 6; ++p) { A[p * 6 + p] *= (1.0 + lambda); d[p] = -g[p]; }
-      if (!chol6(A)) { lambda *= 10.0; if (lambda > 1e16) break; continue; }
-      chol6_fwd(A, d); chol6_bwd(A, d);
-      double cand[6], dn = 0.0, xn = 0.0;
-      for (int p = 0; p < 6; ++p) { cand[p] = pose[p] + d[p]; dn += d[p] * d[p]; xn += pose[p] * pose[p]; }
-      double H2[21], g2[6], cost2;
-      pnp_normal_eq(a, o0, n, in, cand, lane, H2, g2, cost2);
-      if (cost2 < cost) {
-        for (int p = 0; p < 6; ++p) { pose[p] = cand[p]; g[p] = g2[p]; }
-        for (int q = 0; q < 21; ++q) H[q] = H2[q];
-        const bool small = (cost - cost2) <= 1e-14 * cost || dn <= 1e-24 * (xn + 1e-24);
-        cost = cost2;
-        lambda = fmax(lambda * 0.1, 1e-16);
-        if (small) break;
-      } else {
-        if (!(dn > 1e-30 * (xn + 1e-30))) break;     // the step no longer changes the pose
-        lambda *= 10.0;
-        if (lambda > 1e16) break;
+#pragma unroll
+  for (int off = G / 2; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off, G);
+  if (has && gl == 0) {
+    double pose[6] = {0, 0, 0, 0, 0, 0};
+    if (st.best_h >= 0) { rot_to_rvec(bR, pose); pose[3] = bt[0]; pose[4] = bt[1]; pose[5] = bt[2]; }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { a.pose0[6 * (size_t)b + k] = pose[k]; a.pose[6 * (size_t)b + k] = pose[k]; }
+    a.n_inl[b] = cnt; a.best_h[b] = st.best_h; a.n_hyp[b] = st.countit;
+  }
+}
+
+// Pose-only Levenberg-Marquardt on the inliers (geometrytools.cpp:314-324), driver in PnpLm.
+template <int G>
+__global__ void __launch_bounds__(PNP_THREADS) k_pnp_refine(PnpArgs a) {
+  const int gtid = blockIdx.x * PNP_THREADS + threadIdx.x;
+  const int b = gtid / G, gl = threadIdx.x & (G - 1);
+  const bool has = b < a.n_bobs && a.best_h[b] >= 0 && a.n_inl[b] >= 4;
+  const long long o0 = has ? a.bobs_ptr[b] : 0;
+  const int n = has ? (int)(a.bobs_ptr[b + 1] - o0) : 0;
+  const int cam = has ? a.bobs_cam[b] : 0;
+  double in[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) in[k] = a.wintr[9 * cam + k];
+  PnpLm lm;
+  {
+    double p0[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) p0[k] = has ? a.pose[6 * (size_t)b + k] : 0.0;
+    lm.init(p0);
+    if (!has) lm.fin = true;
+  }
+#pragma unroll 1
+  for (int iter = 0; iter <= a.refine_it; ++iter) {
+    if (!__any_sync(0xffffffffu, !lm.fin)) break;
+    double cand[6];
+    lm.propose(cand);
+    // H (upper 21) / g (6) / cost at cand over the inliers of the run, summed over the group in a fixed order
+    double prep[PREP];
+    prep_block(cand, prep);
+    double H2[21], g2[6], cost2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 21; ++k) H2[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) g2[k] = 0.0;
+    if (!lm.fin) {
+#pragma unroll 1
+      for (int i = gl; i < n; i += G) {
+        if (!a.mask[o0 + i]) continue;
+        const float* p3 = a.pts + 3 * (size_t)a.pt[o0 + i];
+        const double X0[3] = {(double)p3[0], (double)p3[1], (double)p3[2]};
+        const double2 w = a.w[o0 + i];
+        double r[2], Ju[6], Jv[6];
+        if (!pnp_residual_jac(prep, in, X0, w.x, w.y, r, Ju, Jv)) { cost2 += 1e12; continue; }   // behind the camera: reject the step
+        cost2 += r[0] * r[0] + r[1] * r[1];
+        int k = 0;
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+#pragma unroll
+          for (int q = p; q < 6; ++q) H2[k++] += Ju[p] * Ju[q] + Jv[p] * Jv[q];
+          g2[p] += Ju[p] * r[0] + Jv[p] * r[1];
+        }
       }
     }
+#pragma unroll
+    for (int k = 0; k < 21; ++k) H2[k] = group_sum<G>(H2[k]);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) g2[k] = group_sum<G>(g2[k]);
+    cost2 = group_sum<G>(cost2);
+    lm.update(cand, H2, g2, cost2);
   }
-  if (lane < 6) a.pose[6 * (size_t)b + lane] = pose[lane];
-  if (lane == 0) {
-    a.n_inl[b] = cnt;
-    if (a.best_h) a.best_h[b] = st.best_h;
-    if (a.n_hyp) a.n_hyp[b] = st.countit;
+  if (has && gl == 0) {
+    bool fin = true;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) fin = fin && is_fin(lm.pose[k]);
+    if (fin) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) a.pose[6 * (size_t)b + k] = lm.pose[k];
+    }
   }
+}
+
+template <int G> static void launch_pnp(const PnpArgs& a, cudaStream_t stream, int64_t* launches) {
+  const long long threads = (long long)a.n_bobs * G;
+  const unsigned grid = (unsigned)((threads + PNP_THREADS - 1) / PNP_THREADS);
+  k_pnp_ransac<G><<<grid, PNP_THREADS, 0, stream>>>(a);
+  ++*launches;
+  if (a.refine) { k_pnp_refine<G><<<grid, PNP_THREADS, 0, stream>>>(a); ++*launches; }
 }
 
 static thread_local std::string g_pnp_err;
@@ -274,10 +311,21 @@ int mcba_pnp_ransac(const mcba_pnp_problem* P, const mcba_pnp_options* opt, int 
   PCU(cudaEventRecord(e0, stream));
   k_pnp_wintr<<<(P->n_cam + 127) / 128, 128, 0, stream>>>(a);
   k_pnp_prepare<<<(unsigned)((nb * 32 + 255) / 256), 256, 0, stream>>>(a);
-  k_pnp_ransac<<<(unsigned)((nb + PNP_WARPS - 1) / PNP_WARPS), PNP_WARPS * 32, 0, stream>>>(a);
+  res->kernel_launches = 2;
+  {
+    // lanes per observation run: every lane gets ~10 corners or more (measured on 48-corner boards: G = 4 2.2 ms, 8 2.6 ms,
+    // 16 3.9 ms, 32 6.8 ms for 129 k runs)
+    const double avg = (double)P->n_obs / (double)P->n_bobs;
+    const char* env = getenv("MCBA_PNP_GROUP");
+    int G = avg <= 64.0 ? 4 : (avg <= 128.0 ? 8 : (avg <= 256.0 ? 16 : 32));
+    if (env && (atoi(env) == 4 || atoi(env) == 8 || atoi(env) == 16 || atoi(env) == 32)) G = atoi(env);
+    if (G == 4) launch_pnp<4>(a, stream, &res->kernel_launches);
+    else if (G == 8) launch_pnp<8>(a, stream, &res->kernel_launches);
+    else if (G == 16) launch_pnp<16>(a, stream, &res->kernel_launches);
+    else launch_pnp<32>(a, stream, &res->kernel_launches);
+  }
   PCU(cudaGetLastError());
   PCU(cudaEventRecord(e1, stream));
-  res->kernel_launches = 3;
   PCU(cudaMemcpyAsync(res->pose, a.pose, nb * 48, cudaMemcpyDeviceToHost, stream));
   PCU(cudaMemcpyAsync(res->n_inliers, a.n_inl, nb * 4, cudaMemcpyDeviceToHost, stream));
   PCU(cudaMemcpyAsync(res->inlier_mask, a.mask, no, cudaMemcpyDeviceToHost, stream));

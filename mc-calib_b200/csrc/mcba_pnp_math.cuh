@@ -369,6 +369,92 @@ MCBA_HD bool pnp_residual_jac(const double* prep, const double* in, const double
   return true;
 }
 
+// 6x6 SPD solve for the damped normal equations (H + lambda diag(H)) d = -g, H given as its upper triangle (21).
+// Returns false when the damped matrix is not positive definite.
+MCBA_HD bool pnp_solve6(const double* H, double lambda, const double* g, double* d) {
+  double L[21], inv[6];          // lower factor, row-major packed: L[i(i+1)/2 + j], j <= i
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+#pragma unroll
+    for (int i = j; i < 6; ++i) {
+      // H upper index of (j, i), j <= i: j*6 - j(j-1)/2 + (i - j)
+      double s = H[j * 6 - j * (j - 1) / 2 + (i - j)];
+      if (i == j) s *= (1.0 + lambda);
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+      if (i == j) {
+        if (!(s > 0.0) || !(s <= DBL_MAX)) return false;
+        const double l = sqrt(s);
+        inv[j] = rcp(l);
+        L[j * (j + 1) / 2 + j] = l;
+      } else {
+        L[i * (i + 1) / 2 + j] = s * inv[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {          // forward
+    double s = -g[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s -= L[i * (i + 1) / 2 + k] * d[k];
+    d[i] = s * inv[i];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {         // backward
+    double s = d[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) s -= L[k * (k + 1) / 2 + i] * d[k];
+    d[i] = s * inv[i];
+  }
+  return true;
+}
+
+// Levenberg-Marquardt driver of the pose-only refinement (damping H + lambda diag(H), lambda /10 on success and x10
+// on failure as cv::solvePnP's iterative solver; stops on a relative step below 1e-8 or when the cost can no longer be
+// improved beyond rounding, instead of OpenCV's FLT_EPSILON / 20 iterations). One evaluation (H, g, cost at a point)
+// per iteration: propose() returns the point to evaluate, update() consumes the evaluation.
+struct PnpLm {
+  double pose[6], H[21], g[6], cost, lambda;
+  bool have, fin, stepok;
+  MCBA_HD void init(const double* p0) {
+    for (int k = 0; k < 6; ++k) pose[k] = p0[k];
+    cost = 0.0; lambda = 1e-3; have = false; fin = false; stepok = true;
+  }
+  MCBA_HD void propose(double* cand) {
+    stepok = true;
+    if (!have || fin) { for (int k = 0; k < 6; ++k) cand[k] = pose[k]; return; }
+    double d[6];
+    if (!pnp_solve6(H, lambda, g, d)) { stepok = false; for (int k = 0; k < 6; ++k) cand[k] = pose[k]; return; }
+    double dn = 0.0, xn = 0.0;
+    for (int k = 0; k < 6; ++k) { cand[k] = pose[k] + d[k]; dn += d[k] * d[k]; xn += pose[k] * pose[k]; }
+    if (dn <= 1e-16 * (xn + 1e-16)) {      // |d| <= 1e-8 |x|: take the step, converged
+      for (int k = 0; k < 6; ++k) pose[k] = cand[k];
+      fin = true;
+    }
+  }
+  MCBA_HD void update(const double* cand, const double* H2, const double* g2, double cost2) {
+    if (fin) return;
+    if (!have) {
+      for (int k = 0; k < 21; ++k) H[k] = H2[k];
+      for (int k = 0; k < 6; ++k) g[k] = g2[k];
+      cost = cost2; have = true;
+      if (!(cost2 <= DBL_MAX)) fin = true;   // the starting pose cannot be evaluated
+      return;
+    }
+    if (stepok && cost2 < cost) {
+      for (int k = 0; k < 21; ++k) H[k] = H2[k];
+      for (int k = 0; k < 6; ++k) { g[k] = g2[k]; pose[k] = cand[k]; }
+      if (cost - cost2 <= 1e-12 * cost) fin = true;
+      cost = cost2;
+      lambda = fmax(lambda * 0.1, 1e-16);
+    } else {
+      if (stepok && cost2 - cost <= 1e-12 * cost) fin = true;   // at the minimum up to rounding
+      lambda *= 10.0;
+      if (lambda > 1e16) fin = true;
+    }
+  }
+};
+
 // splitmix64: the counter-based generator behind the RANSAC draws (the reference seeds std::mt19937 from
 // std::random_device at every draw, i.e. it is not reproducible; here draw h of board observation b under seed s is a
 // pure function of (s, b, h)).

@@ -158,28 +158,17 @@ extern "C" int pnptest_ransac(int n, const float* u, const float* v, const float
     }
   };
   if (refine && st.best_h >= 0 && cnt >= 4) {
-    double H[21], g[6], cost; normal_eq(x, H, g, cost);
-    double lambda = 1e-3;
-    for (int iter = 0; iter < refine_it; ++iter) {
-      double A[36], d[6]; int k = 0;
-      for (int a = 0; a < 6; ++a) for (int c = a; c < 6; ++c) { A[c * 6 + a] = H[k]; A[a * 6 + c] = H[k]; ++k; }
-      for (int a = 0; a < 6; ++a) { A[a * 6 + a] *= (1.0 + lambda); d[a] = -g[a]; }
-      if (!chol6(A)) { lambda *= 10.0; if (lambda > 1e16) break; continue; }
-      chol6_fwd(A, d); chol6_bwd(A, d);
-      double cand[6], dn = 0, xn = 0;
-      for (int a = 0; a < 6; ++a) { cand[a] = x[a] + d[a]; dn += d[a] * d[a]; xn += x[a] * x[a]; }
-      double H2[21], g2[6], cost2; normal_eq(cand, H2, g2, cost2);
-      if (cost2 < cost) {
-        for (int a = 0; a < 6; ++a) { x[a] = cand[a]; g[a] = g2[a]; }
-        for (int a = 0; a < 21; ++a) H[a] = H2[a];
-        const bool small = (cost - cost2) <= 1e-14 * cost || dn <= 1e-24 * (xn + 1e-24);
-        cost = cost2; lambda = fmax(lambda * 0.1, 1e-16);
-        if (small) break;
-      } else {
-        if (!(dn > 1e-30 * (xn + 1e-30))) break;
-        lambda *= 10.0; if (lambda > 1e16) break;
-      }
+    PnpLm lm; lm.init(x);
+    for (int iter = 0; iter <= refine_it && !lm.fin; ++iter) {
+      double cand[6], H2[21], g2[6], cost2;
+      lm.propose(cand);
+      if (lm.fin) break;
+      normal_eq(cand, H2, g2, cost2);
+      lm.update(cand, H2, g2, cost2);
     }
+    bool fin = true;
+    for (int k = 0; k < 6; ++k) fin = fin && is_fin(lm.pose[k]);
+    if (fin) for (int k = 0; k < 6; ++k) x[k] = lm.pose[k];
   }
   for (int k = 0; k < 6; ++k) pose[k] = x[k];
   *best_h = st.best_h; *n_hyp = st.countit;
