@@ -33,6 +33,15 @@ def main():
     o = synth.generate_observations(s)
     prob, init, gt = synth.make_problem(s, o, 1)
     P = pnp.PnpProblem(prob, s.intr_gt)
+    try:      # pinned host arrays, like bench.py's e2e leg
+        import torch
+        P._pinned = []
+        for name in ("u", "v", "pt_idx", "bobs_ptr", "bobs_cam"):
+            t = torch.from_numpy(getattr(P, name)).pin_memory()
+            P._pinned.append(t)
+            setattr(P, name, t.numpy())
+    except Exception:
+        pass
     opt = pnp.default_options(threshold_px=args.threshold, max_iterations=1000, seed=1)
     pnp.ransac(P, opt)                       # warm-up: context, module load
     k_ms, t_ms = [], []
