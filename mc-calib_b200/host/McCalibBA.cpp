@@ -292,9 +292,76 @@ void CameraGroup::refineCameraGroupAndObjectsAndIntrinsics(const int nb_iteratio
 void CameraGroup::refineCameraGroupAndObjectsThenIntrinsics(const int nb_iterations, bool with_intrinsics) { refineStage(4, nb_iterations, with_intrinsics); }
 
 // ---------------------------------------------------------------------------------------------- Calibration
+// stage-1 packing of every camera's valid board observations, camera-major (what the batched mode of libmcba wants:
+// problem id == camera slot, one e-block per board observation)
+namespace {
+void packAllCamerasStage1(Calibration& calib, Packed& pk, std::vector<int32_t>* cam_problem) {
+  for (const auto& it_cam : calib.cams_) {
+    const std::shared_ptr<Camera>& cam = it_cam.second;
+    for (const auto& it : cam->board_observations_) {                  // Camera.cpp:272
+      auto bo = it.second.lock();
+      if (!bo || !bo->valid_) continue;                                // :274
+      auto board = bo->board_3d_.lock();
+      if (!board || bo->charuco_id_.empty()) continue;
+      const int cs = pk.camSlot(cam, nullptr, false);
+      const int bs = pk.boardSlot(board, nullptr, false);              // only for its point table
+      (void)bs;
+      pk.beginBobs(cs, pk.poseSlot(&bo->pose_), 0);
+      for (size_t i = 0; i < bo->charuco_id_.size(); ++i) pk.addObs(bo->pts_2d_[i], pk.board_pt_base[board->board_id_] + bo->charuco_id_[i]);
+    }
+  }
+  pk.board_is_ref.clear(); pk.board_pose.clear(); pk.board_pose_dst.clear();   // stage 1 has no board block
+  pk.stage = 1;
+  if (cam_problem) { cam_problem->resize(pk.cam_model.size()); for (size_t c = 0; c < cam_problem->size(); ++c) (*cam_problem)[c] = (int32_t)c; }
+}
+}  // namespace
+
+// McCalib.cpp:713-716 loops Camera::refineIntrinsicCalibration over the cameras: the per-camera problems are independent,
+// so they are handed to libmcba as ONE batched launch (mcba_solve_batched: one Levenberg-Marquardt state per camera on
+// the device); a single camera goes through the same path.
 void Calibration::refineIntrinsicAndPoseAllCam() {
   g_cuda_device = cuda_device_;
-  for (const auto& it : cams_) it.second->refineIntrinsicCalibration(nb_iterations_);   // McCalib.cpp:714-715
+  Packed pk; std::vector<int32_t> cam_problem;
+  packAllCamerasStage1(*this, pk, &cam_problem);
+  if (pk.u.empty()) return;
+  mcba_problem P = pk.problem();
+  P.cam_problem = cam_problem.data(); P.n_problems = (int32_t)cam_problem.size();
+  void* h = nullptr;
+  int rc = mcba_create(&h, &P, g_cuda_device);
+  if (rc == MCBA_OK) {
+    mcba_options opt; mcba_default_options(&opt);
+    opt.max_num_iterations = nb_iterations_; opt.verbose = 0;          // one table per camera would interleave
+    mcba_params X = pk.params();
+    std::vector<mcba_summary> summaries(cam_problem.size());
+    rc = mcba_solve_batched(h, &X, &opt, summaries.data());
+    if (rc == MCBA_OK) pk.scatter(1);
+  }
+  if (rc != MCBA_OK) { g_last_error = h ? mcba_last_error(h) : "mcba_create failed"; std::fprintf(stderr, "[McCalibBA] libmcba error %d: %s\n", rc, g_last_error.c_str()); }
+  mcba_destroy(h);
+}
+
+// McCalib.cpp:722-726 evaluates BoardObs::computeReprojectionError for every board observation (BoardObs.cpp:165-200:
+// mean corner error under pose_ and the camera's intrinsics; it only logs). Returns the mean of those per-board means.
+double Calibration::computeReproErrAllBoard() {
+  g_cuda_device = cuda_device_;
+  Packed pk;
+  packAllCamerasStage1(*this, pk, nullptr);
+  if (pk.u.empty()) return 0.0;
+  mcba_problem P = pk.problem();
+  void* h = nullptr;
+  std::vector<double> err(pk.u.size());
+  int rc = mcba_create(&h, &P, g_cuda_device);
+  if (rc == MCBA_OK) { mcba_params X = pk.params(); rc = mcba_reprojection_errors(h, &X, err.data()); }
+  if (rc != MCBA_OK) { g_last_error = h ? mcba_last_error(h) : "mcba_create failed"; mcba_destroy(h); return -1.0; }
+  mcba_destroy(h);
+  double sum = 0.0;
+  const size_t nb = pk.bobs_cam.size();
+  for (size_t b = 0; b < nb; ++b) {
+    double s = 0.0;
+    for (int64_t i = pk.bobs_ptr[b]; i < pk.bobs_ptr[b + 1]; ++i) s += err[i];
+    sum += s / (double)(pk.bobs_ptr[b + 1] - pk.bobs_ptr[b]);
+  }
+  return sum / (double)nb;
 }
 void Calibration::refineAllObject3D() {
   g_cuda_device = cuda_device_;

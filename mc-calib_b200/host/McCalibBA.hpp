@@ -136,6 +136,18 @@ public:
   std::map<int, std::shared_ptr<Frame>> frames_;
 
   bool loadConfig(const std::string& yaml_path);       // the keys of McCalib.cpp:39-79 that the refinement path uses
+  // Calibration::Calibration(config_path) (McCalib.cpp:30-135): the keys above plus number_camera, number_board,
+  // boards_index, number_x/y_square[_per_board], square_size[_per_board], quaternion_averaging, cam_params_path,
+  // keypoints_path, save_path; creates cams_ (Camera(i, distortion)) and boards_3d_ (Board.cpp:22-72 corner grid)
+  bool initialization(const std::string& config_path);
+  std::string cam_params_path_, keypoints_path_, save_path_;
+  int quaternion_averaging_ = 1;
+  bool boardExtraction();                              // McCalib.cpp:219-226, keypoint-file branch (detection is out of scope)
+  bool initializeCalibrationAllCam();                  // McCalib.cpp:662-695, parameter-file branch (cv::calibrateCamera is out of scope)
+  void initIntrinsic();                                // McCalib.cpp:2085-2092
+  double computeReproErrAllBoard();                    // McCalib.cpp:722-726 (returns the mean of the per-board means it logs)
+  bool saveIntrinsics(const std::string& path) const;  // camera_matrix / distortion_vector / distortion_type per camera: the
+                                                       // layout initializeCalibrationAllCam reads back
   // on-disk formats either side of the path (cv::FileStorage YAML)
   void insertNewBoard(const int cam_idx, const int frame_idx, const int board_idx, const std::vector<Point2f>& pts_2d,
                       const std::vector<int>& charuco_idx, const std::string& frame_path);   // McCalib.cpp:594-642

@@ -391,3 +391,89 @@ bool Calibration::loadInitialIntrinsics(const std::string& path) {
 }
 
 }  // namespace McCalib
+
+// ------------------------------------------------------------------------------------------ workflow head
+namespace McCalib {
+
+bool Calibration::initialization(const std::string& config_path) {
+  if (config_path.size() < 4 || config_path.substr(config_path.size() - 4) != ".yml") { g_last_error = "config must be a .yml"; return false; }   // :31-34
+  ocvyaml::Node fs; ocvyaml::Parser parser; std::string err;
+  if (!parser.parseFile(config_path, fs, &err)) { g_last_error = err; return false; }
+  const int nb_camera = fs["number_camera"].asInt(0);                          // :41-44
+  int nb_board = fs["number_board"].asInt(0);                                  // :46-49
+  if (nb_camera <= 0 || nb_board <= 0) { g_last_error = "number_camera and number_board must be positive"; return false; }
+  const int nb_x_square = fs["number_x_square"].asInt(0), nb_y_square = fs["number_y_square"].asInt(0);
+  // quaternion_averaging: the reference asks for the key "quaternion_averaging:" (with the colon, McCalib.cpp:57), which
+  // no file has, so its quaternion_averaging_ always keeps the default (1); same here
+  if (!fs["ransac_threshold"].empty()) ransac_thresh_ = (float)fs["ransac_threshold"].asDouble(10.0);
+  if (!fs["number_iterations"].empty()) nb_iterations_ = fs["number_iterations"].asInt(1000);
+  distortion_model_ = fs["distortion_model"].asInt(0);
+  distortion_per_camera_ = fs["distortion_per_camera"].asInts();
+  std::vector<int> boards_index = fs["boards_index"].asInts();
+  cam_params_path_ = fs["cam_params_path"].scalar; keypoints_path_ = fs["keypoints_path"].scalar; save_path_ = fs["save_path"].scalar;
+  std::vector<double> square_size_per_board = fs["square_size_per_board"].asDoubles();
+  std::vector<int> nx_per_board = fs["number_x_square_per_board"].asInts(), ny_per_board = fs["number_y_square_per_board"].asInts();
+  fix_intrinsic_ = fs["fix_intrinsic"].asInt(0);
+  if (!boards_index.empty()) nb_board = (int)boards_index.size();              // :82-84
+  int max_board_idx = nb_board - 1;
+  if (!boards_index.empty()) max_board_idx = *std::max_element(boards_index.begin(), boards_index.end());
+  if (nx_per_board.empty()) { nx_per_board.assign(max_board_idx + 1, nb_x_square); ny_per_board.assign(max_board_idx + 1, nb_y_square); }   // :89-92
+  if (distortion_per_camera_.empty()) distortion_per_camera_.assign(nb_camera, distortion_model_);   // :105-106
+  if ((int)distortion_per_camera_.size() < nb_camera) { g_last_error = "distortion_per_camera shorter than number_camera"; return false; }
+  for (int i = 0; i < nb_camera; ++i) {                                        // :109-113
+    auto cam = std::make_shared<Camera>();
+    cam->cam_idx_ = i; cam->distortion_model_ = distortion_per_camera_[i];
+    cams_[i] = cam;
+  }
+  if (boards_index.empty()) { boards_index.resize(nb_board); for (int b = 0; b < nb_board; ++b) boards_index[b] = b; }   // :116-119
+  for (int board_idx = 0; board_idx < nb_board; ++board_idx) {                 // :125-134 + Board.cpp:22-72
+    int nx, ny; double sq;
+    if (square_size_per_board.empty()) { nx = nb_x_square; ny = nb_y_square; sq = fs["square_size"].asDouble(0.0); }
+    else {
+      const int bi = boards_index[board_idx];
+      if (bi >= (int)nx_per_board.size() || bi >= (int)ny_per_board.size() || bi >= (int)square_size_per_board.size()) { g_last_error = "per-board lists shorter than the board index"; return false; }
+      nx = nx_per_board[bi]; ny = ny_per_board[bi]; sq = square_size_per_board[bi];
+    }
+    auto board = std::make_shared<Board>();
+    board->board_id_ = board_idx;
+    for (int y = 0; y < ny - 1; ++y) for (int x = 0; x < nx - 1; ++x) board->pts_3d_.push_back(Point3f{(float)(x * sq), (float)(y * sq), 0.f});
+    boards_3d_[board_idx] = board;
+  }
+  return true;
+}
+
+bool Calibration::boardExtraction() {
+  if (keypoints_path_.empty() || keypoints_path_ == "None") { g_last_error = "board detection from images is outside this library: set keypoints_path"; return false; }
+  return loadDetectedKeypoints(keypoints_path_);
+}
+
+bool Calibration::initializeCalibrationAllCam() {
+  if (cam_params_path_.empty() || cam_params_path_ == "None") { g_last_error = "intrinsic initialisation from images (cv::calibrateCamera) is outside this library: set cam_params_path"; return false; }
+  return loadInitialIntrinsics(cam_params_path_);
+}
+
+void Calibration::initIntrinsic() {
+  if (!initializeCalibrationAllCam()) { std::fprintf(stderr, "[McCalibBA] %s\n", g_last_error.c_str()); return; }
+  estimatePoseAllBoards();
+  if (fix_intrinsic_ == 0) refineIntrinsicAndPoseAllCam();
+  computeReproErrAllBoard();
+}
+
+bool Calibration::saveIntrinsics(const std::string& path) const {
+  std::ofstream f(path);
+  if (!f) return false;
+  f.precision(17);
+  f << "%YAML:1.0\n---\nnb_camera: " << cams_.size() << "\n";
+  for (const auto& it : cams_) {
+    const auto& in = it.second->intrinsics_;
+    f << "camera_" << it.first << ":\n";
+    f << "   camera_matrix: !!opencv-matrix\n      rows: 3\n      cols: 3\n      dt: d\n      data: [ " << in[0] << ", 0., " << in[2] << ", 0., " << in[1] << ", " << in[3] << ", 0., 0., 1. ]\n";
+    const int nd = it.second->distortion_model_ == 0 ? 5 : 4;
+    f << "   distortion_vector: !!opencv-matrix\n      rows: 1\n      cols: " << nd << "\n      dt: d\n      data: [ ";
+    for (int k = 0; k < nd; ++k) f << in[4 + k] << (k + 1 < nd ? ", " : " ]\n");
+    f << "   distortion_type: " << it.second->distortion_model_ << "\n";
+  }
+  return (bool)f;
+}
+
+}  // namespace McCalib

@@ -61,8 +61,20 @@ class Parser {
     while (std::getline(in, l)) {
       if (!l.empty() && l.back() == '\r') l.pop_back();
       if (l.rfind("%YAML", 0) == 0 || l == "---" || l == "...") continue;
+      // comments: '#' at the start of the line or after white space, outside quotes (the reference's config files
+      // carry one on almost every line)
+      {
+        bool q = false; char qc = 0;
+        for (size_t i = 0; i < l.size(); ++i) {
+          const char c = l[i];
+          if (q) { if (c == '\\') ++i; else if (c == qc) q = false; continue; }
+          if (c == '"' || c == '\'') { q = true; qc = c; continue; }
+          if (c == '#' && (i == 0 || l[i - 1] == ' ' || l[i - 1] == '\t')) { l.erase(i); break; }
+        }
+        while (!l.empty() && (l.back() == ' ' || l.back() == '\t')) l.pop_back();
+      }
       const size_t first = l.find_first_not_of(' ');
-      if (first == std::string::npos || l[first] == '#') continue;
+      if (first == std::string::npos) continue;
       lines_.push_back({(int)first, l.substr(first)});
     }
     root = Node();

@@ -3,6 +3,7 @@
 //       Calibration::loadDetectedKeypoints + loadInitialIntrinsics + saveDetectedKeypoints
 //   io_main avgrot <in.txt> <out.txt>          getAverageRotation on lists of rotation vectors
 //   io_main grouppose <in.txt> <out.txt>       CameraGroup::computeObjPoseInCameraGroup + CameraGroupObs::computeObjectsPose
+//   io_main config <config.yml> <out.txt>      Calibration::initialization (the constructor of the reference's Calibration)
 #include <cstdio>
 #include <fstream>
 #include <string>
@@ -87,11 +88,30 @@ static int grouppose(char** argv) {
   return 0;
 }
 
+static int config(char** argv) {
+  Calibration calib;
+  if (!calib.initialization(argv[2])) { std::fprintf(stderr, "initialization: %s\n", g_last_error.c_str()); return 1; }
+  std::ofstream out(argv[3]);
+  out.precision(9);
+  out << calib.cams_.size() << " " << calib.boards_3d_.size() << " " << calib.nb_iterations_ << " " << calib.ransac_thresh_ << " "
+      << calib.fix_intrinsic_ << " " << calib.quaternion_averaging_ << "\n";
+  out << calib.cam_params_path_ << "\n" << calib.keypoints_path_ << "\n" << calib.save_path_ << "\n";
+  for (const auto& c : calib.cams_) out << c.second->distortion_model_ << " ";
+  out << "\n";
+  for (const auto& b : calib.boards_3d_) {
+    out << b.second->pts_3d_.size();
+    for (const Point3f& p : b.second->pts_3d_) out << " " << p.x << " " << p.y << " " << p.z;
+    out << "\n";
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 4) { std::fprintf(stderr, "usage: %s keypoints|avgrot|grouppose ...\n", argv[0]); return 2; }
   const std::string mode = argv[1];
   if (mode == "keypoints") return keypoints(argc, argv);
   if (mode == "avgrot") return avgrot(argv);
   if (mode == "grouppose") return grouppose(argv);
+  if (mode == "config") return config(argv);
   return 2;
 }

@@ -247,3 +247,63 @@ def test_calibration_from_observations_only(tmp_path, scene):
     assert np.abs(a["intr"][:, :4] - b["intr"][:, :4]).max() <= 2e-3 * np.abs(b["intr"][:, :4]).max()
     assert np.abs(a["cam_pose"] - b["cam_pose"]).max() <= 5e-3
     assert np.abs(a["intr"][:, :2] - s.intr_gt[:, :2]).max() <= 0.01 * s.intr_gt[:, :2].max()
+
+
+def test_workflow_head_from_files(tmp_path):
+    """calibrate.cpp's first steps from files only: Calibration(config) -> boardExtraction (keypoint YAML written by
+    OpenCV) -> initIntrinsic (camera-parameter YAML written by OpenCV, batched P3P RANSAC, batched stage-1 LM). The
+    refined intrinsics (read back with OpenCV) are checked against a Python run of the same two GPU calls and the
+    ground truth."""
+    import cv2
+    from mcba import pnp
+    import test_host_io as hio
+    s = synth.make_scene("c2", n_frames=80)
+    o = synth.generate_observations(s)
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    cfg, kp, cp, out, kp_out = (str(tmp_path / n) for n in ("config.yml", "kp.yml", "cams.yml", "intr.yml", "kp_out.yml"))
+    hio.write_keypoints_with_opencv(kp, s, o)
+    hio.write_camera_params_with_opencv(cp, s, s.intr_init)
+    nx, ny = s.cfg["grid"]
+    hio.write_config(cfg, n_cam=s.n_cam, n_board=s.n_board, nx=nx + 1, ny=ny + 1, square=s.cfg["square"],
+                     dist_pc="[" + ", ".join(str(int(m)) for m in s.cam_model) + "]", cam_params=cp, keypoints=kp, thr=10, iters=200)
+    r = subprocess.run([os.path.join(HOST, "calibrate_main"), cfg, out, kp_out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("valid board observations")][0].split()
+    n_valid, n_kept, mean_err = int(line[3]), int(line[6]), float(line[-2])
+    fs = cv2.FileStorage(out, cv2.FILE_STORAGE_READ)
+    got = np.zeros((s.n_cam, 9))
+    for c in range(s.n_cam):
+        n = fs.getNode(f"camera_{c}")
+        K, D = n.getNode("camera_matrix").mat(), n.getNode("distortion_vector").mat().ravel()
+        got[c, :4] = [K[0, 0], K[1, 1], K[0, 2], K[1, 2]]
+        got[c, 4:4 + len(D)] = D
+        assert int(n.getNode("distortion_type").real()) == int(s.cam_model[c])
+    fs.release()
+    # the same two GPU calls from Python, on the facade's packing order (camera-major)
+    prob, init, gt = synth.make_problem(s, o, 1)
+    order = np.concatenate([np.nonzero(prob.bobs_cam == c)[0] for c in range(s.n_cam)])
+    obs = np.concatenate([np.arange(prob.bobs_ptr[b], prob.bobs_ptr[b + 1]) for b in order])
+    counts = np.diff(prob.bobs_ptr)[order]
+    intr0 = s.intr_init.copy()
+    intr0[s.cam_model == 1, 8] = 0.0
+    sub = mcba.Problem(1, prob.u[obs], prob.v[obs], prob.pt_idx[obs], np.concatenate([[0], np.cumsum(counts)]), prob.bobs_cam[order],
+                       np.arange(len(order)), np.zeros(len(order)), prob.pts_xyz, prob.cam_model, len(order), 0)
+    # estimatePoseAllBoards walks board_observations_ in insertion order = camera-major file order
+    r1 = pnp.ransac(pnp.PnpProblem(sub, intr0), pnp.default_options(threshold_px=10.0, max_iterations=200, seed=0))
+    assert n_valid == int((r1.n_inliers >= 4).sum()) and n_kept == int(r1.inlier_mask.sum())
+    keep = r1.inlier_mask.astype(bool)
+    cnt2 = np.array([keep[a:b].sum() for a, b in zip(sub.bobs_ptr[:-1], sub.bobs_ptr[1:])])
+    sub2 = mcba.Problem(1, sub.u[keep], sub.v[keep], sub.pt_idx[keep], np.concatenate([[0], np.cumsum(cnt2)]), sub.bobs_cam,
+                        np.arange(len(order)), np.zeros(len(order)), prob.pts_xyz, prob.cam_model, len(order), 0,
+                        cam_problem=np.arange(s.n_cam), n_problems=s.n_cam)
+    p = mcba.Params(np.zeros((s.n_cam, 6)), r1.pose, np.zeros((0, 6)), intr0)
+    h = mcba.Handle(sub2)
+    h.solve_batched(p, mcba.default_options(max_num_iterations=200))
+    err = None
+    h.close()
+    assert np.abs(got - p.intrinsics).max() <= 1e-9 * np.abs(p.intrinsics).max()
+    assert np.abs(got[:, :2] - s.intr_gt[:, :2]).max() <= 0.01 * s.intr_gt[:, :2].max()
+    assert 0.2 < mean_err < 0.6
+    # the re-saved keypoints no longer hold the corners the RANSAC rejected
+    kept_file = hio.read_keypoints_with_opencv(kp_out, s.n_cam)
+    assert sum(len(x) for c in kept_file.values() for x in c["ids"]) == n_kept

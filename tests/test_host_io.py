@@ -237,3 +237,84 @@ def test_group_pose_initialisation(io_main, tmp_path):
             assert np.abs(got[ob][3:] - want[3:]).max() < 1e-12
             for j in idx:                                 # every observation of the object carries the group pose
                 assert np.allclose(group_pose[j], got[ob], atol=0, rtol=0)
+
+
+CONFIG_TEMPLATE = """%YAML:1.0
+
+######################################## Boards Parameters ###################################################
+number_x_square: {nx}         # number of squares in the X direction
+number_y_square: {ny}         # number of squares the Y direction
+resolution_x: 500          # horizontal resolution in pixel
+resolution_y: 500          # vertical resolution in pixel
+length_square: 0.04        # parameters on the marker (can be kept as it is)
+length_marker: 0.03        # parameters on the marker (can be kept as it is)
+number_board: {n_board}            # number of boards used for calibration
+boards_index: {boards_index}           # leave it empty [] if the board index are ranging from zero to number_board
+square_size: {square}         # size of each square of the board in cm/mm/whatever you want
+
+############# Boards Parameters for different board size (leave empty if all boards have the same size) #################
+number_x_square_per_board: {nx_pb}
+number_y_square_per_board: {ny_pb}
+square_size_per_board: {sq_pb}
+
+######################################## Camera Parameters ###################################################
+distortion_model: {dist}             # 0:Brown (perspective) // 1: Kannala (fisheye)
+distortion_per_camera : {dist_pc}         # specify the model per camera
+number_camera: {n_cam}           # number of cameras in the rig to calibrate
+refine_corner: 1           # activate or deactivate the corner refinement
+min_perc_pts: 0.5           # min percentage of points visible to assume a good detection
+
+cam_params_path: "{cam_params}"   # file with cameras intrinsics to initialize the intrinsic, write "None" if no initialization available
+fix_intrinsic: {fix} #if 1 then the intrinsic parameters will not be estimated nor refined (initial value needed)
+
+######################################## Images Parameters ###################################################
+root_path: "../data/Images"
+cam_prefix: "Cam_"
+keypoints_path: "{keypoints}" # "None" #
+
+######################################## Optimization Parameters #############################################
+quaternion_averaging: 1    # use Quaternion Averaging or median for average rotation
+ransac_threshold: {thr}       # RANSAC threshold in pixel (keep it high just to remove strong outliers)
+number_iterations: {iters}    # Max number of iterations for the non linear refinement
+
+######################################## Output Parameters ###################################################
+save_path: "{save}"
+save_detection: 0
+save_reprojection: 0
+camera_params_file_name: "" # "name.yml"
+"""
+
+
+def write_config(path, **kw):
+    d = dict(nx=5, ny=5, n_board=1, boards_index="[]", square=0.192, nx_pb="[]", ny_pb="[]", sq_pb="[]", dist=0, dist_pc="[]",
+             n_cam=2, cam_params="None", fix=0, keypoints="None", thr=10, iters=1000, save="/tmp/out")
+    d.update(kw)
+    with open(path, "w") as f:
+        f.write(CONFIG_TEMPLATE.format(**d))
+
+
+def test_config_constructor(io_main, tmp_path):
+    """Calibration::Calibration(config) (McCalib.cpp:30-135, Board.cpp:22-72) on config files in the reference's layout
+    (a '#' comment on almost every line, 'key : value' with a space before the colon, empty lists)."""
+    cfg, out = str(tmp_path / "c.yml"), str(tmp_path / "o.txt")
+    write_config(cfg, n_cam=3, n_board=2, nx=5, ny=4, square=0.192, dist=0, dist_pc="[0, 1, 0]", thr=7.5, iters=250, fix=1,
+                 cam_params="/x/cams.yml", keypoints="/x/kp.yml")
+    subprocess.check_call([io_main, "config", cfg, out])
+    rows = open(out).read().split("\n")
+    assert rows[0].split() == ["3", "2", "250", "7.5", "1", "1"]
+    assert rows[1:4] == ["/x/cams.yml", "/x/kp.yml", "/tmp/out"]
+    assert rows[4].split() == ["0", "1", "0"]
+    for b in range(2):
+        v = np.array(rows[5 + b].split(), float)
+        assert int(v[0]) == 4 * 3                          # (nx - 1)(ny - 1) corners
+        pts = v[1:].reshape(-1, 3)
+        want = np.array([[x * np.float32(0.192), y * np.float32(0.192), 0] for y in range(3) for x in range(4)], np.float32)
+        assert np.allclose(pts, want, rtol=1e-7)
+    # boards of different sizes selected through boards_index
+    write_config(cfg, n_cam=1, n_board=2, boards_index="[2, 0]", nx_pb="[5, 9, 7]", ny_pb="[5, 9, 4]", sq_pb="[0.1, 0.2, 0.3]")
+    subprocess.check_call([io_main, "config", cfg, out])
+    rows = open(out).read().split("\n")
+    assert rows[0].split()[:2] == ["1", "2"]
+    v0, v1 = (np.array(rows[5 + b].split(), float) for b in range(2))
+    assert int(v0[0]) == 6 * 3 and int(v1[0]) == 4 * 4
+    assert np.isclose(v0[1:].reshape(-1, 3)[1, 0], 0.3) and np.isclose(v1[1:].reshape(-1, 3)[1, 0], 0.1)
