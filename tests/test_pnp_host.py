@@ -59,3 +59,56 @@ def test_abi_has_no_cpu_fallback():
     P, opt, _ = pnp_util.make_case("c1_t2")
     with pytest.raises(mcba.McbaError):
         pnp.ransac(P, opt)
+
+
+def _run_one(hostlib, xyz, uv, intr, model=0, thr=2.0, it=50, seed=3):
+    import ctypes as C
+    n = len(xyz)
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    u, v = np.ascontiguousarray(uv[:, 0], np.float32), np.ascontiguousarray(uv[:, 1], np.float32)
+    pose, pose0, mask = np.zeros(6), np.zeros(6), np.zeros(max(n, 1), np.uint8)
+    bh, nh = C.c_int(), C.c_int()
+    dp = mcba.c_f64p
+    cnt = hostlib.pnptest_ransac(n, u.ctypes.data_as(mcba.c_f32p), v.ctypes.data_as(mcba.c_f32p), xyz.ctypes.data_as(mcba.c_f32p),
+                                 model, np.ascontiguousarray(intr, np.float64).ctypes.data_as(dp), thr, it, 0.99, 1, 20, seed, 0,
+                                 pose.ctypes.data_as(dp), pose0.ctypes.data_as(dp), mask.ctypes.data_as(mcba.c_u8p),
+                                 C.byref(bh), C.byref(nh))
+    return cnt, bh.value, nh.value, pose, mask[:n]
+
+
+def test_degenerate_and_hostile_inputs(hostlib):
+    """Collinear corners, non-finite pixels, points behind the camera, exactly four corners: never a crash, never a
+    non-finite pose, and 'no pose' (best = -1, zero inliers) where no hypothesis can exist."""
+    from mcba import synth
+    intr = synth.BROWN_GT
+    rng = np.random.default_rng(0)
+    rv, t = np.array([0.2, -0.1, 0.05]), np.array([0.1, -0.05, 2.0])
+    R = pnp_util.rot(rv)
+    grid = np.array([[x * 0.1, y * 0.1, 0.0] for y in range(4) for x in range(4)])
+    uv = synth.project(intr, np.int32(0), grid @ R.T + t)
+    # exact data: all inliers, pose recovered
+    cnt, bh, nh, pose, mask = _run_one(hostlib, grid, uv, intr)
+    assert cnt == 16 and bh >= 0 and pnp_util.pose_diff(pose, np.concatenate([rv, t])) < 1e-5
+    # four corners only
+    cnt, bh, nh, pose, mask = _run_one(hostlib, grid[[0, 3, 12, 15]], uv[[0, 3, 12, 15]], intr)
+    assert cnt == 4 and np.isfinite(pose).all() and pnp_util.pose_diff(pose, np.concatenate([rv, t])) < 1e-5
+    # every corner on one line: P3P is degenerate for every draw
+    line = np.array([[x * 0.05, 0.0, 0.0] for x in range(10)])
+    uvl = synth.project(intr, np.int32(0), line @ R.T + t)
+    cnt, bh, nh, pose, mask = _run_one(hostlib, line, uvl, intr)
+    assert (cnt, bh) == (0, -1) and nh == 50 and not pose.any() and not mask.any()
+    # non-finite and absurd pixels among good ones: they are never inliers, the pose is still found
+    bad = uv.copy()
+    bad[1] = [np.nan, 5.0]
+    bad[7] = [np.inf, -np.inf]
+    bad[9] = [1e30, 1e30]
+    cnt, bh, nh, pose, mask = _run_one(hostlib, grid, bad, intr)
+    assert np.isfinite(pose).all() and cnt == 13 and not mask[[1, 7, 9]].any()
+    assert pnp_util.pose_diff(pose, np.concatenate([rv, t])) < 1e-5
+    # everything non-finite: no pose
+    cnt, bh, nh, pose, mask = _run_one(hostlib, grid, np.full_like(uv, np.nan), intr)
+    assert (cnt, bh) == (0, -1) and not pose.any()
+    # pure noise: whatever is selected is finite
+    for k in range(20):
+        cnt, bh, nh, pose, mask = _run_one(hostlib, rng.normal(size=(12, 3)), rng.uniform(0, 1900, size=(12, 2)), intr, seed=k)
+        assert np.isfinite(pose).all() and cnt == int(mask.sum())
