@@ -459,7 +459,11 @@ static int cholesky_reduced(Handle* H) {
   static const bool want_prof = getenv("MCBA_CHOL_PROF") != nullptr;
   if (want_prof && !H->d_chol_prof) { CU(cudaMalloc((void**)&H->d_chol_prof, 8 * sizeof(long long))); CU(cudaMemset(H->d_chol_prof, 0, 8 * sizeof(long long))); }
   long long* prof = H->d_chol_prof;
-  void* args[] = {&S, &n, &z, &fail, &prof};
+  // back-substitution: 1 = CTA 0 alone, pipelined, no grid sync (its update traffic, n^2/2 doubles through one SM, only
+  // pays off for small systems: 0.532 vs 0.539 ms at n = 1020); 0 = updates spread over the CTAs, one grid sync per block
+  static const int bs_env = []() { const char* e = getenv("MCBA_CHOL_BACKSOLVE"); return e ? atoi(e) : -1; }();
+  int mode = bs_env >= 0 ? bs_env : (n <= 1536 ? 1 : 0);
+  void* args[] = {&S, &n, &z, &fail, &prof, &mode};
   ++H->n_launches;
   CU(cudaLaunchCooperativeKernel((void*)k_chol_coop, dim3(H->chol_grid), dim3(CC_THREADS), args, CC_SMEM, H->stream));
   return MCBA_OK;

@@ -682,9 +682,10 @@ __global__ void k_build_reduced(const double* __restrict__ FF, const double* __r
 // performs the forward substitution for free), grid sync, DMMA trailing update on 64x64 lower tiles, grid sync.
 // CTA 0 finishes with the backward substitution L^T z = y.
 constexpr int CC_B = 64, CC_LD = 68, CC_DL = 65, CC_THREADS = 256;
-constexpr int CC_SMEM = (2 * CC_B * CC_DL + 2 * CC_B * CC_LD + CC_B) * 8;
+constexpr int CC_SMEM = (2 * CC_B * CC_DL + 2 * CC_B * CC_LD + CC_B + 2 * CC_B + 4 * CC_B) * 8;
 __global__ void __launch_bounds__(CC_THREADS) k_chol_coop(double* __restrict__ S, int n, double* __restrict__ z,
-                                                          int* __restrict__ fail, long long* __restrict__ prof) {
+                                                          int* __restrict__ fail, long long* __restrict__ prof,
+                                                          int backsolve_mode) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) double sm[];
@@ -856,6 +857,96 @@ __global__ void __launch_bounds__(CC_THREADS) k_chol_coop(double* __restrict__ S
     __threadfence();
     grid.sync();
     CC_PROF(4);
+  }
+  // ---- backward substitution L^T z = y (y = row n of S).
+  // backsolve_mode 1 (default): CTA 0 alone, no grid sync. y lives in shared memory; per 64-block b (from the last one)
+  // warp 0 runs the 64-step solve of the diagonal block while warps 1-7 fetch the next diagonal block and apply the
+  // DEFERRED part of the previous block's update (columns left of the next chunk); then all warps apply block b's
+  // update to the one chunk the next solve needs. No grid sync, but all update traffic (n^2/2 doubles) goes through
+  // one SM: chosen by the host for small systems only (mcba_api.cu, cholesky_reduced).
+  if (backsolve_mode == 1) {
+    if (blockIdx.x != 0) return;
+    double* yrow = S + (size_t)n * n;
+    double* ysm = Pa;                     // [n <= 2*CC_B*CC_LD]: Pa and Pb are contiguous
+    double* zbuf = invd + CC_B;           // [2][64] z of the block being solved / of the previous block
+    double* red = invd + 3 * CC_B;        // [4][64]
+    double* Lcur = Lm; double* Lnext = D;
+    const int nblk = (n + CC_B - 1) / CC_B;
+    __syncthreads();
+    for (int i = tid; i < n; i += CC_THREADS) ysm[i] = yrow[i];
+    {
+      const int j0 = (nblk - 1) * CC_B, jb = min(CC_B, n - j0);
+      for (int e = tid; e < CC_B * CC_B; e += CC_THREADS) {
+        const int r = e >> 6, c = e & 63;
+        Lcur[r * CC_DL + c] = (r < jb && c <= r) ? S[(size_t)(j0 + r) * n + j0 + c] : 0.0;
+      }
+    }
+    __syncthreads();
+    for (int b = nblk - 1; b >= 0; --b) {
+      const int j0 = b * CC_B, jb = min(CC_B, n - j0);
+      double* zb = zbuf + (b & 1) * CC_B;
+      const double* zprev = zbuf + ((b + 1) & 1) * CC_B;
+      if (warp == 0) {
+        if (lane < jb) invd[lane] = 1.0 / Lcur[lane * CC_DL + lane];
+        if (lane + 32 < jb) invd[lane + 32] = 1.0 / Lcur[(lane + 32) * CC_DL + lane + 32];
+        __syncwarp();
+        double a0 = (lane < jb) ? ysm[j0 + lane] : 0.0, a1 = (lane + 32 < jb) ? ysm[j0 + lane + 32] : 0.0;
+        for (int j = jb - 1; j >= 0; --j) {
+          const double zj = __shfl_sync(0xffffffffu, (j < 32) ? a0 : a1, j & 31) * invd[j];
+          if (lane == (j & 31)) { if (j < 32) a0 = zj; else a1 = zj; }
+          if (lane < j) a0 -= zj * Lcur[j * CC_DL + lane];
+          if (lane + 32 < j) a1 -= zj * Lcur[j * CC_DL + lane + 32];
+        }
+        zb[lane] = (lane < jb) ? a0 : 0.0;
+        zb[lane + 32] = (lane + 32 < jb) ? a1 : 0.0;
+        if (lane < jb) ysm[j0 + lane] = a0;
+        if (lane + 32 < jb) ysm[j0 + lane + 32] = a1;
+      } else {
+        const int t = tid - 32, nt = CC_THREADS - 32;
+        if (b > 0) {                      // next diagonal block
+          const int p0 = (b - 1) * CC_B;
+          for (int e = t; e < CC_B * CC_B; e += nt) {
+            const int r = e >> 6, c = e & 63;
+            Lnext[r * CC_DL + c] = (c <= r) ? S[(size_t)(p0 + r) * n + p0 + c] : 0.0;
+          }
+        }
+        if (b + 1 < nblk) {               // deferred update of block b+1 on the columns left of chunk b
+          const int q0 = (b + 1) * CC_B, qb = min(CC_B, n - q0);
+          for (int i = t; i < j0; i += nt) {
+            double s0 = 0.0, s1 = 0.0;
+            const double* col = S + (size_t)q0 * n + i;
+            // 16 loads in flight per thread: one SM has to pull up to 0.5 MB per block out of L2
+#pragma unroll 1
+            for (int k = 0; k < CC_B; k += 16) {
+              double v[16];
+#pragma unroll
+              for (int u = 0; u < 16; ++u) v[u] = (k + u < qb) ? col[(size_t)(k + u) * n] : 0.0;
+#pragma unroll
+              for (int u = 0; u < 16; u += 2) { s0 += v[u] * zprev[k + u]; s1 += v[u + 1] * zprev[k + u + 1]; }
+            }
+            ysm[i] -= s0 + s1;
+          }
+        }
+      }
+      __syncthreads();
+      if (b > 0) {                        // block b's update of chunk b-1, all threads
+        const int i = j0 - CC_B + (tid & 63), kg = tid >> 6;
+        double v[16], s0 = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) { const int k = kg + 4 * kk; v[kk] = (k < jb) ? S[(size_t)(j0 + k) * n + i] : 0.0; }
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) s0 += v[kk] * zb[kg + 4 * kk];
+        red[kg * 64 + (tid & 63)] = s0;
+        __syncthreads();
+        if (tid < 64) ysm[j0 - CC_B + tid] -= (red[tid] + red[64 + tid]) + (red[128 + tid] + red[192 + tid]);
+      }
+      __syncthreads();
+      double* tmp = Lcur; Lcur = Lnext; Lnext = tmp;
+    }
+    const bool failed = *fail != 0;
+    for (int i = tid; i < n; i += CC_THREADS) z[i] = failed ? 0.0 : ysm[i];
+    CC_PROF(5);
+    return;
   }
   // ---- backward substitution L^T z = y (y = row n of S, in place). Per 64-block, from the last one: CTA 0 solves the
   // diagonal block and publishes z_b; one grid sync; then the update y[i] -= sum_k L[j0+k][i] z_b[k] of the columns to
