@@ -19,6 +19,7 @@
 #include <cstring>
 #include <chrono>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -102,7 +103,7 @@ struct Handle {
   // peer-memory path of the Schur reduction (k_syrk_sum_p2p)
   bool p2p = false; unsigned long long p2p_epoch = 0;
   unsigned long long* d_p2p_flags = nullptr; unsigned int* d_p2p_counter = nullptr; int* d_p2p_err = nullptr;
-  double* d_p2p_stage = nullptr;
+  double* d_p2p_stage = nullptr; bool ZtZ_pooled = false;
   double* peer_stage[P2P_MAX_RANKS] = {nullptr}; double* peer_ZtZ[P2P_MAX_RANKS] = {nullptr}; unsigned long long* peer_flags[P2P_MAX_RANKS] = {nullptr};
   std::vector<void*> ipc_opened;
   // LM state
@@ -584,10 +585,41 @@ static int download_params(Handle* H, mcba_params* p) {
 // (mcba_comm_init, and mcba_set_stage after the buffers were reallocated). Falls back to the NCCL allreduce
 // (p2p = false) if anything is refused on any rank; MCBA_P2P=0 disables it.
 struct IpcRecord { cudaIpcMemHandle_t h[3]; long long off[3]; int ok; int pad; };
+// Buffers whose CUDA IPC handles go to other ranks are never cudaFree'd while the process lives: freeing an exported
+// allocation before every importer has closed its mapping is undefined behaviour, and mcba_destroy is not a
+// collective. They are recycled through this process-wide pool instead (one allocation of >= 2 MB each, so that an IPC
+// handle covers exactly one buffer).
+struct ExportPool {
+  struct Item { void* p; size_t bytes; int device; bool used; };
+  std::mutex m; std::vector<Item> items;
+  void* acquire(int device, size_t bytes) {
+    bytes = std::max<size_t>(bytes, (size_t)2 << 20);
+    std::lock_guard<std::mutex> g(m);
+    for (auto& it : items)
+      if (!it.used && it.device == device && it.bytes >= bytes && it.bytes <= 2 * bytes) { it.used = true; return it.p; }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    items.push_back({p, bytes, device, true});
+    return p;
+  }
+  void release(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> g(m);
+    for (auto& it : items) if (it.p == p) it.used = false;
+  }
+};
+static ExportPool g_export_pool;
 static int close_p2p(Handle* H) {
   for (void* p : H->ipc_opened) cudaIpcCloseMemHandle(p);
   H->ipc_opened.clear(); H->p2p = false;
   return MCBA_OK;
+}
+// give the exported buffers of this handle back to the pool (after every rank has unmapped them, or at destruction,
+// when no kernel of any rank can touch them any more: k_syrk_sum_p2p only returns once all peers are done with them)
+static void release_exported(Handle* H) {
+  g_export_pool.release(H->d_p2p_stage); H->d_p2p_stage = nullptr;
+  g_export_pool.release(H->d_p2p_flags); H->d_p2p_flags = nullptr;
+  if (H->ZtZ_pooled) { g_export_pool.release(H->d_ZtZ); H->d_ZtZ = nullptr; H->ZtZ_pooled = false; }
 }
 static int setup_p2p(Handle* H) {
   close_p2p(H);
@@ -597,13 +629,25 @@ static int setup_p2p(Handle* H) {
   typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
   static range_fn get_range = []() -> range_fn { void* l = dlopen("libcuda.so.1", RTLD_NOW); return l ? (range_fn)dlsym(l, "cuMemGetAddressRange_v2") : nullptr; }();
   const int N = H->n_ranks;
-  if (!H->d_p2p_flags) {
-    if (dalloc(H, &H->d_p2p_flags, (size_t)1 << 18) || dalloc(H, &H->d_p2p_counter, (size_t)2) || dalloc(H, &H->d_p2p_err, (size_t)1)) return MCBA_ERR_CUDA;   // flags: 2 MB, an allocation of their own
-    CU(cudaMemset(H->d_p2p_flags, 0, ((size_t)1 << 18) * sizeof(unsigned long long)));
+  if (!H->d_p2p_counter) {
+    if (dalloc(H, &H->d_p2p_counter, (size_t)2) || dalloc(H, &H->d_p2p_err, (size_t)1)) return MCBA_ERR_CUDA;
     CU(cudaMemset(H->d_p2p_counter, 0, 2 * sizeof(unsigned int))); CU(cudaMemset(H->d_p2p_err, 0, sizeof(int)));
   }
-  const size_t stage_n = std::max<size_t>((size_t)H->syrk_tiles * SY_T * SY_T, (size_t)1 << 18);
-  if (dalloc(H, &H->d_p2p_stage, stage_n)) return MCBA_ERR_CUDA;
+  // exported buffers come from the pool and are cleared BEFORE their handles are published (a peer may start writing
+  // flags as soon as it has opened them); the epochs restart with them
+  g_export_pool.release(H->d_p2p_stage); g_export_pool.release(H->d_p2p_flags);
+  const size_t zz_bytes = (size_t)H->ldz * H->ldz * sizeof(double);
+  H->d_p2p_stage = (double*)g_export_pool.acquire(H->device, (size_t)H->syrk_tiles * SY_T * SY_T * sizeof(double));
+  H->d_p2p_flags = (unsigned long long*)g_export_pool.acquire(H->device, (size_t)2 * P2P_MAX_RANKS * sizeof(unsigned long long));
+  if (!H->ZtZ_pooled) {
+    double* zz = (double*)g_export_pool.acquire(H->device, zz_bytes);
+    if (zz) { dfree(&H->d_ZtZ); H->d_ZtZ = zz; H->ZtZ_pooled = true; }
+  }
+  if (!H->d_p2p_stage || !H->d_p2p_flags || !H->ZtZ_pooled) { H->err = "cudaMalloc(exported buffers)"; return MCBA_ERR_CUDA; }
+  CU(cudaMemset(H->d_ZtZ, 0, zz_bytes));   // the lower triangle is never written
+  CU(cudaMemset(H->d_p2p_flags, 0, (size_t)2 * P2P_MAX_RANKS * sizeof(unsigned long long)));
+  CU(cudaDeviceSynchronize());
+  H->p2p_epoch = 0;
   IpcRecord mine; std::memset(&mine, 0, sizeof(mine));
   void* ptrs[3] = {H->d_p2p_stage, H->d_ZtZ, H->d_p2p_flags};
   mine.ok = get_range ? 1 : 0;
@@ -705,8 +749,9 @@ void mcba_destroy(void* h) {
     cudaFree(H->d_chol_prof);
   }
   close_p2p(H);
+  release_exported(H);
   if (H->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(H->comm);
-  dfree(&H->d_p2p_flags); dfree(&H->d_p2p_counter); dfree(&H->d_p2p_err); dfree(&H->d_p2p_stage);
+  dfree(&H->d_p2p_counter); dfree(&H->d_p2p_err);
   for (auto& p : H->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : H->free_events) cudaEventDestroy(e);
   if (H->tm_a) { cudaEventDestroy(H->tm_a); cudaEventDestroy(H->tm_b); }
@@ -825,10 +870,11 @@ int mcba_set_stage(void* h, int stage) {
   CU(cudaSetDevice(H->device));
   if (stage == H->stage) return MCBA_OK;
   int rc;
-  if (H->n_ranks > 1) {   // every rank unmaps its peers' buffers before anybody frees them
+  if (H->n_ranks > 1) {   // every rank unmaps its peers' buffers before anybody recycles them
     close_p2p(H);
     if ((rc = allreduce_sum(H, H->d_scalars, 1))) return rc;
     CU(cudaStreamSynchronize(H->stream));
+    release_exported(H);
   }
   rc = setup_stage(H, stage);
   if (rc) return rc;
