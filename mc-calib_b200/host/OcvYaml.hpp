@@ -185,7 +185,13 @@ class Parser {
     }
     Node n;
     if (rest.empty()) {
-      if (pos_ < lines_.size() && (lines_[pos_].indent > parent_indent ||
+      // cv::FileStorage puts an empty (or short) collection of a block parent on its own, deeper line: "key:\n   []"
+      if (pos_ < lines_.size() && lines_[pos_].indent > parent_indent &&
+          (lines_[pos_].text[0] == '[' || lines_[pos_].text[0] == '{')) {
+        const std::string t = lines_[pos_].text;
+        ++pos_;
+        n = parseFlowFrom(t);
+      } else if (pos_ < lines_.size() && (lines_[pos_].indent > parent_indent ||
                                    (lines_[pos_].indent == parent_indent && lines_[pos_].text.rfind("- ", 0) == 0)))
         n = parseBlock(lines_[pos_].indent);
       else { n.kind = Node::SCALAR; }

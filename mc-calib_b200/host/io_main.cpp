@@ -4,11 +4,13 @@
 //   io_main avgrot <in.txt> <out.txt>          getAverageRotation on lists of rotation vectors
 //   io_main grouppose <in.txt> <out.txt>       CameraGroup::computeObjPoseInCameraGroup + CameraGroupObs::computeObjectsPose
 //   io_main config <config.yml> <out.txt>      Calibration::initialization (the constructor of the reference's Calibration)
+//   io_main yamldump <in.yml> <out.json>       the parsed tree of a cv::FileStorage YAML file as JSON
 #include <cstdio>
 #include <fstream>
 #include <string>
 
 #include "McCalibBA.hpp"
+#include "OcvYaml.hpp"
 
 using namespace McCalib;
 
@@ -106,6 +108,34 @@ static int config(char** argv) {
   return 0;
 }
 
+// canonical JSON of a parsed file: scalars as strings, maps in file order
+static void dumpNode(const ocvyaml::Node& n, std::ofstream& out) {
+  if (n.kind == ocvyaml::Node::SEQ) {
+    out << "[";
+    for (size_t i = 0; i < n.seq.size(); ++i) { if (i) out << ","; dumpNode(n.seq[i], out); }
+    out << "]";
+  } else if (n.kind == ocvyaml::Node::MAP) {
+    out << "{";
+    for (size_t i = 0; i < n.map.size(); ++i) {
+      if (i) out << ",";
+      out << "\"" << n.map[i].first << "\":";
+      dumpNode(n.map[i].second, out);
+    }
+    out << "}";
+  } else {
+    out << "\"";
+    for (char c : n.scalar) { if (c == '"' || c == '\\') out << '\\'; out << c; }
+    out << "\"";
+  }
+}
+static int yamldump(char** argv) {
+  ocvyaml::Node root; ocvyaml::Parser parser; std::string err;
+  if (!parser.parseFile(argv[2], root, &err)) { std::fprintf(stderr, "parse: %s\n", err.c_str()); return 1; }
+  std::ofstream out(argv[3]);
+  dumpNode(root, out);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 4) { std::fprintf(stderr, "usage: %s keypoints|avgrot|grouppose ...\n", argv[0]); return 2; }
   const std::string mode = argv[1];
@@ -113,5 +143,6 @@ int main(int argc, char** argv) {
   if (mode == "avgrot") return avgrot(argv);
   if (mode == "grouppose") return grouppose(argv);
   if (mode == "config") return config(argv);
+  if (mode == "yamldump") return yamldump(argv);
   return 2;
 }

@@ -318,3 +318,103 @@ def test_config_constructor(io_main, tmp_path):
     v0, v1 = (np.array(rows[5 + b].split(), float) for b in range(2))
     assert int(v0[0]) == 6 * 3 and int(v1[0]) == 4 * 4
     assert np.isclose(v0[1:].reshape(-1, 3)[1, 0], 0.3) and np.isclose(v1[1:].reshape(-1, 3)[1, 0], 0.1)
+
+
+def test_yaml_reader_on_random_opencv_files(io_main, tmp_path):
+    """Random nested documents emitted by cv::FileStorage (block and flow sequences and maps, strings that need
+    quoting, negative / exponent numbers, long flow sequences that wrap, matrices) parse to the tree OpenCV reads back."""
+    import json
+    rng = np.random.default_rng(0)
+    words = ["a", "Cam_001/000012.png", "with space", "x:y", "#hash", "1e5", "", "-", "[b]", "q\"uote", "tab\tin"]
+
+    def gen(fs, depth, name):
+        """writes a random value under `name`, returns the expected canonical tree"""
+        kind = rng.integers(0, 6 if depth < 3 else 3)
+        if kind == 0:
+            v = int(rng.integers(-10**6, 10**6))
+            fs.write(name, v)
+            return str(v)
+        if kind == 1:
+            v = float(rng.choice([rng.normal() * 10.0 ** rng.integers(-12, 12), float(rng.integers(-5, 5)), 0.1, -2.5e-7]))
+            fs.write(name, v)
+            return ("f", v)
+        if kind == 2:
+            v = str(rng.choice(words))
+            fs.write(name, v)
+            return ("s", v)
+        if kind == 3:
+            n = int(rng.integers(0, 40))
+            flow = bool(rng.integers(0, 2))
+            fs.startWriteStruct(name, cv2.FileNode_SEQ | (cv2.FileNode_FLOW if flow else 0))
+            out = []
+            for _ in range(n):
+                if flow:
+                    v = float(np.float32(rng.normal() * 1000))
+                    fs.write("", v)
+                    out.append(("f", v))
+                else:
+                    out.append(gen(fs, depth + 1, ""))
+            fs.endWriteStruct()
+            return out
+        if kind == 4:
+            n = int(rng.integers(1, 6))
+            fs.startWriteStruct(name, cv2.FileNode_MAP)
+            out = {}
+            for k in range(n):
+                key = f"key_{depth}_{k}"
+                out[key] = gen(fs, depth + 1, key)
+            fs.endWriteStruct()
+            return out
+        r, c = int(rng.integers(1, 5)), int(rng.integers(1, 7))
+        m = rng.normal(size=(r, c)) * 100
+        fs.write(name, m)
+        return {"rows": str(r), "cols": str(c), "dt": ("s", "d"), "data": [("f", float(x)) for x in m.ravel()]}
+
+    def check(got, want, path):
+        if isinstance(want, dict):
+            assert isinstance(got, dict) and list(got.keys()) == list(want.keys()), path
+            for k in want:
+                check(got[k], want[k], path + "/" + k)
+        elif isinstance(want, list):
+            assert isinstance(got, list) and len(got) == len(want), (path, got, want)
+            for i, (g, w) in enumerate(zip(got, want)):
+                check(g, w, f"{path}[{i}]")
+        elif isinstance(want, tuple) and want[0] == "f":
+            assert float(got) == pytest.approx(want[1], rel=1e-15, abs=0), (path, got, want)
+        elif isinstance(want, tuple):
+            assert got == want[1], (path, got, want)
+        else:
+            assert got == want, (path, got, want)
+
+    for trial in range(80):
+        f, out = str(tmp_path / f"r{trial}.yml"), str(tmp_path / f"r{trial}.json")
+        fs = cv2.FileStorage(f, cv2.FILE_STORAGE_WRITE)
+        want = {}
+        for k in range(int(rng.integers(1, 8))):
+            want[f"top_{k}"] = gen(fs, 0, f"top_{k}")
+        fs.release()
+        r = subprocess.run([io_main, "yamldump", f, out], capture_output=True, text=True)
+        assert r.returncode == 0, (r.stderr, open(f).read())
+        check(json.loads(open(out).read(), strict=False), want, f"trial{trial}")
+
+
+def test_keypoint_file_with_an_empty_camera(io_main, tmp_path):
+    """A camera without any detection: OpenCV writes its block sequences as '[]' on a line of their own."""
+    s = synth.make_scene("c2", n_frames=6)
+    o = synth.generate_observations(s)
+    # drop every observation of camera 1
+    keep = np.nonzero(o.bobs_cam != 1)[0]
+    o2 = synth.Scene()
+    o2.frame_lo, o2.frame_hi = o.frame_lo, o.frame_hi
+    sel = np.concatenate([np.arange(o.bobs_ptr[b], o.bobs_ptr[b + 1]) for b in keep])
+    cnt = np.diff(o.bobs_ptr)[keep]
+    o2.bobs_frame, o2.bobs_cam, o2.bobs_board = o.bobs_frame[keep], o.bobs_cam[keep], o.bobs_board[keep]
+    o2.bobs_ptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    o2.u, o2.v, o2.pt_idx = o.u[sel], o.v[sel], o.pt_idx[sel]
+    kin, kout, dump, boards = (str(tmp_path / n) for n in ("kp.yml", "kp_out.yml", "dump.txt", "boards.txt"))
+    write_keypoints_with_opencv(kin, s, o2)
+    assert "[]" in open(kin).read()
+    write_boards(boards, s)
+    r = subprocess.run([io_main, "keypoints", boards, kin, "None", kout, dump], capture_output=True, text=True)
+    # the reference asserts frame_idxs.size() != 0 for every camera (McCalib.cpp:201); the loader reports it instead of aborting
+    assert r.returncode == 1 and "camera_1" in r.stderr
