@@ -355,7 +355,11 @@ bool Calibration::saveDetectedKeypoints(const std::string& path) const {
         }
     writeFlow(f, "   ", "frame_idxs: ", frame_idxs);
     f << "   frame_paths:\n";
-    for (const std::string& p : frame_paths) f << "      - \"" << p << "\"\n";
+    for (const std::string& p : frame_paths) {   // quoted, with the two escapes cv::FileStorage itself uses
+      f << "      - \"";
+      for (char ch : p) { if (ch == '"' || ch == '\\') f << '\\'; f << ch; }
+      f << "\"\n";
+    }
     writeFlow(f, "   ", "board_idxs: ", board_idxs);
     f << "   pts_2d:\n";
     for (const BoardObs* bo : obs) {

@@ -109,7 +109,7 @@ def test_keypoint_and_intrinsics_files_round_trip_with_opencv(io_main, tmp_path)
     s = synth.make_scene("c2", n_frames=12)
     o = synth.generate_observations(s)
     kin, kout, cp, dump, boards = (str(tmp_path / n) for n in ("kp_in.yml", "kp_out.yml", "cams.yml", "dump.txt", "boards.txt"))
-    write_keypoints_with_opencv(kin, s, o)
+    write_keypoints_with_opencv(kin, s, o, frame_path=lambda c, f: f"/data/My \"Rig\"/Cam_{c:03d}\\{f:06d} #1.png")
     write_camera_params_with_opencv(cp, s, s.intr_init)
     write_boards(boards, s)
     r = subprocess.run([io_main, "keypoints", boards, kin, cp, kout, dump], capture_output=True, text=True)
