@@ -316,24 +316,31 @@ def main():
 
     # ---- pose initialisation that feeds the BA: every board observation of this rank's shard in
     # one mcba_pnp_ransac call (P3P RANSAC + pose refinement), host buffers in, poses out; shards are independent ----
-    pose_init = None
-    try:
+    pose_init, pi_local = None, None
+    try:      # local work only inside the try: a rank that fails here must still take part in the collectives below
         from mcba import pnp
         p1, _, gt1 = synth.make_problem(s, o, 1)
         P1 = pinned_problem(torch, pnp.PnpProblem(p1, s.intr_gt))
         popt = pnp.default_options(threshold_px=10.0, max_iterations=1000, seed=1)
         pnp.ransac(P1, popt, device=local_rank)
         runs = [pnp.ransac(P1, popt, device=local_rank) for _ in range(3)]
-        k_ms, t_ms = min(r.kernel_ms for r in runs), min(r.total_ms for r in runs)
-        k_ms, t_ms = allmax(k_ms), allmax(t_ms)
-        nb_global = int(allsum(float(P1.n_bobs)))
-        pose_init = {"board_observations": nb_global, "kernel_ms": k_ms, "total_ms": t_ms,
-                     "bobs_per_s_kernels": nb_global / (k_ms * 1e-3), "bobs_per_s_e2e": nb_global / (t_ms * 1e-3),
-                     "kernel_launches": int(runs[-1].kernel_launches), "draws": int(runs[-1].n_hypotheses.sum()),
-                     "note": "threshold 10 px, <= 1000 draws (the reference's YAML defaults); e2e = pinned host arrays -> device, "
-                             "4 kernels, poses / inlier masks back; OpenCV single-thread loop of the reference: tools/bench_pnp.py"}
+        pi_local = (min(r.kernel_ms for r in runs), min(r.total_ms for r in runs), float(P1.n_bobs),
+                    int(runs[-1].kernel_launches), int(runs[-1].n_hypotheses.sum()))
     except Exception as e:   # the BA line must not depend on the extra leg
         pose_init = {"error": repr(e)}
+    k_ms = allmax(pi_local[0] if pi_local else -1.0)
+    t_ms = allmax(pi_local[1] if pi_local else -1.0)
+    nb_global = int(allsum(pi_local[2] if pi_local else 0.0))
+    n_ok = int(allsum(1.0 if pi_local else 0.0))
+    if pi_local and n_ok == world:
+        pose_init = {"board_observations": nb_global, "kernel_ms": k_ms, "total_ms": t_ms,
+                     "bobs_per_s_kernels": nb_global / (k_ms * 1e-3), "bobs_per_s_e2e": nb_global / (t_ms * 1e-3),
+                     "kernel_launches": pi_local[3], "draws_rank0": pi_local[4],
+                     "note": "threshold 10 px, <= 1000 draws (the reference's YAML defaults); e2e = pinned host arrays -> device, "
+                             "4 kernels, poses / inlier masks back; every rank poses its own shard, no collective; "
+                             "OpenCV single-thread loop of the reference: tools/bench_pnp.py"}
+    elif pose_init is None:
+        pose_init = {"error": "the pose_init leg failed on another rank"}
 
     # ---- CPU baseline (rank 0, N = 1 only): oracle port, bounded sample ---------------------------------------------
     cpu = None

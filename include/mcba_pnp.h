@@ -1,7 +1,8 @@
 /*
  * mcba_pnp.h — C ABI of the pose initialisation that feeds the bundle adjustment: every board
  * (or object) observation gets its pose w.r.t. its camera from a P3P RANSAC followed by a pose-only non-linear
- * refinement on the inliers — all observations of a calibration in ONE launch, one warp per observation.
+ * refinement on the inliers — all observations of a calibration in ONE call (four kernels; a group of 4-32 lanes per
+ * observation, several observations per warp).
  *
  * Replaces, in the reference (paths under /root/reference/McCalib/):
  *   ransacP3PDistortion / ransacP3P          src/geometrytools.cpp:709-751, :233-326

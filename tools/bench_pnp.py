@@ -55,7 +55,7 @@ def main():
     line = {
         "metric": "board-observation poses per second (P3P RANSAC + pose refinement)", "unit": "bobs/s",
         "value": P.n_bobs / (k * 1e-3), "e2e": {"value": P.n_bobs / (t * 1e-3), "unit": "bobs/s",
-                                                "includes": "H2D of the observations, 3 kernels, D2H of poses/masks, device allocation"},
+                                                "includes": "H2D of the observations (pinned host arrays), 4 kernels, D2H of poses/masks, device allocation"},
         "kernel_ms": k, "total_ms": t, "n_bobs": int(P.n_bobs), "n_obs": int(P.n_obs),
         "draws_total": int(r.n_hypotheses.sum()), "draws_evaluated_lanes": int(32 * np.ceil(r.n_hypotheses / 32).sum()),
         "without_pose": int((r.best_hypothesis < 0).sum()), "mean_inlier_fraction": float(r.n_inliers.sum() / P.n_obs),
