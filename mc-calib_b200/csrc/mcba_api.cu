@@ -65,6 +65,7 @@ struct Handle {
   std::string err;
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream_b = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // F^T F assembly overlaps the e-block assembly
   // problem (host copies of the small things)
   int stage = 0, n_cam = 0, n_pose = 0, n_board = 0, n_pts = 0, nb = 0;
   int64_t n_obs = 0, npad = 0;
@@ -132,6 +133,7 @@ static cudaEvent_t get_event(Handle* H) {
 static void flush_timers(Handle* H) {
   if (H->pending.empty()) return;
   cudaStreamSynchronize(H->stream);
+  if (H->stream_b) cudaStreamSynchronize(H->stream_b);
   for (auto& p : H->pending) {
     float ms = 0; cudaEventElapsedTime(&ms, p.a, p.b);
     H->kf_ms[p.fam] += ms; H->kf_launches[p.fam] += 1;
@@ -139,10 +141,10 @@ static void flush_timers(Handle* H) {
   }
   H->pending.clear();
 }
-struct Timed {   // RAII: brackets the launches of one kernel family with CUDA events on the library stream
-  Handle* H; int fam; cudaEvent_t a;
-  Timed(Handle* h, int f) : H(h), fam(f) { a = get_event(H); cudaEventRecord(a, H->stream); }
-  ~Timed() { cudaEvent_t b = get_event(H); cudaEventRecord(b, H->stream); H->pending.push_back({fam, a, b}); if (H->pending.size() > 4096) flush_timers(H); }
+struct Timed {   // RAII: brackets the launches of one kernel family with CUDA events on the stream they are issued to
+  Handle* H; int fam; cudaEvent_t a; cudaStream_t st;
+  Timed(Handle* h, int f, cudaStream_t s = nullptr) : H(h), fam(f), st(s ? s : h->stream) { a = get_event(H); cudaEventRecord(a, st); }
+  ~Timed() { cudaEvent_t b = get_event(H); cudaEventRecord(b, st); H->pending.push_back({fam, a, b}); if (H->pending.size() > 4096) flush_timers(H); }
 };
 
 template <typename T> static int dalloc(Handle* H, T** p, size_t n) {
@@ -380,31 +382,43 @@ static int eval_observations(Handle* H, int which, double* target) {
 static int eval_assemble(Handle* H, bool first) {
   int rc;
   const StageDims sd = stage_dims(H->stage);
+  // Two independent readers of the per-board-observation records: the e-block assembly (main stream) and the
+  // F^T F / F^T r assembly (pair reduction -> [allreduce] -> dense F^T F; stream_b). They meet before k_fstep.
+  // (single GPU only for now: with ranks the pair-record allreduce would move to stream_b as well, which has not been
+  // measured on a multi-GPU box yet; there everything stays on the main stream, in this order)
+  const bool ov = H->stream_b != nullptr && H->n_ranks == 1;
+  cudaStream_t sb = ov ? H->stream_b : H->stream;
+  if (ov) { CU(cudaEventRecord(H->ev_fork, H->stream)); CU(cudaStreamWaitEvent(H->stream_b, H->ev_fork, 0)); }
+  {
+    Timed t(H, KF_PAIR, sb);
+    if (H->n_chunks > 0) {
+      ++H->n_launches;
+      DISPATCH_STAGE(H->stage, (k_pair_reduce<ST><<<H->n_chunks, 256, 0, sb>>>(H->d_chunks, H->d_pair_bobs, H->d_brec, H->d_pair_partial)));
+      CHECK_LAUNCH();
+    }
+    const int n = H->n_pair * H->NE;
+    ++H->n_launches;
+    DISPATCH_STAGE(H->stage, (k_pair_final<ST><<<(n + 255) / 256, 256, 0, sb>>>(H->d_pair_chunk_ptr, H->n_pair, H->d_pair_partial, H->d_pair_rec)));
+    CHECK_LAUNCH();
+  }
+  if (H->n_ranks > 1) {   // the only NCCL call of this phase; the next one (scalar gather) comes after the join
+    Timed t(H, KF_NCCL, sb);
+    const int nrc = g_nccl.AllReduce(H->d_pair_rec, H->d_pair_rec, (size_t)H->n_pair * H->NE, NCCL_DOUBLE, NCCL_SUM, H->comm, sb);
+    if (nrc != 0) { H->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?"); return MCBA_ERR_NCCL; }
+  }
+  {
+    Timed t(H, KF_PAIR, sb);
+    const int n = H->n_f * H->n_f + H->n_f;
+    ++H->n_launches;
+    DISPATCH_STAGE(H->stage, (k_ff_assemble<ST><<<(n + 255) / 256, 256, 0, sb>>>(H->d_pair_rec, H->n_cam, H->n_board, H->Wc, H->Wb, H->n_f, H->d_FF, H->d_gf)));
+    CHECK_LAUNCH();
+  }
+  if (ov) CU(cudaEventRecord(H->ev_join, H->stream_b));
   if (H->n_pose > 0) {
     Timed t(H, KF_EASSEMBLE);
     ++H->n_launches;
     DISPATCH_STAGE(H->stage, (k_eblock_assemble<ST><<<H->n_pose, 192, 6 * H->ldz * 8, H->stream>>>(
         H->d_bobs, H->d_pose_bobs_ptr, H->d_brec, H->n_cam, H->Wc, H->Wb, H->n_f, H->ldz, H->d_Hoo, H->d_Wt)));
-    CHECK_LAUNCH();
-  }
-  {
-    Timed t(H, KF_PAIR);
-    if (H->n_chunks > 0) {
-      ++H->n_launches;
-      DISPATCH_STAGE(H->stage, (k_pair_reduce<ST><<<H->n_chunks, 256, 0, H->stream>>>(H->d_chunks, H->d_pair_bobs, H->d_brec, H->d_pair_partial)));
-      CHECK_LAUNCH();
-    }
-    const int n = H->n_pair * H->NE;
-    ++H->n_launches;
-    DISPATCH_STAGE(H->stage, (k_pair_final<ST><<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_pair_chunk_ptr, H->n_pair, H->d_pair_partial, H->d_pair_rec)));
-    CHECK_LAUNCH();
-  }
-  if ((rc = allreduce_sum(H, H->d_pair_rec, (size_t)H->n_pair * H->NE))) return rc;
-  {
-    Timed t(H, KF_PAIR);
-    const int n = H->n_f * H->n_f + H->n_f;
-    ++H->n_launches;
-    DISPATCH_STAGE(H->stage, (k_ff_assemble<ST><<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_pair_rec, H->n_cam, H->n_board, H->Wc, H->Wb, H->n_f, H->d_FF, H->d_gf)));
     CHECK_LAUNCH();
   }
   {
@@ -414,6 +428,7 @@ static int eval_assemble(Handle* H, bool first) {
       k_eblock_grad<<<(H->n_pose + 127) / 128, 128, 0, H->stream>>>(H->d_pose[H->cur], H->d_Wt, H->n_pose, H->n_f, H->ldz, H->d_part_e);
       CHECK_LAUNCH();
     }
+    if (ov) CU(cudaStreamWaitEvent(H->stream, H->ev_join, 0));   // F^T F and F^T r are ready
     ++H->n_launches;
     k_fstep<<<1, 1024, 0, H->stream>>>(fstate(H, H->cur), fstate(H, H->cur), nullptr, H->d_FF, H->d_gf, H->d_scale_f, H->n_f, H->n_cam, H->Wc, H->Wb, sd.cam ? 1 : 0, H->d_scalars + SC_F0);
     CHECK_LAUNCH();
@@ -768,6 +783,7 @@ void mcba_destroy(void* h) {
   dfree(&H->d_cam_sc); dfree(&H->d_cam_cost);
   for (int w = 0; w < 2; ++w) { dfree(&H->d_cam_pose[w]); dfree(&H->d_pose[w]); dfree(&H->d_board[w]); dfree(&H->d_intr[w]); }
   dfree(&H->d_prep_cam); dfree(&H->d_prep_pose); dfree(&H->d_prep_board);
+  if (H->stream_b) { cudaStreamSynchronize(H->stream_b); cudaStreamDestroy(H->stream_b); cudaEventDestroy(H->ev_fork); cudaEventDestroy(H->ev_join); }
   if (H->stream) cudaStreamDestroy(H->stream);
   delete H;
 }
@@ -801,6 +817,10 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   CU(cudaSetDevice(device));
   H->device = device;
   CU(cudaStreamCreate(&H->stream));
+  {
+    static const bool overlap = []() { const char* e = getenv("MCBA_OVERLAP"); return !e || atoi(e) != 0; }();
+    if (overlap) { CU(cudaStreamCreateWithFlags(&H->stream_b, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&H->ev_fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&H->ev_join, cudaEventDisableTiming)); }
+  }
   H->n_cam = P->n_cam; H->n_pose = P->n_pose; H->n_board = std::max(0, P->n_board); H->n_pts = P->n_pts;
   H->n_obs = P->n_obs; H->nb = (int)P->n_bobs; H->npad = ((P->n_obs + 31) / 32) * 32; H->n_obs_global = P->n_obs;
   mark("device + stream");
