@@ -178,6 +178,8 @@ Pose6 composePose(const Pose6& outer, const Pose6& inner);   // x -> outer(inner
 Pose6 invertPose(const Pose6& p);
 // geometrytools.cpp:832-893: Markley quaternion averaging (largest eigenvector of the mean outer product, antipodal
 // quaternions flipped to w >= 0) or the per-component median of the rotation vectors
+std::array<double, 4> convertRotationMatrixToQuaternion(const double* R /*9, row-major*/);   // geometrytools.cpp:771-806, (x, y, z, w)
+std::array<double, 9> convertQuaternionToRotationMatrix(const std::array<double, 4>& q);     // geometrytools.cpp:808-830
 std::array<double, 3> getAverageRotation(std::vector<double>& r1, std::vector<double>& r2, std::vector<double>& r3,
                                          const bool use_quaternion_averaging = true);
 

@@ -226,6 +226,32 @@ void topEigenvector4(double A[4][4], double* q) {
 }
 }  // namespace
 
+std::array<double, 4> convertRotationMatrixToQuaternion(const double* R) {
+  std::array<double, 4> Q{};                                                    // x y z w
+  const double trace = R[0] + R[4] + R[8];
+  if (trace > 0.0) {
+    double s = std::sqrt(trace + 1.0);
+    Q[3] = s * 0.5; s = 0.5 / s;
+    Q[0] = (R[7] - R[5]) * s; Q[1] = (R[2] - R[6]) * s; Q[2] = (R[3] - R[1]) * s;
+  } else {
+    const int i = R[0] < R[4] ? (R[4] < R[8] ? 2 : 1) : (R[0] < R[8] ? 2 : 0);
+    const int j = (i + 1) % 3, k = (i + 2) % 3;
+    double s = std::sqrt(R[i * 3 + i] - R[j * 3 + j] - R[k * 3 + k] + 1.0);
+    Q[i] = s * 0.5; s = 0.5 / s;
+    Q[3] = (R[k * 3 + j] - R[j * 3 + k]) * s;
+    Q[j] = (R[j * 3 + i] + R[i * 3 + j]) * s;
+    Q[k] = (R[k * 3 + i] + R[i * 3 + k]) * s;
+  }
+  return Q;
+}
+
+std::array<double, 9> convertQuaternionToRotationMatrix(const std::array<double, 4>& q) {
+  const double q0 = q[3], q1 = q[0], q2 = q[1], q3 = q[2];                     // q0 = w
+  return {2 * (q0 * q0 + q1 * q1) - 1, 2 * (q1 * q2 - q0 * q3), 2 * (q1 * q3 + q0 * q2),
+          2 * (q1 * q2 + q0 * q3), 2 * (q0 * q0 + q2 * q2) - 1, 2 * (q2 * q3 - q0 * q1),
+          2 * (q1 * q3 - q0 * q2), 2 * (q2 * q3 + q0 * q1), 2 * (q0 * q0 + q3 * q3) - 1};
+}
+
 std::array<double, 3> getAverageRotation(std::vector<double>& r1, std::vector<double>& r2, std::vector<double>& r3,
                                          const bool use_quaternion_averaging) {
   std::array<double, 3> out{0, 0, 0};
@@ -235,33 +261,14 @@ std::array<double, 3> getAverageRotation(std::vector<double>& r1, std::vector<do
   for (size_t n = 0; n < r1.size(); ++n) {
     const double rv[3] = {r1[n], r2[n], r3[n]};
     double R[9]; rotVecToMat(rv, R);
-    // convertRotationMatrixToQuaternion (:771-806), (x, y, z, w)
-    double Q[4];
-    const double trace = R[0] + R[4] + R[8];
-    if (trace > 0.0) {
-      double s = std::sqrt(trace + 1.0);
-      Q[3] = s * 0.5; s = 0.5 / s;
-      Q[0] = (R[7] - R[5]) * s; Q[1] = (R[2] - R[6]) * s; Q[2] = (R[3] - R[1]) * s;
-    } else {
-      const int i = R[0] < R[4] ? (R[4] < R[8] ? 2 : 1) : (R[0] < R[8] ? 2 : 0);
-      const int j = (i + 1) % 3, k = (i + 2) % 3;
-      double s = std::sqrt(R[i * 3 + i] - R[j * 3 + j] - R[k * 3 + k] + 1.0);
-      Q[i] = s * 0.5; s = 0.5 / s;
-      Q[3] = (R[k * 3 + j] - R[j * 3 + k]) * s;
-      Q[j] = (R[j * 3 + i] + R[i * 3 + j]) * s;
-      Q[k] = (R[k * 3 + i] + R[i * 3 + k]) * s;
-    }
+    std::array<double, 4> Q = convertRotationMatrixToQuaternion(R);
     if (Q[3] < 0) for (double& x : Q) x = -x;                                   // antipodal configurations (:861-864)
     for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) A[a][b] += Q[a] * Q[b];
   }
   for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) A[a][b] /= (double)r1.size();
   double q[4]; topEigenvector4(A, q);
-  // convertQuaternionToRotationMatrix (:808-830): q0 = w, q1..q3 = x, y, z; the sign of q cancels
-  const double q0 = q[3], q1 = q[0], q2 = q[1], q3 = q[2];
-  const double R[9] = {2 * (q0 * q0 + q1 * q1) - 1, 2 * (q1 * q2 - q0 * q3), 2 * (q1 * q3 + q0 * q2),
-                       2 * (q1 * q2 + q0 * q3), 2 * (q0 * q0 + q2 * q2) - 1, 2 * (q2 * q3 - q0 * q1),
-                       2 * (q1 * q3 - q0 * q2), 2 * (q2 * q3 + q0 * q1), 2 * (q0 * q0 + q3 * q3) - 1};
-  matToRotVec(R, out.data());
+  const std::array<double, 9> R = convertQuaternionToRotationMatrix({q[0], q[1], q[2], q[3]});   // the sign of q cancels
+  matToRotVec(R.data(), out.data());
   return out;
 }
 

@@ -108,6 +108,42 @@ static int config(char** argv) {
   return 0;
 }
 
+// lines "m r0..r8" -> quaternion (x y z w); "q x y z w" -> rotation matrix; "b rx ry rz" (degrees as the reference's test
+// passes them to cv::Rodrigues, i.e. used as radians) -> matrix before and after the quaternion round trip
+static int quat(char** argv) {
+  std::ifstream in(argv[2]); std::ofstream out(argv[3]);
+  out.precision(17);
+  std::string kind;
+  while (in >> kind) {
+    if (kind == "m") { double R[9]; for (double& x : R) in >> x; for (double x : convertRotationMatrixToQuaternion(R)) out << x << " "; }
+    else if (kind == "q") { std::array<double, 4> q; for (double& x : q) in >> x; for (double x : convertQuaternionToRotationMatrix(q)) out << x << " "; }
+    else if (kind == "b") {
+      double rv[3]; for (double& x : rv) in >> x;
+      double R[9]; rotVecToMat(rv, R);
+      const auto R2 = convertQuaternionToRotationMatrix(convertRotationMatrixToQuaternion(R));
+      for (double x : R) out << x << " ";
+      for (double x : R2) out << x << " ";
+    }
+    out << "\n";
+  }
+  return 0;
+}
+
+// pose helpers: "r rx ry rz" -> R (9); "v r0..r8" -> rotation vector; "c a(6) b(6)" -> composePose(a, b); "i p(6)" -> invertPose
+static int pose(char** argv) {
+  std::ifstream in(argv[2]); std::ofstream out(argv[3]);
+  out.precision(17);
+  std::string kind;
+  while (in >> kind) {
+    if (kind == "r") { double rv[3], R[9]; for (double& x : rv) in >> x; rotVecToMat(rv, R); for (double x : R) out << x << " "; }
+    else if (kind == "v") { double R[9], rv[3]; for (double& x : R) in >> x; matToRotVec(R, rv); for (double x : rv) out << x << " "; }
+    else if (kind == "c") { Pose6 a, b; for (double& x : a) in >> x; for (double& x : b) in >> x; for (double x : composePose(a, b)) out << x << " "; }
+    else if (kind == "i") { Pose6 a; for (double& x : a) in >> x; for (double x : invertPose(a)) out << x << " "; }
+    out << "\n";
+  }
+  return 0;
+}
+
 // canonical JSON of a parsed file: scalars as strings, maps in file order
 static void dumpNode(const ocvyaml::Node& n, std::ofstream& out) {
   if (n.kind == ocvyaml::Node::SEQ) {
@@ -144,5 +180,7 @@ int main(int argc, char** argv) {
   if (mode == "grouppose") return grouppose(argv);
   if (mode == "config") return config(argv);
   if (mode == "yamldump") return yamldump(argv);
+  if (mode == "quat") return quat(argv);
+  if (mode == "pose") return pose(argv);
   return 2;
 }

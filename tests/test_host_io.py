@@ -418,3 +418,69 @@ def test_keypoint_file_with_an_empty_camera(io_main, tmp_path):
     r = subprocess.run([io_main, "keypoints", boards, kin, "None", kout, dump], capture_output=True, text=True)
     # the reference asserts frame_idxs.size() != 0 for every camera (McCalib.cpp:201); the loader reports it instead of aborting
     assert r.returncode == 1 and "camera_1" in r.stderr
+
+
+def test_reference_geometrytools_known_answers(io_main, tmp_path):
+    """The four cases of the reference's own tests/test_geometrytools.cpp (:9-101), same inputs, same expected values,
+    same 1 % BOOST_CHECK_CLOSE tolerance; the round-trip sweep additionally against cv2.Rodrigues."""
+    fin, fout = tmp_path / "in.txt", tmp_path / "out.txt"
+    lines = ["m 1 0 0 0 1 0 0 0 1",
+             "m -0.9999 -0.1998 -0.3996 0.1998 0.6000 -0.8000 0.3996 -0.8000 -0.5999",
+             "q 0.2809946 0.8377387 -0.4188693 -0.2092473"]
+    sweep = [(ax, ay, az) for ax in range(-20, 21, 4) for ay in range(-45, 91, 5) for az in range(-270, -179, 6)]
+    lines += [f"b {ax} {ay} {az}" for ax, ay, az in sweep]
+    fin.write_text("\n".join(lines) + "\n")
+    subprocess.check_call([io_main, "quat", str(fin), str(fout)])
+    rows = [np.array(l.split(), float) for l in open(fout)]
+
+    def close(a, b, pct=1.0):            # BOOST_CHECK_CLOSE: relative difference in percent w.r.t. both values
+        a, b = np.asarray(a, float), np.asarray(b, float)
+        return np.all((a == b) | (np.abs(a - b) <= pct / 100.0 * np.minimum(np.abs(a), np.abs(b))))
+
+    assert close(rows[0], [0, 0, 0, 1])                                          # CheckRotationMatrixToQuaternionConversion1
+    assert close(rows[1][1:], [0.8944, -0.4472, -0.2234]) and abs(rows[1][0]) < 1e-3   # ...Conversion2 (x = 0 in the reference)
+    assert close(rows[2], [-0.7545152, 0.2955056, -0.5859892, 0.6460947, 0.4911810, -0.5842113,
+                           0.1151891, -0.8194008, -0.5615281])                  # CheckQuaternionToRotationMatrixConversion
+    for (ax, ay, az), r in zip(sweep, rows[3:]):                                 # CheckRotationMatrixToQuaternionAndBackConversion
+        before, after = r[:9], r[9:]
+        assert np.abs(after - before).max() < 1e-12
+        Rcv, _ = cv2.Rodrigues(np.array([ax, ay, az], float))
+        assert np.abs(before - Rcv.ravel()).max() < 1e-12
+
+
+def test_pose_helpers_against_opencv(io_main, tmp_path):
+    """rotVecToMat / matToRotVec / composePose / invertPose (the facade's stand-ins for cv::Rodrigues, RVecT2Proj,
+    Proj2RT, invertRvecT) against cv2.Rodrigues and 4x4 matrix algebra, including the reference's own ProjToVecAllZeros
+    case (tests/simple_unit_tests_example.cpp:10-18: the identity gives an all-zero vector) and rotations near pi."""
+    rng = np.random.default_rng(0)
+    lines, checks = ["v 1 0 0 0 1 0 0 0 1"], [("zero",)]
+    for k in range(300):
+        ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+        ang = [rng.uniform(0, np.pi), np.pi - abs(rng.normal()) * 1e-6, abs(rng.normal()) * 1e-9][k % 3]
+        rv = ax * ang
+        R, _ = cv2.Rodrigues(rv)
+        lines.append("r " + " ".join(repr(float(x)) for x in rv)); checks.append(("r", R))
+        lines.append("v " + " ".join(repr(float(x)) for x in R.ravel())); checks.append(("v", R))
+        a = np.concatenate([rv, rng.normal(size=3)])
+        b = np.concatenate([Rot.random(random_state=int(rng.integers(1 << 30))).as_rotvec(), rng.normal(size=3)])
+        lines.append("c " + " ".join(repr(float(x)) for x in np.concatenate([a, b]))); checks.append(("c", a, b))
+        lines.append("i " + " ".join(repr(float(x)) for x in a)); checks.append(("i", a))
+    fin, fout = tmp_path / "in.txt", tmp_path / "out.txt"
+    fin.write_text("\n".join(lines) + "\n")
+    subprocess.check_call([io_main, "pose", str(fin), str(fout)])
+    rows = [np.array(l.split(), float) for l in open(fout)]
+
+    def T(p):
+        M = np.eye(4); M[:3, :3] = cv2.Rodrigues(np.asarray(p[:3], float))[0]; M[:3, 3] = p[3:]
+        return M
+    for row, chk in zip(rows, checks):
+        if chk[0] == "zero":
+            assert np.array_equal(row, np.zeros(3))
+        elif chk[0] == "r":
+            assert np.abs(row.reshape(3, 3) - chk[1]).max() < 1e-12
+        elif chk[0] == "v":
+            assert np.abs(cv2.Rodrigues(row)[0] - chk[1]).max() < 1e-9
+        elif chk[0] == "c":
+            assert np.abs(T(row) - T(chk[1]) @ T(chk[2])).max() < 1e-9
+        else:
+            assert np.abs(T(row) @ T(chk[1]) - np.eye(4)).max() < 1e-9
