@@ -291,8 +291,8 @@ __global__ void __launch_bounds__(192) k_eblock_assemble(const int4* __restrict_
   __syncthreads();
   const int b0 = pose_bobs_ptr[o], b1 = pose_bobs_ptr[o + 1];
   if (tid < 6 * C::WF) {
-    const int k = tid / C::WF, j = tid % C::WF;           // e-row k, local f column j
-    const int off = C::cidx(j, C::E0 + k);
+    const int j = tid / 6, k = tid % 6;                   // local f column j, e-row k: consecutive threads read consecutive
+    const int off = C::cidx(j, C::E0 + k);                // doubles of the record's f x e part (CI_FE + 6 j + k = CI_FE + tid)
     for (int b = b0; b < b1; ++b) {
       const int4 rec = bobs[b];
       const int gcol = (j < C::B0) ? rec.y * Wc + j : n_cam * Wc + rec.w * Wb + (j - C::B0);
