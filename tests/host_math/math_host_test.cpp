@@ -174,3 +174,32 @@ extern "C" int pnptest_ransac(int n, const float* u, const float* v, const float
   *best_h = st.best_h; *n_hyp = st.countit;
   return cnt;
 }
+
+// ---- the product's trust-region bookkeeping (csrc/mcba_lm.cuh), driven from a list of per-iteration inputs ----
+#include "../../mc-calib_b200/csrc/mcba_lm.cuh"
+// steps: n_steps rows of {solver_ok, mcc, step_norm, cand_norm, cand_cost, accepted_cost, accepted_grad_max}
+// (the last two are what the re-evaluation at an accepted point returns). Writes one mcba_trace_row per recorded
+// iteration; returns their number; *termination = mcba_termination or -1 when the inputs ran out first.
+extern "C" int lmtest_replay(const mcba_options* opt, double cost0, double grad0, double xnorm0, int n_steps,
+                             const double* steps, mcba_trace_row* rows, int rows_cap, int* termination,
+                             int* n_successful, int* n_unsuccessful, double* final_cost) {
+  LmState s; lm_init(s, *opt);
+  lm_iteration_zero(s, cost0, grad0, xnorm0);
+  int n_rows = 0, k = 0;
+  *termination = -1;
+  for (;;) {
+    mcba_trace_row rec;
+    const int cont = lm_finalize(s, *opt, &rec);
+    if (n_rows < rows_cap) rows[n_rows] = rec;
+    ++n_rows;
+    if (!cont) { *termination = s.termination; break; }
+    if (k >= n_steps) break;
+    const double* in = steps + 7 * k++;
+    LmStep st; st.solver_ok = in[0] != 0.0; st.mcc = in[1]; st.step_norm = in[2]; st.cand_norm = in[3]; st.cand_cost = in[4];
+    const int d = lm_decide(s, *opt, st);
+    if (d == LM_TERMINATED) { *termination = s.termination; break; }
+    if (d == LM_ACCEPT) lm_accepted_eval(s, *opt, in[5], in[6]);
+  }
+  *n_successful = s.num_successful; *n_unsuccessful = s.num_unsuccessful; *final_cost = s.x_cost;
+  return n_rows;
+}
