@@ -1,0 +1,139 @@
+"""Host logic of the McCalib-shaped facade on a CPU-only box: the drivers of mc-calib_b200/host are linked against a
+CPU stand-in of the C ABI (tests/stub_abi: the CPU oracle behind mcba_solve / mcba_solve_batched /
+mcba_reprojection_errors, the sequential host restatement of the PnP kernels behind mcba_pnp_ransac) and run end to end.
+What is checked is the facade itself — walking order, packing into the flat ABI arrays, scattering results back, the
+pose-initialisation flows, the file formats — against the same checker called directly on problems packed in Python.
+The product library is not involved (it has no CPU path); tests/test_gpu_facade.py runs the same flows on the GPU."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import mcba
+import pnp_util
+from mcba import pnp, synth
+from test_gpu_facade import write_scene
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STUB = os.path.join(REPO, "tests", "stub_abi")
+
+
+@pytest.fixture(scope="module")
+def bins(oracle):
+    subprocess.check_call(["make", "-s", "-C", STUB])
+    return os.path.join(STUB, "facade_main_cpu"), os.path.join(STUB, "calibrate_main_cpu")
+
+
+@pytest.fixture(scope="module")
+def scene():
+    s = synth.make_scene("c2", n_frames=24)
+    o = synth.generate_observations(s)
+    return s, o
+
+
+def run(binary, tmp_path, s, o, flow, extra=()):
+    scene_f, out = str(tmp_path / "scene.txt"), str(tmp_path / f"out_{flow}.txt")
+    write_scene(scene_f, s, o)
+    r = subprocess.run([binary, scene_f, flow, out, *extra], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    rows = [np.array(l.split(), float) for l in open(out)]
+    nc, nbd, nf, nbo = s.n_cam, s.n_board, o.frame_hi - o.frame_lo, len(o.bobs_cam)
+    cams = np.array(rows[1:1 + nc])
+    rest = rows[1 + nc + nbd + nf:]
+    res = dict(avg=float(rows[0][0]), intr=cams[:, :9], cam_pose=cams[:, 9:], board=np.array(rows[1 + nc:1 + nc + nbd]),
+               obj=np.array(rows[1 + nc + nbd:1 + nc + nbd + nf]), bobs_pose=np.array(rest[:nbo]), oo_pose=np.array(rest[nbo:]), out=out)
+    if os.path.exists(out + ".init.txt"):
+        ir = [np.array(l.split(), float) for l in open(out + ".init.txt")]
+        res.update(valid=np.array([r_[0] for r_ in ir[:nbo]], int), kept=np.array([r_[1] for r_ in ir[:nbo]], int))
+    return res
+
+
+def test_final_flow_packs_and_scatters_like_the_direct_call(bins, tmp_path, scene, oracle):
+    """refineAllCameraGroupAndObjects then ...AndIntrinsic == stage 4 then stage 5 on the problem packed in Python."""
+    s, o = scene
+    got = run(bins[0], tmp_path, s, o, "final")
+    prob, init, gt = synth.make_problem(s, o, 4)
+    p = init.copy()
+    p.intrinsics[:] = s.intr_init
+    assert oracle.solve(prob, p)[0] == 0
+    assert oracle.solve(prob.with_stage(5), p)[0] == 0
+    assert np.abs(got["intr"] - p.intrinsics).max() <= 1e-9 * np.abs(p.intrinsics).max()
+    assert np.abs(got["cam_pose"] - p.cam_pose).max() <= 1e-9
+    assert np.abs(got["board"] - p.board_pose).max() <= 1e-9
+    assert np.abs(got["obj"] - p.pose).max() <= 1e-9
+    import cv2       # the savers' files read back with OpenCV
+    fs = cv2.FileStorage(got["out"] + ".cameras.yml", cv2.FILE_STORAGE_READ)
+    K = fs.getNode("camera_1").getNode("camera_matrix").mat()
+    assert np.allclose([K[0, 0], K[1, 1], K[0, 2], K[1, 2]], p.intrinsics[1, :4], rtol=1e-8)
+    fs.release()
+
+
+def test_intrinsics_flow_batches_the_cameras(bins, tmp_path, scene, oracle):
+    """refineIntrinsicAndPoseAllCam hands all cameras to mcba_solve_batched: per camera identical to a single solve."""
+    s, o = scene
+    got = run(bins[0], tmp_path, s, o, "intrinsics")
+    prob, init, gt = synth.make_problem(s, o, 1)
+    for c in range(s.n_cam):
+        sel = np.nonzero(prob.bobs_cam == c)[0]
+        counts = np.diff(prob.bobs_ptr)[sel]
+        obs = np.concatenate([np.arange(prob.bobs_ptr[b], prob.bobs_ptr[b + 1]) for b in sel])
+        sub = mcba.Problem(1, prob.u[obs], prob.v[obs], prob.pt_idx[obs], np.concatenate([[0], np.cumsum(counts)]),
+                           np.zeros(len(sel)), np.arange(len(sel)), np.zeros(len(sel)), prob.pts_xyz, prob.cam_model[c:c + 1],
+                           len(sel), 0)
+        p = mcba.Params(np.zeros((1, 6)), init.pose[sel], np.zeros((0, 6)), init.intrinsics[c:c + 1])
+        assert oracle.solve(sub, p)[0] == 0
+        assert np.abs(got["intr"][c] - p.intrinsics[0]).max() <= 1e-9 * np.abs(p.intrinsics[0]).max()
+        assert np.abs(got["bobs_pose"][sel] - p.pose).max() <= 1e-9
+
+
+def test_objects_flow(bins, tmp_path, scene, oracle):
+    s, o = scene
+    got = run(bins[0], tmp_path, s, o, "objects")
+    prob, init, gt = synth.make_problem(s, o, 2)
+    p = init.copy()
+    p.intrinsics[:] = s.intr_init
+    assert oracle.solve(prob, p)[0] == 0
+    assert np.abs(got["board"] - p.board_pose).max() <= 1e-9
+    assert np.abs(got["oo_pose"] - p.pose).max() <= 1e-9
+
+
+def test_pose_initialisation_flow(bins, tmp_path, scene):
+    """estimatePoseAllBoards on the facade's packing == the same checker on the Python packing (draws keyed by the
+    observation index, so any difference in order or content shows); validity and kept corners follow BoardObs.cpp:143-161."""
+    s, o = scene
+    got = run(bins[0], tmp_path, s, o, "init", extra=("3.0", "5"))
+    prob, init, gt = synth.make_problem(s, o, 1)
+    P = pnp.PnpProblem(prob, s.intr_init)
+    opt = pnp.mcba_pnp_options(3.0, 1000, 0.99, 1, 20, 5)
+    want = pnp_util.host_ransac_all(pnp_util.host_lib(), P, opt)
+    assert np.array_equal(got["bobs_pose"], want["pose"])
+    assert np.array_equal(got["kept"], want["n_inliers"]) and np.array_equal(got["valid"], (want["n_inliers"] >= 4).astype(int))
+    assert (want["n_inliers"] < np.diff(prob.bobs_ptr)).any()
+    # every frame got a group pose close to the ground truth (reference camera's observation, or the average)
+    err = [pnp_util.pose_diff(got["obj"][f], o.obj_gt[f]) for f in range(len(got["obj"])) if got["obj"][f].any()]
+    assert len(err) > 0.9 * len(got["obj"]) and np.median(err) < 0.05
+
+
+def test_workflow_head_from_files(bins, tmp_path, oracle):
+    """Calibration(config) -> boardExtraction -> initIntrinsic from a config file, a keypoint file and a camera-parameter
+    file written by OpenCV; refined focal lengths land near the ground truth."""
+    import cv2
+    import test_host_io as hio
+    s = synth.make_scene("c1", n_frames=40)
+    o = synth.generate_observations(s)
+    cfg, kp, cp, out = (str(tmp_path / n) for n in ("config.yml", "kp.yml", "cams.yml", "intr.yml"))
+    hio.write_keypoints_with_opencv(kp, s, o)
+    hio.write_camera_params_with_opencv(cp, s, s.intr_init)
+    nx, ny = s.cfg["grid"]
+    hio.write_config(cfg, n_cam=s.n_cam, n_board=s.n_board, nx=nx + 1, ny=ny + 1, square=s.cfg["square"], cam_params=cp,
+                     keypoints=kp, thr=10, iters=100)
+    r = subprocess.run([bins[1], cfg, out], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    fs = cv2.FileStorage(out, cv2.FILE_STORAGE_READ)
+    for c in range(s.n_cam):
+        K = fs.getNode(f"camera_{c}").getNode("camera_matrix").mat()
+        assert abs(K[0, 0] - s.intr_gt[c, 0]) <= 0.01 * s.intr_gt[c, 0] and abs(K[1, 1] - s.intr_gt[c, 1]) <= 0.01 * s.intr_gt[c, 1]
+    fs.release()
+    line = [l for l in r.stdout.splitlines() if l.startswith("valid board observations")][0].split()
+    assert int(line[3]) == len(o.bobs_cam) and 0.2 < float(line[-2]) < 0.6
