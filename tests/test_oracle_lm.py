@@ -35,6 +35,24 @@ def test_trace_fixture(cfg, stage, oracle):
     assert np.abs(p.intrinsics - np.array(doc["intrinsics"])).max() <= 1e-7 * np.abs(p.intrinsics).max()
 
 
+@pytest.mark.parametrize("stage", [1, 2, 3])
+def test_trace_fixture_stages_1_to_3(stage, oracle):
+    doc = json.load(open(os.path.join(GOLD, f"trace_c2_stage{stage}.json")))
+    prob, init, gt, s, o = synth.config_problem("c2", stage, n_frames=doc["n_frames"])
+    p = init.copy()
+    rc, summ, tr = oracle.solve(prob, p)
+    assert rc == 0 and prob.n_obs == doc["n_obs"]
+    assert (summ.termination, summ.num_successful_steps, summ.num_unsuccessful_steps) == \
+           (doc["termination"], doc["num_successful_steps"], doc["num_unsuccessful_steps"])
+    assert len(tr) == len(doc["rows"])
+    for r, d in zip(tr, doc["rows"]):
+        assert (r.iteration, r.step_is_valid, r.step_is_successful) == (d["iteration"], d["valid"], d["successful"])
+        assert abs(r.cost - d["cost"]) <= 1e-9 * d["cost"]
+        assert abs(r.trust_region_radius - d["radius"]) <= 1e-6 * d["radius"]
+    assert abs(summ.rms_px - doc["rms_px"]) <= 1e-8
+    assert np.abs(p.pose[:10] - np.array(doc["pose_first10"])).max() <= 1e-7
+
+
 def test_trace_bookkeeping(oracle):
     """Ceres rules: iteration 0 is recorded as a successful step with radius = initial radius; after a successful
     step with ratio rho the radius grows by 1/max(1/3, 1-(2 rho-1)^3); cost is monotone over successful steps."""
