@@ -135,3 +135,34 @@ def test_minimum_matches_scipy_huber(oracle):
         return ((w[:, None] * res).reshape(-1) @ J)[free]
     g0, g1 = np.abs(grad(x0)).max(), np.abs(grad(x_star)).max()
     assert g1 <= 1e-7 * g0
+
+
+@pytest.mark.parametrize("stage", [1, 2, 3, 4, 5])
+def test_first_lm_step_matches_dense_numpy(stage, oracle):
+    """LevenbergMarquardtStrategy::ComputeStep restated densely in numpy (Jacobi scaling 1/(1+|J_j|), diagonal clamp,
+    D = sqrt(diag/radius), one dense solve of (Js^T Js + D^2) y = Js^T r, delta = -s o y): the oracle's Schur elimination
+    + Cholesky must produce the same first step (step norm, model cost change through rho, cost at the new point)."""
+    prob, init, gt, s, o = synth.config_problem("c1", stage, n_frames=30)
+    p = init.copy()
+    if stage in (1, 5):
+        p.intrinsics[:] = s.intr_init
+    opt = mcba.default_options(max_num_iterations=1)
+    p0 = p.copy()
+    rc, summ, tr = oracle.solve(prob, p, opt)
+    assert rc == 0 and len(tr) == 2 and tr[1].step_is_valid == 1
+    _, cost0, res, jac, _ = oracle.eval(prob, p0, opt)
+    J = dense_jacobian(prob, jac)
+    r = res.reshape(-1)
+    sc = 1.0 / (1.0 + np.sqrt((J * J).sum(0)))
+    Js = J * sc
+    diag = np.clip((Js * Js).sum(0), opt.min_lm_diagonal, opt.max_lm_diagonal)
+    H = Js.T @ Js + np.diag(diag / opt.initial_trust_region_radius)
+    y = np.linalg.solve(H, Js.T @ r)
+    delta = -sc * y
+    assert tr[1].step_norm == 0.0   # Ceres only fills step_norm in ParameterToleranceReached, i.e. after a first success
+    m = Js @ (-y)
+    mcc = -m @ (r + 0.5 * m)
+    x1 = params_to_x(prob, p0) + delta
+    assert tr[1].step_is_successful == 1
+    assert np.abs(params_to_x(prob, p) - x1).max() <= 1e-7 * max(1.0, np.abs(x1).max())
+    assert abs((cost0 - tr[1].cost) / mcc - tr[1].relative_decrease) <= 1e-6 * abs(tr[1].relative_decrease)
