@@ -350,3 +350,15 @@ def batched_intrinsics_problem(n_cameras=4096, n_frames=300, seed=1005, cam_lo=0
     init = Params(np.zeros((ncam, 6)), np.concatenate(poses_init), np.zeros((0, 6)), np.array(intr_init))
     gt = Params(np.zeros((ncam, 6)), np.concatenate(poses_gt), np.zeros((0, 6)), np.array(intr_gt))
     return prob, init, gt
+
+
+def shard_problem(prob, params, rank, world):
+    """Frame shard `rank` of `world` of a stage 3-5 problem: a contiguous range of e-blocks with all
+    their board observations; camera / board / intrinsics blocks are replicated. -> (Problem, Params, (lo, hi))."""
+    lo, hi = (prob.n_pose * rank) // world, (prob.n_pose * (rank + 1)) // world
+    b0, b1 = np.searchsorted(prob.bobs_pose, [lo, hi])
+    o0, o1 = prob.bobs_ptr[b0], prob.bobs_ptr[b1]
+    sub = Problem(prob.stage, prob.u[o0:o1], prob.v[o0:o1], prob.pt_idx[o0:o1], prob.bobs_ptr[b0:b1 + 1] - o0,
+                  prob.bobs_cam[b0:b1], prob.bobs_pose[b0:b1] - lo, prob.bobs_board[b0:b1], prob.pts_xyz, prob.cam_model,
+                  hi - lo, prob.n_board, prob.cam_is_ref, prob.board_is_ref)
+    return sub, Params(params.cam_pose, params.pose[lo:hi], params.board_pose, params.intrinsics), (lo, hi)

@@ -90,6 +90,43 @@ def main():
         assert abs(s5.rms_px - o5.rms_px) <= 1e-6
         assert np.abs(p.intrinsics - po.intrinsics).max() <= 1e-6 * np.abs(po.intrinsics).max()
         print(f"MGPU_OK set_stage world {world} iterations {s4.num_iterations}+{s5.num_iterations}", flush=True)
+    # the non-accept branches of the trust-region loop on 2 ranks (tests/lm_cases.py): every rank must take the same
+    # decision from the gathered scalars - rejected steps, invalid steps (recovering / FAILURE), NO_CONVERGENCE, radius exit
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import lm_cases
+    for name in ("reject_c2_s5", "reject_c2_s4", "invalid_recover_c2_s5", "invalid_failure_c2_s5", "no_convergence_c2_s5",
+                 "min_radius_c2_s5", "parameter_tolerance_c2_s5"):
+        prob, p0, opt, _ = lm_cases.make_case(name)
+        sub, p, (lo, hi) = synth.shard_problem(prob, p0, rank, world)
+        h = mcba.Handle(sub, device=local)
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = ctypes.create_string_buffer(128)
+            assert h.lib.mcba_nccl_unique_id(buf) == 0
+            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        h.comm_init(rank, world, uid.cpu().numpy().tobytes())
+        summ, trace = h.solve(p, opt)
+        h.close()
+        n_max = (prob.n_pose + world - 1) // world
+        mine = torch.zeros(n_max * 6, dtype=torch.float64, device="cuda")
+        mine[:(hi - lo) * 6] = torch.from_numpy(p.pose.reshape(-1)).cuda()
+        poses = [torch.zeros(n_max * 6, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(poses, mine)
+        if rank == 0:
+            import oracle_py
+            po = p0.copy()
+            rc, so, to = oracle_py.solve(prob, po, opt)
+            assert rc == 0
+            full = p0.copy()
+            full.cam_pose[:], full.board_pose[:], full.intrinsics[:] = p.cam_pose, p.board_pose, p.intrinsics
+            for r in range(world):
+                a, b = (prob.n_pose * r) // world, (prob.n_pose * (r + 1)) // world
+                full.pose[a:b] = poses[r][:(b - a) * 6].cpu().numpy().reshape(-1, 6)
+            lm_cases.check_expectation(name, summ, trace)
+            lm_cases.assert_same_run(name, (full, summ, trace), (po, so, to))
+            print(f"MGPU_OK branch {name} world {world} sequence {lm_cases.sequence(trace)} termination {summ.termination}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

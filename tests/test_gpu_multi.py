@@ -19,4 +19,4 @@ def test_sharded_solve_matches_oracle(world):
            "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(HERE, "mgpu_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("MGPU_OK") == 3
+    assert out.stdout.count("MGPU_OK") == 3 + 7   # 3 default-option solves + 7 LM branch cases
