@@ -70,6 +70,6 @@ def test_batched_device_driver_follows_each_cameras_oracle(name, oracle):
         assert (s.termination, s.num_successful_steps, s.num_unsuccessful_steps, s.num_iterations) == \
                (so.termination, so.num_successful_steps, so.num_unsuccessful_steps, so.num_iterations), (name, c)
         assert (s.termination, s.num_iterations) == (g[c]["termination"], g[c]["num_iterations"])
-        assert abs(s.final_cost - so.final_cost) <= 1e-9 * so.final_cost
+        assert abs(s.final_cost - so.final_cost) <= (1e-9 if so.termination == 0 else 1e-6) * so.final_cost, (name, c)
         assert np.abs(pg.intrinsics[c] - p.intrinsics[0]).max() <= 1e-6 * np.abs(p.intrinsics[0]).max(), (name, c)
         assert np.abs(pg.pose[b0:b1] - p.pose).max() <= 1e-6 * max(1.0, np.abs(p.pose).max()), (name, c)
