@@ -120,11 +120,22 @@ void mcba_default_options(mcba_options *opt);
 int mcba_create(void **handle, const mcba_problem *prob, int device);
 int mcba_set_stage(void *handle, int stage);
 
+/* Device-resident observations shared between calls. The pose initialisation (mcba_pnp_ransac, mcba_pnp.h) and the
+ * bundle adjustment that follows it read the same corner arrays (the reference keeps them once, in BoardObs /
+ * Object3DObs: McCalib/include/BoardObs.hpp:27-33). After mcba_obs_register every mcba_create / mcba_pnp_ransac whose
+ * u, v, pt_idx pointers, n_obs and device match uses the resident copy instead of uploading again (12 B per corner).
+ * mcba_obs_release frees it; it fails with MCBA_ERR_INVALID while a handle still uses the copy. */
+int mcba_obs_register(const float *u, const float *v, const int32_t *pt_idx, int64_t n_obs, int device);
+int mcba_obs_release(const float *u, int device);
+
 /* Multi-GPU: this process owns one GPU and one shard (contiguous e-block range, all f-blocks replicated).
  * nccl_unique_id is the 128-byte ncclUniqueId produced by mcba_nccl_unique_id on rank 0 and broadcast
  * by the caller (torch.distributed / MPI / file). Must be called before mcba_solve on every rank. */
 int mcba_nccl_unique_id(void *id_out_128B);
 int mcba_comm_init(void *handle, int rank, int n_ranks, const void *nccl_unique_id_128B);
+/* Which data plane sums the reduced system across ranks: 0 = single rank, 1 = NCCL allreduce, 2 = fused into the
+ * Schur kernel's epilogue over NVLink peer memory (the default when CUDA IPC is available on every rank). */
+int mcba_schur_reduce_mode(void *handle);
 
 /* ceres::Solve replacement. trace may be NULL. For batched problems summary/trace describe problem 0
  * unless summaries (an array of n_problems) is given through mcba_solve_batched. */

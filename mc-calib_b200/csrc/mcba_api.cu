@@ -84,6 +84,7 @@ struct Handle {
   double *d_syrk_partial = nullptr, *d_pair_partial = nullptr, *d_pair_rec = nullptr, *d_part_e = nullptr;
   double *d_red_scratch = nullptr, *d_scalars = nullptr, *d_gather = nullptr;
   int* d_fail = nullptr;
+  bool obs_shared = false;   // d_u / d_v / d_pt belong to the observation cache (mcba_obs_register)
   double *d_jmat = nullptr, *d_resmat = nullptr;   // lazily allocated
   int syrk_nt = 0, syrk_tiles = 0, syrk_nsplit = 0; int64_t syrk_rows_per_split = 0;
   int chol_grid = 1, n_sm = 148;
@@ -102,7 +103,7 @@ struct Handle {
   // comm
   int rank = 0, n_ranks = 1; nccl_comm_t comm = nullptr;
   // peer-memory path of the Schur reduction (k_syrk_sum_p2p)
-  bool p2p = false; unsigned long long p2p_epoch = 0;
+  bool p2p = false; unsigned long long p2p_epoch = 0; int p2p_grid = 0;
   unsigned long long* d_p2p_flags = nullptr; unsigned int* d_p2p_counter = nullptr; int* d_p2p_err = nullptr;
   double* d_p2p_stage = nullptr; bool ZtZ_pooled = false;
   double* peer_stage[P2P_MAX_RANKS] = {nullptr}; double* peer_ZtZ[P2P_MAX_RANKS] = {nullptr}; unsigned long long* peer_flags[P2P_MAX_RANKS] = {nullptr};
@@ -114,11 +115,13 @@ struct Handle {
   double ev_cost = 0, ev_x_norm = 0, ev_grad_max = 0;   // outputs of the last eval_jacobian
   mcba_summary summ;
   std::vector<mcba_trace_row> trace;
+  std::vector<double> x0_cam, x0_pose, x0_board, x0_intr;   // start point of the solve in flight (returned on FAILURE)
   int64_t n_obs_global = 0;
   // timing
   struct Pending { int fam; cudaEvent_t a, b; };
   std::vector<Pending> pending; std::vector<cudaEvent_t> free_events;
   int64_t kf_launches[KF_COUNT] = {0}; double kf_ms[KF_COUNT] = {0};
+  double kf_ms_at_begin[KF_COUNT] = {0};   // snapshot taken by mcba_solve_begin: mcba_summary::t_* are per-solve deltas
   int64_t n_launches = 0;   // kernels launched by this handle
   cudaEvent_t tm_a = nullptr, tm_b = nullptr;
 };
@@ -147,13 +150,28 @@ struct Timed {   // RAII: brackets the launches of one kernel family with CUDA e
   ~Timed() { cudaEvent_t b = get_event(H); cudaEventRecord(b, st); H->pending.push_back({fam, a, b}); if (H->pending.size() > 4096) flush_timers(H); }
 };
 
+// Device memory comes from the device's default stream-ordered pool, with the release threshold lifted: what
+// mcba_destroy gives back stays in the pool, so a create / solve / destroy cycle (one per refine* stage and camera
+// group in the reference's workflow) does not pay cudaMalloc / cudaFree (each a device-wide synchronisation) again.
+static void keep_pool(int device) {
+  static std::mutex m; static bool done[64] = {false};
+  std::lock_guard<std::mutex> g(m);
+  if (device < 0 || device >= 64 || done[device]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  cudaGetLastError();
+  done[device] = true;
+}
 template <typename T> static int dalloc(Handle* H, T** p, size_t n) {
-  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (*p) { cudaFreeAsync(*p, H->stream); *p = nullptr; }
   if (n == 0) n = 1;
-  CU(cudaMalloc((void**)p, n * sizeof(T)));
+  CU(cudaMallocAsync((void**)p, n * sizeof(T), H->stream));
   return 0;
 }
-template <typename T> static void dfree(T** p) { if (*p) { cudaFree(*p); *p = nullptr; } }
+template <typename T> static void dfree(Handle* H, T** p) { if (*p) { cudaFreeAsync(*p, H->stream); *p = nullptr; } }
 
 struct StageDims { bool cam, intr, board; int K, NT, NE, WF, NCOMP; };
 static StageDims stage_dims(int stage) {
@@ -256,7 +274,7 @@ static int setup_stage(Handle* H, int stage) {
   if (dalloc(H, &H->d_pair_partial, (size_t)H->n_chunks * H->NE)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_pair_rec, (size_t)H->n_pair * H->NE)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_part_e, np * 4)) return MCBA_ERR_CUDA;
-  dfree(&H->d_jmat); dfree(&H->d_resmat);
+  dfree(H, &H->d_jmat); dfree(H, &H->d_resmat);
   H->have_scale = false;
   // opt in to > 48 KB dynamic shared memory
   DISPATCH_STAGE(stage, {
@@ -307,7 +325,7 @@ static int launch_prep(Handle* H, int which) {
   return MCBA_OK;
 }
 
-static int grid_for(int nb, int ctas_per_sm) { return std::max(1, std::min((nb + OBS_WARPS - 1) / OBS_WARPS, 148 * ctas_per_sm)); }
+static int grid_for(const Handle* H, int nb, int ctas_per_sm) { return std::max(1, std::min((nb + OBS_WARPS - 1) / OBS_WARPS, H->n_sm * ctas_per_sm)); }
 
 template <int MODE> static int launch_obs(Handle* H, int which, double huber_a) {
   if (H->nb == 0) return MCBA_OK;
@@ -317,7 +335,7 @@ template <int MODE> static int launch_obs(Handle* H, int which, double huber_a) 
   DISPATCH_STAGE(H->stage, {
     constexpr bool ACC = (MODE == MODE_FUSED || MODE == MODE_FROM_J);
     const int sm = OBS_WARPS * (CTX_SIZE + (ACC ? Cols<ST>::NC * TS : 0)) * 8;
-    const int grid = grid_for(H->nb, ACC ? std::min(4, std::max(1, (227 * 1024) / (sm + 1024))) : 8);
+    const int grid = grid_for(H, H->nb, ACC ? std::min(4, std::max(1, (227 * 1024) / (sm + 1024))) : 8);
     ++H->n_launches;
     k_observations<ST, MODE><<<grid, OBS_WARPS * 32, sm, H->stream>>>(a);
   });
@@ -425,7 +443,7 @@ static int eval_assemble(Handle* H, bool first) {
     Timed t(H, KF_REDUCE);
     if (H->n_pose > 0) {
       ++H->n_launches;
-      k_eblock_grad<<<(H->n_pose + 127) / 128, 128, 0, H->stream>>>(H->d_pose[H->cur], H->d_Wt, H->n_pose, H->n_f, H->ldz, H->d_part_e);
+      k_eblock_grad<<<(H->n_pose + 127) / 128, 128, 0, H->stream>>>(H->d_pose[H->cur], H->d_Wt, H->d_Hoo, H->n_pose, H->n_f, H->ldz, H->d_part_e);
       CHECK_LAUNCH();
     }
     if (ov) CU(cudaStreamWaitEvent(H->stream, H->ev_join, 0));   // F^T F and F^T r are ready
@@ -458,7 +476,8 @@ static int eval_assemble(Handle* H, bool first) {
   H->ev_cost = cost;
   H->ev_x_norm = std::sqrt(xe2 + hs[SC_F0 + 0]);
   H->ev_grad_max = gmax;
-  if (!std::isfinite(cost)) return MCBA_ERR_NUMERIC;
+  // Evaluator validity as in Ceres: cost, gradient and every Jacobian column must be finite
+  if (!std::isfinite(cost) || !std::isfinite(gmax)) return MCBA_ERR_NUMERIC;
   return MCBA_OK;
 }
 
@@ -473,7 +492,7 @@ static int cholesky_reduced(Handle* H) {
   if (n > 2 * CC_B * CC_LD) { H->err = "reduced system too large for the cooperative Cholesky (n_f > 8704)"; return MCBA_ERR_INVALID; }
   double* S = H->d_S; double* z = H->d_zf; int* fail = H->d_fail;
   static const bool want_prof = getenv("MCBA_CHOL_PROF") != nullptr;
-  if (want_prof && !H->d_chol_prof) { CU(cudaMalloc((void**)&H->d_chol_prof, 8 * sizeof(long long))); CU(cudaMemset(H->d_chol_prof, 0, 8 * sizeof(long long))); }
+  if (want_prof && !H->d_chol_prof) { CU(cudaMalloc((void**)&H->d_chol_prof, 16 * sizeof(long long))); CU(cudaMemset(H->d_chol_prof, 0, 16 * sizeof(long long))); }
   long long* prof = H->d_chol_prof;
   // back-substitution: 1 = CTA 0 alone, pipelined, no grid sync (its update traffic, n^2/2 doubles through one SM, only
   // pays off for small systems: 0.532 vs 0.539 ms at n = 1020); 0 = updates spread over the CTAs, one grid sync per block
@@ -517,7 +536,10 @@ static int compute_step(Handle* H, LmStep* out) {
       pa.partial = H->d_syrk_partial; pa.nsplit = H->syrk_nsplit;
       pa.rank = H->rank; pa.n_ranks = H->n_ranks; pa.epoch = ++H->p2p_epoch; pa.n_tiles = H->syrk_tiles; pa.nt = H->syrk_nt; pa.ldz = H->ldz;
       pa.counter = H->d_p2p_counter; pa.err = H->d_p2p_err;
-      k_syrk_sum_p2p<<<2 * H->n_sm, 256, 0, H->stream>>>(pa);   // co-resident by construction: 2 CTAs of 256 threads per SM
+      // the CTAs of this kernel wait for one another (and for the peers' kernels): a cooperative launch makes the
+      // driver guarantee co-residency of the whole grid (it fails with an error instead of deadlocking)
+      void* pargs[] = {&pa};
+      CU(cudaLaunchCooperativeKernel((void*)k_syrk_sum_p2p, dim3(H->p2p_grid), dim3(256), pargs, 0, H->stream));
     } else {
       k_syrk_sum<<<dim3(H->syrk_tiles, 8), 256, 0, H->stream>>>(H->d_syrk_partial, H->syrk_tiles, H->syrk_nt, H->syrk_nsplit, H->ldz, H->d_ZtZ);
     }
@@ -656,7 +678,7 @@ static int setup_p2p(Handle* H) {
   H->d_p2p_flags = (unsigned long long*)g_export_pool.acquire(H->device, (size_t)2 * P2P_MAX_RANKS * sizeof(unsigned long long));
   if (!H->ZtZ_pooled) {
     double* zz = (double*)g_export_pool.acquire(H->device, zz_bytes);
-    if (zz) { dfree(&H->d_ZtZ); H->d_ZtZ = zz; H->ZtZ_pooled = true; }
+    if (zz) { dfree(H, &H->d_ZtZ); H->d_ZtZ = zz; H->ZtZ_pooled = true; }
   }
   if (!H->d_p2p_stage || !H->d_p2p_flags || !H->ZtZ_pooled) { H->err = "cudaMalloc(exported buffers)"; return MCBA_ERR_CUDA; }
   CU(cudaMemset(H->d_ZtZ, 0, zz_bytes));   // the lower triangle is never written
@@ -676,11 +698,11 @@ static int setup_p2p(Handle* H) {
   char *d_send = nullptr, *d_recv = nullptr;
   if (dalloc(H, &d_send, sizeof(IpcRecord)) || dalloc(H, &d_recv, sizeof(IpcRecord) * (size_t)N)) return MCBA_ERR_CUDA;
   CU(cudaMemcpy(d_send, &mine, sizeof(mine), cudaMemcpyHostToDevice));
-  if (g_nccl.AllGather(d_send, d_recv, sizeof(IpcRecord), /*ncclChar*/ 0, H->comm, H->stream) != 0) { cudaFree(d_send); cudaFree(d_recv); H->err = "ncclAllGather(ipc handles)"; return MCBA_ERR_NCCL; }
+  if (g_nccl.AllGather(d_send, d_recv, sizeof(IpcRecord), /*ncclChar*/ 0, H->comm, H->stream) != 0) { cudaFreeAsync(d_send, H->stream); cudaFreeAsync(d_recv, H->stream); H->err = "ncclAllGather(ipc handles)"; return MCBA_ERR_NCCL; }
   std::vector<IpcRecord> all(N);
   CU(cudaMemcpyAsync(all.data(), d_recv, sizeof(IpcRecord) * (size_t)N, cudaMemcpyDeviceToHost, H->stream));
   CU(cudaStreamSynchronize(H->stream));
-  cudaFree(d_send); cudaFree(d_recv);
+  cudaFreeAsync(d_send, H->stream); cudaFreeAsync(d_recv, H->stream);
   bool ok = true;
   for (int r = 0; r < N; ++r) ok = ok && all[r].ok;
   for (int r = 0; r < P2P_MAX_RANKS; ++r) { H->peer_stage[r] = nullptr; H->peer_ZtZ[r] = nullptr; H->peer_flags[r] = nullptr; }
@@ -706,11 +728,74 @@ static int setup_p2p(Handle* H) {
   CU(cudaMemcpyAsync(&verdict, H->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, H->stream));
   CU(cudaStreamSynchronize(H->stream));
   if (verdict < N - 0.5) { close_p2p(H); return MCBA_OK; }
+  { int per_sm = 0; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_syrk_sum_p2p, 256, 0));
+    H->p2p_grid = std::min(2, std::max(1, per_sm)) * H->n_sm; }
   H->p2p = true;
   return MCBA_OK;
 }
 
+// ---- device-resident observations shared between calls (mcba_obs_register) ----------------------------------------
+// The pose initialisation (mcba_pnp_ransac) and the bundle adjustment that follows (mcba_create) read the same u / v /
+// pt_idx arrays. A caller that registers them pays the H2D copy (12 B per corner: 74 MB for a 6.18 M-corner shard) once;
+// every later call whose u pointer, length and device match a registered entry uses the resident copy.
+struct ObsEntry { const float* u; const float* v; const int32_t* pt; int64_t n; int device; float* d_u; float* d_v; int32_t* d_pt; int users; };
+static std::mutex g_obs_mutex;
+static std::vector<ObsEntry> g_obs;
+namespace mcba {
+bool obs_cache_acquire(const float* u, const float* v, const int32_t* pt, int64_t n, int device, float** d_u, float** d_v, int32_t** d_pt) {
+  std::lock_guard<std::mutex> g(g_obs_mutex);
+  for (auto& e : g_obs)
+    if (e.u == u && e.v == v && e.pt == pt && e.n == n && e.device == device) { ++e.users; *d_u = e.d_u; *d_v = e.d_v; *d_pt = e.d_pt; return true; }
+  return false;
+}
+void obs_cache_release(const float* d_u) {
+  std::lock_guard<std::mutex> g(g_obs_mutex);
+  for (auto& e : g_obs) if (e.d_u == d_u && e.users > 0) --e.users;
+}
+}  // namespace mcba
+
+// pt_idx range check on the device (replaces a single-threaded 6 M-element host loop in mcba_create)
+__global__ void k_validate_pt(const int32_t* __restrict__ pt, int64_t n, int n_pts, int* __restrict__ bad) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool b = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) { const int p = pt[i]; b = b || p < 0 || p >= n_pts; }
+  if (b) *bad = 1;
+}
+
 extern "C" {
+
+int mcba_obs_register(const float* u, const float* v, const int32_t* pt_idx, int64_t n_obs, int device) {
+  if (!u || !v || !pt_idx || n_obs <= 0) return MCBA_ERR_INVALID;
+  { float *a, *b; int32_t* c;
+    if (mcba::obs_cache_acquire(u, v, pt_idx, n_obs, device, &a, &b, &c)) { mcba::obs_cache_release(a); return MCBA_OK; } }
+  if (cudaSetDevice(device) != cudaSuccess) return MCBA_ERR_CUDA;
+  const int64_t npad = ((n_obs + 31) / 32) * 32;
+  ObsEntry e{u, v, pt_idx, n_obs, device, nullptr, nullptr, nullptr, 0};
+  if (cudaMalloc((void**)&e.d_u, npad * 4) != cudaSuccess || cudaMalloc((void**)&e.d_v, npad * 4) != cudaSuccess ||
+      cudaMalloc((void**)&e.d_pt, npad * 4) != cudaSuccess ||
+      cudaMemcpy(e.d_u, u, n_obs * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(e.d_v, v, n_obs * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(e.d_pt, pt_idx, n_obs * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError(); cudaFree(e.d_u); cudaFree(e.d_v); cudaFree(e.d_pt); return MCBA_ERR_CUDA;
+  }
+  std::lock_guard<std::mutex> g(g_obs_mutex);
+  g_obs.push_back(e);
+  return MCBA_OK;
+}
+int mcba_obs_release(const float* u, int device) {
+  std::lock_guard<std::mutex> g(g_obs_mutex);
+  for (size_t i = 0; i < g_obs.size(); ++i)
+    if (g_obs[i].u == u && g_obs[i].device == device) {
+      if (g_obs[i].users > 0) return MCBA_ERR_INVALID;   // a live handle still reads it
+      cudaSetDevice(device); cudaFree(g_obs[i].d_u); cudaFree(g_obs[i].d_v); cudaFree(g_obs[i].d_pt);
+      g_obs.erase(g_obs.begin() + i);
+      return MCBA_OK;
+    }
+  return MCBA_ERR_INVALID;
+}
+
+/* 0: one rank; 1: NCCL allreduce of the reduced system; 2: fused split-K sum + reduction over NVLink peer memory */
+int mcba_schur_reduce_mode(void* h) { Handle* H = (Handle*)h; if (!H) return MCBA_ERR_INVALID; return H->n_ranks <= 1 ? 0 : (H->p2p ? 2 : 1); }
 
 void mcba_default_options(mcba_options* o) {
   o->max_num_iterations = 50;   // Ceres default; the reference overrides it with YAML number_iterations
@@ -733,7 +818,7 @@ int mcba_kernel_stats(void* h, int k, int64_t* launches, double* total_ms) {
 int mcba_reset_kernel_stats(void* h) {
   Handle* H = (Handle*)h; if (!H) return MCBA_ERR_INVALID;
   flush_timers(H);
-  for (int k = 0; k < KF_COUNT; ++k) { H->kf_launches[k] = 0; H->kf_ms[k] = 0; }
+  for (int k = 0; k < KF_COUNT; ++k) { H->kf_launches[k] = 0; H->kf_ms[k] = 0; H->kf_ms_at_begin[k] = 0; }
   return MCBA_OK;
 }
 int mcba_jacobian_width(int stage) { return stage_dims(stage).K; }
@@ -766,25 +851,26 @@ void mcba_destroy(void* h) {
   close_p2p(H);
   release_exported(H);
   if (H->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(H->comm);
-  dfree(&H->d_p2p_counter); dfree(&H->d_p2p_err);
+  dfree(H, &H->d_p2p_counter); dfree(H, &H->d_p2p_err);
   for (auto& p : H->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : H->free_events) cudaEventDestroy(e);
   if (H->tm_a) { cudaEventDestroy(H->tm_a); cudaEventDestroy(H->tm_b); }
-  dfree(&H->d_u); dfree(&H->d_v); dfree(&H->d_pt); dfree(&H->d_pts); dfree(&H->d_bobs); dfree(&H->d_pose_bobs_ptr);
-  dfree(&H->d_cam_model); dfree(&H->d_cam_is_ref); dfree(&H->d_board_is_ref);
-  dfree(&H->d_pair_bobs); dfree(&H->d_chunks); dfree(&H->d_pair_chunk_ptr);
-  dfree(&H->d_brec); dfree(&H->d_brec_alt); dfree(&H->d_cost_bobs); dfree(&H->d_Hoo); dfree(&H->d_Wt); dfree(&H->d_Z); dfree(&H->d_L);
-  dfree(&H->d_scale_e); dfree(&H->d_diag_e); dfree(&H->d_scale_f); dfree(&H->d_diag_f);
-  dfree(&H->d_FF); dfree(&H->d_gf); dfree(&H->d_S); dfree(&H->d_rhs); dfree(&H->d_zf); dfree(&H->d_ZtZ); dfree(&H->d_hz);
-  dfree(&H->d_syrk_partial); dfree(&H->d_pair_partial); dfree(&H->d_pair_rec); dfree(&H->d_part_e);
-  dfree(&H->d_red_scratch); dfree(&H->d_scalars); dfree(&H->d_gather); dfree(&H->d_fail);
-  dfree(&H->d_jmat); dfree(&H->d_resmat);
-  dfree(&H->d_cam_ptr); dfree(&H->d_lm); dfree(&H->d_gate_jac); dfree(&H->d_active); dfree(&H->d_cam_fail); dfree(&H->d_n_active);
-  dfree(&H->d_cam_sc); dfree(&H->d_cam_cost);
-  for (int w = 0; w < 2; ++w) { dfree(&H->d_cam_pose[w]); dfree(&H->d_pose[w]); dfree(&H->d_board[w]); dfree(&H->d_intr[w]); }
-  dfree(&H->d_prep_cam); dfree(&H->d_prep_pose); dfree(&H->d_prep_board);
+  if (H->obs_shared) { obs_cache_release(H->d_u); H->d_u = nullptr; H->d_v = nullptr; H->d_pt = nullptr; }
+  dfree(H, &H->d_u); dfree(H, &H->d_v); dfree(H, &H->d_pt); dfree(H, &H->d_pts); dfree(H, &H->d_bobs); dfree(H, &H->d_pose_bobs_ptr);
+  dfree(H, &H->d_cam_model); dfree(H, &H->d_cam_is_ref); dfree(H, &H->d_board_is_ref);
+  dfree(H, &H->d_pair_bobs); dfree(H, &H->d_chunks); dfree(H, &H->d_pair_chunk_ptr);
+  dfree(H, &H->d_brec); dfree(H, &H->d_brec_alt); dfree(H, &H->d_cost_bobs); dfree(H, &H->d_Hoo); dfree(H, &H->d_Wt); dfree(H, &H->d_Z); dfree(H, &H->d_L);
+  dfree(H, &H->d_scale_e); dfree(H, &H->d_diag_e); dfree(H, &H->d_scale_f); dfree(H, &H->d_diag_f);
+  dfree(H, &H->d_FF); dfree(H, &H->d_gf); dfree(H, &H->d_S); dfree(H, &H->d_rhs); dfree(H, &H->d_zf); dfree(H, &H->d_ZtZ); dfree(H, &H->d_hz);
+  dfree(H, &H->d_syrk_partial); dfree(H, &H->d_pair_partial); dfree(H, &H->d_pair_rec); dfree(H, &H->d_part_e);
+  dfree(H, &H->d_red_scratch); dfree(H, &H->d_scalars); dfree(H, &H->d_gather); dfree(H, &H->d_fail);
+  dfree(H, &H->d_jmat); dfree(H, &H->d_resmat);
+  dfree(H, &H->d_cam_ptr); dfree(H, &H->d_lm); dfree(H, &H->d_gate_jac); dfree(H, &H->d_active); dfree(H, &H->d_cam_fail); dfree(H, &H->d_n_active);
+  dfree(H, &H->d_cam_sc); dfree(H, &H->d_cam_cost);
+  for (int w = 0; w < 2; ++w) { dfree(H, &H->d_cam_pose[w]); dfree(H, &H->d_pose[w]); dfree(H, &H->d_board[w]); dfree(H, &H->d_intr[w]); }
+  dfree(H, &H->d_prep_cam); dfree(H, &H->d_prep_pose); dfree(H, &H->d_prep_board);
   if (H->stream_b) { cudaStreamSynchronize(H->stream_b); cudaStreamDestroy(H->stream_b); cudaEventDestroy(H->ev_fork); cudaEventDestroy(H->ev_join); }
-  if (H->stream) cudaStreamDestroy(H->stream);
+  if (H->stream) { cudaStreamSynchronize(H->stream); cudaStreamDestroy(H->stream); }
   delete H;
 }
 
@@ -816,6 +902,7 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   if (cc_major != 10) { H->err = "libmcba is built for sm_100a (B200) only"; return MCBA_ERR_CUDA; }
   CU(cudaSetDevice(device));
   H->device = device;
+  keep_pool(device);
   CU(cudaStreamCreate(&H->stream));
   {
     static const bool overlap = []() { const char* e = getenv("MCBA_OVERLAP"); return !e || atoi(e) != 0; }();
@@ -824,7 +911,7 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   H->n_cam = P->n_cam; H->n_pose = P->n_pose; H->n_board = std::max(0, P->n_board); H->n_pts = P->n_pts;
   H->n_obs = P->n_obs; H->nb = (int)P->n_bobs; H->npad = ((P->n_obs + 31) / 32) * 32; H->n_obs_global = P->n_obs;
   mark("device + stream");
-  // validate + pack
+  // validate + pack the board-observation table (host, small)
   std::vector<int4> bobs(H->nb + 1);
   std::vector<int> ppt(H->n_pose + 1, 0);
   H->h_bobs_cam.resize(H->nb); H->h_bobs_pose.resize(H->nb); H->h_bobs_board.resize(H->nb);
@@ -841,23 +928,35 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   if (H->nb > 0 && (P->bobs_ptr[0] != 0 || P->bobs_ptr[H->nb] != P->n_obs)) { H->err = "bobs_ptr must cover [0, n_obs)"; return MCBA_ERR_INVALID; }
   bobs[H->nb] = make_int4((int)P->n_obs, 0, 0, 0);
   for (int o = 0; o < H->n_pose; ++o) ppt[o + 1] = std::max(ppt[o + 1], ppt[o]);
-  for (int64_t i = 0; i < P->n_obs; ++i) if (P->pt_idx[i] < 0 || P->pt_idx[i] >= P->n_pts) { H->err = "pt_idx out of range"; return MCBA_ERR_INVALID; }
+  // the three big uploads run behind the host work that follows (point table, pair lists of setup_stage)
+  if (dalloc(H, &H->d_fail, (size_t)2)) return MCBA_ERR_CUDA;
+  CU(cudaMemsetAsync(H->d_fail, 0, 2 * sizeof(int), H->stream));
+  if (P->n_obs > 0 && obs_cache_acquire(P->u, P->v, P->pt_idx, P->n_obs, device, &H->d_u, &H->d_v, &H->d_pt)) {
+    H->obs_shared = true;
+  } else {
+    if (dalloc(H, &H->d_u, (size_t)H->npad) || dalloc(H, &H->d_v, (size_t)H->npad) || dalloc(H, &H->d_pt, (size_t)H->npad)) return MCBA_ERR_CUDA;
+    CU(cudaMemcpyAsync(H->d_u, P->u, P->n_obs * sizeof(float), cudaMemcpyHostToDevice, H->stream));
+    CU(cudaMemcpyAsync(H->d_v, P->v, P->n_obs * sizeof(float), cudaMemcpyHostToDevice, H->stream));
+    CU(cudaMemcpyAsync(H->d_pt, P->pt_idx, P->n_obs * sizeof(int32_t), cudaMemcpyHostToDevice, H->stream));
+  }
+  if (P->n_obs > 0) {
+    ++H->n_launches;
+    k_validate_pt<<<std::min<int64_t>(4 * n_sm, (P->n_obs + 255) / 256), 256, 0, H->stream>>>(H->d_pt, P->n_obs, P->n_pts, H->d_fail + 1);
+    CHECK_LAUNCH();
+  }
   std::vector<double> pts((size_t)std::max(1, P->n_pts) * 3);
   for (int i = 0; i < P->n_pts * 3; ++i) pts[i] = (double)P->pts_xyz[i];
   mark("validate + pack (host)");
-  if (dalloc(H, &H->d_u, (size_t)H->npad) || dalloc(H, &H->d_v, (size_t)H->npad) || dalloc(H, &H->d_pt, (size_t)H->npad)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_pts, pts.size()) || dalloc(H, &H->d_bobs, bobs.size()) || dalloc(H, &H->d_pose_bobs_ptr, ppt.size())) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_cam_model, (size_t)H->n_cam) || dalloc(H, &H->d_cam_is_ref, (size_t)H->n_cam) || dalloc(H, &H->d_board_is_ref, (size_t)std::max(1, H->n_board))) return MCBA_ERR_CUDA;
-  CU(cudaMemcpy(H->d_u, P->u, P->n_obs * sizeof(float), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(H->d_v, P->v, P->n_obs * sizeof(float), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(H->d_pt, P->pt_idx, P->n_obs * sizeof(int32_t), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(H->d_pts, pts.data(), pts.size() * sizeof(double), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(H->d_bobs, bobs.data(), bobs.size() * sizeof(int4), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(H->d_pose_bobs_ptr, ppt.data(), ppt.size() * sizeof(int), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(H->d_cam_model, P->cam_model, H->n_cam * sizeof(int32_t), cudaMemcpyHostToDevice));
+  // small tables from vector storage of this call: pageable copies are staged before cudaMemcpyAsync returns
+  CU(cudaMemcpyAsync(H->d_pts, pts.data(), pts.size() * sizeof(double), cudaMemcpyHostToDevice, H->stream));
+  CU(cudaMemcpyAsync(H->d_bobs, bobs.data(), bobs.size() * sizeof(int4), cudaMemcpyHostToDevice, H->stream));
+  CU(cudaMemcpyAsync(H->d_pose_bobs_ptr, ppt.data(), ppt.size() * sizeof(int), cudaMemcpyHostToDevice, H->stream));
+  CU(cudaMemcpyAsync(H->d_cam_model, P->cam_model, H->n_cam * sizeof(int32_t), cudaMemcpyHostToDevice, H->stream));
   std::vector<uint8_t> zc((size_t)std::max(H->n_cam, std::max(1, H->n_board)), 0);
-  CU(cudaMemcpy(H->d_cam_is_ref, P->cam_is_ref ? P->cam_is_ref : zc.data(), H->n_cam, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(H->d_board_is_ref, (P->board_is_ref && H->n_board > 0) ? P->board_is_ref : zc.data(), std::max(1, H->n_board), cudaMemcpyHostToDevice));
+  CU(cudaMemcpyAsync(H->d_cam_is_ref, P->cam_is_ref ? P->cam_is_ref : zc.data(), H->n_cam, cudaMemcpyHostToDevice, H->stream));
+  CU(cudaMemcpyAsync(H->d_board_is_ref, (P->board_is_ref && H->n_board > 0) ? P->board_is_ref : zc.data(), std::max(1, H->n_board), cudaMemcpyHostToDevice, H->stream));
   mark("observation alloc + H2D");
   for (int w = 0; w < 2; ++w) {
     if (dalloc(H, &H->d_cam_pose[w], (size_t)H->n_cam * 6) || dalloc(H, &H->d_pose[w], (size_t)H->n_pose * 6) ||
@@ -866,7 +965,7 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   }
   if (dalloc(H, &H->d_prep_cam, (size_t)H->n_cam * PREP) || dalloc(H, &H->d_prep_pose, (size_t)H->n_pose * PREP) ||
       dalloc(H, &H->d_prep_board, (size_t)std::max(1, H->n_board) * PREP)) return MCBA_ERR_CUDA;
-  if (dalloc(H, &H->d_red_scratch, (size_t)512 * 8) || dalloc(H, &H->d_scalars, (size_t)SC_N) || dalloc(H, &H->d_gather, (size_t)SC_N * 64) || dalloc(H, &H->d_fail, (size_t)1)) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_red_scratch, (size_t)512 * 8) || dalloc(H, &H->d_scalars, (size_t)SC_N) || dalloc(H, &H->d_gather, (size_t)SC_N * 64)) return MCBA_ERR_CUDA;
   CU(cudaMemset(H->d_scalars, 0, SC_N * sizeof(double)));
   H->n_sm = n_sm;
   CU(cudaFuncSetAttribute(k_chol_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, CC_SMEM));
@@ -878,7 +977,10 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   const int rc = setup_stage(H, P->stage);
   if (rc) return rc;
   mark("setup_stage (pair lists + allocs)");
-  CU(cudaDeviceSynchronize());
+  int bad_pt = 0;   // the stream sync below also ends the lifetime requirement of the host vectors above
+  CU(cudaMemcpyAsync(&bad_pt, H->d_fail + 1, sizeof(int), cudaMemcpyDeviceToHost, H->stream));
+  CU(cudaStreamSynchronize(H->stream));
+  if (bad_pt) { H->err = "pt_idx out of range"; return MCBA_ERR_INVALID; }
   mark("device sync");
   if (prof) std::fprintf(stderr, "[mcba_create] total %8.3f ms\n", now_ms() - t_begin);
   return MCBA_OK;
@@ -954,6 +1056,12 @@ int mcba_solve_begin(void* h, const mcba_params* p, const mcba_options* opt) {
   H->opt = o;
   int rc;
   if ((rc = upload_params(H, p))) return rc;
+  H->x0_pose.assign(p->pose, p->pose + (size_t)H->n_pose * 6);
+  H->x0_intr.assign(p->intrinsics, p->intrinsics + (size_t)H->n_cam * 9);
+  if (p->cam_pose) H->x0_cam.assign(p->cam_pose, p->cam_pose + (size_t)H->n_cam * 6); else H->x0_cam.clear();
+  if (p->board_pose && H->n_board > 0) H->x0_board.assign(p->board_pose, p->board_pose + (size_t)H->n_board * 6); else H->x0_board.clear();
+  flush_timers(H);
+  for (int k = 0; k < KF_COUNT; ++k) H->kf_ms_at_begin[k] = H->kf_ms[k];
   H->solving = true; H->trace.clear(); H->have_scale = false;
   std::memset(&H->summ, 0, sizeof(H->summ));
   lm_init(H->lm, o);
@@ -1003,6 +1111,13 @@ int mcba_solve_end(void* h, mcba_params* p, mcba_summary* summary) {
   H->summ.num_iterations = H->lm.num_recorded;
   H->summ.num_successful_steps = H->lm.num_successful; H->summ.num_unsuccessful_steps = H->lm.num_unsuccessful;
   H->summ.final_cost = H->lm.minimum_cost < DBL_MAX ? H->lm.minimum_cost : H->lm.x_cost;
+  if (H->lm.termination == MCBA_FAILURE) {
+    // ceres::Solve (solver.cc, Minimize): when the summary is not usable (FAILURE) the parameter blocks get the
+    // ORIGINAL values back, whatever the minimizer had reached. Same here: the start point is re-uploaded and returned.
+    mcba_params x0 = {H->x0_cam.empty() ? nullptr : H->x0_cam.data(), H->x0_pose.data(), H->x0_board.empty() ? nullptr : H->x0_board.data(), H->x0_intr.data()};
+    const StageDims sd = stage_dims(H->stage);
+    if ((!sd.cam || x0.cam_pose) && (!sd.board || x0.board_pose) && (rc = upload_params(H, &x0))) return rc;
+  }
   // unrobustified RMS at the returned parameters: cost pass with the loss disabled
   if ((rc = launch_prep(H, H->cur))) return rc;
   if ((rc = launch_obs<MODE_COST>(H, H->cur, 0.0))) return rc;
@@ -1012,10 +1127,12 @@ int mcba_solve_end(void* h, mcba_params* p, mcba_summary* summary) {
   double c = 0; for (int r = 0; r < H->n_ranks; ++r) c += hs[(size_t)r * SC_N + SC_COST];
   H->summ.rms_px = std::sqrt(2.0 * c / (double)std::max<int64_t>(1, H->n_obs_global));
   flush_timers(H);
-  H->summ.t_jacobian_ms = H->kf_ms[KF_FUSED] + H->kf_ms[KF_MATERIALIZE] + H->kf_ms[KF_FROM_J] + H->kf_ms[KF_PREP];
-  H->summ.t_schur_ms = H->kf_ms[KF_EASSEMBLE] + H->kf_ms[KF_PAIR] + H->kf_ms[KF_EFACTOR] + H->kf_ms[KF_SYRK] + H->kf_ms[KF_REDUCED] + H->kf_ms[KF_BACKSUBST];
-  H->summ.t_chol_ms = H->kf_ms[KF_CHOL]; H->summ.t_cost_ms = H->kf_ms[KF_COST]; H->summ.t_comm_ms = H->kf_ms[KF_NCCL];
-  double tot = 0; for (int k = 0; k < KF_COUNT; ++k) tot += H->kf_ms[k];
+  double dt[KF_COUNT];   // this solve only (a handle is reused across stages and mcba_eval calls)
+  for (int k = 0; k < KF_COUNT; ++k) dt[k] = H->kf_ms[k] - H->kf_ms_at_begin[k];
+  H->summ.t_jacobian_ms = dt[KF_FUSED] + dt[KF_MATERIALIZE] + dt[KF_FROM_J] + dt[KF_PREP];
+  H->summ.t_schur_ms = dt[KF_EASSEMBLE] + dt[KF_PAIR] + dt[KF_EFACTOR] + dt[KF_SYRK] + dt[KF_REDUCED] + dt[KF_BACKSUBST];
+  H->summ.t_chol_ms = dt[KF_CHOL]; H->summ.t_cost_ms = dt[KF_COST]; H->summ.t_comm_ms = dt[KF_NCCL];
+  double tot = 0; for (int k = 0; k < KF_COUNT; ++k) tot += dt[k];
   H->summ.t_total_ms = tot;
   if (p && (rc = download_params(H, p))) return rc;
   if (summary) *summary = H->summ;
@@ -1180,12 +1297,12 @@ int mcba_reprojection_errors(void* h, const mcba_params* p, double* err) {
   ObsArgs a = obs_args(H, 0, 0.0);
   if (H->nb > 0) {
     ++H->n_launches;
-    DISPATCH_STAGE(H->stage, (k_reproj_err<ST><<<grid_for(H->nb, 8), OBS_WARPS * 32, OBS_WARPS * CTX_SIZE * 8, H->stream>>>(a, d_err)));
+    DISPATCH_STAGE(H->stage, (k_reproj_err<ST><<<grid_for(H, H->nb, 8), OBS_WARPS * 32, OBS_WARPS * CTX_SIZE * 8, H->stream>>>(a, d_err)));
   }
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(err, d_err, H->n_obs * sizeof(double), cudaMemcpyDeviceToHost, H->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(H->stream);
-  cudaFree(d_err);
+  cudaFreeAsync(d_err, H->stream);
   if (e != cudaSuccess) { H->err = cudaGetErrorString(e); return MCBA_ERR_CUDA; }
   return MCBA_OK;
 }

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 #include <stdint.h>
+#include <math_constants.h>
 #include "mcba_math.cuh"
 
 namespace mcba {
@@ -407,18 +408,22 @@ __global__ void k_scale_diag(const double* __restrict__ Hoo, int n_pose, const d
 }
 
 // Gradient max-norm pieces |x - (x + (-g))| (computed through Plus as Ceres does) and |x|^2, per e-block.
-// part[o] = {sum x^2, max |x - (x - g)|}
-__global__ void k_eblock_grad(const double* __restrict__ pose, const double* __restrict__ Wt, int n_pose, int n_f,
-                              int ldz, double* __restrict__ part) {
+// part[o] = {sum x^2, max |x - (x - g)|}. A non-finite gradient entry or Jacobian column (its squared norm is the
+// diagonal of E^T E) turns the max into +inf: Ceres' evaluator rejects non-finite residuals, gradients AND Jacobian
+// values (IsArrayValid), not only a non-finite cost.
+__global__ void k_eblock_grad(const double* __restrict__ pose, const double* __restrict__ Wt, const double* __restrict__ Hoo,
+                              int n_pose, int n_f, int ldz, double* __restrict__ part) {
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= n_pose) return;
   double s = 0.0, m = 0.0;
+  bool finite = true;
   for (int k = 0; k < 6; ++k) {
     const double x = pose[(size_t)o * 6 + k], gk = Wt[((size_t)o * 6 + k) * ldz + n_f];
     const double pg = x + (-gk);
     s += x * x; m = fmax(m, fabs(x - pg));
+    finite = finite && isfinite(gk) && isfinite(Hoo[(size_t)o * 36 + k * 7]);
   }
-  part[(size_t)o * 2] = s; part[(size_t)o * 2 + 1] = m;
+  part[(size_t)o * 2] = s; part[(size_t)o * 2 + 1] = finite ? m : CUDART_INF;
 }
 
 // K2c: factor the e-block, Z[o] = L^-1 (s_e [W | g] s_f). One CTA per e-block; every thread factors its own
@@ -1100,9 +1105,10 @@ __global__ void __launch_bounds__(1024) k_fstep(FState cur, FState cand, const d
       const double xc = x + sj * (-z);
       *f_slot(cand, j, n_cam, Wc, Wb, has_cam) = xc;
       a0 += z * sj * gf[j]; a1 += z * hzv[j]; a2 += (x - xc) * (x - xc); a3 += xc * xc;
-    } else {
+    } else {   // hzv is F^T F here: a non-finite gradient entry or Jacobian column -> +inf (see k_eblock_grad)
       const double pg = x + (-gf[j]);
       a0 += x * x; a1 = fmax(a1, fabs(x - pg));
+      if (!isfinite(gf[j]) || !isfinite(hzv[(size_t)j * n_f + j])) a1 = CUDART_INF;
     }
   }
   red[0][t] = a0; red[1][t] = a1; red[2][t] = a2; red[3][t] = a3;

@@ -247,6 +247,10 @@ using namespace mcba;
 
 #define PCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { g_pnp_err = std::string(#x) + ": " + cudaGetErrorString(e_); goto fail; } } while (0)
 
+namespace mcba {   // mcba_api.cu: device-resident observations shared between calls (mcba_obs_register)
+bool obs_cache_acquire(const float* u, const float* v, const int32_t* pt, int64_t n, int device, float** d_u, float** d_v, int32_t** d_pt);
+void obs_cache_release(const float* d_u);
+}
 extern "C" {
 
 void mcba_pnp_default_options(mcba_pnp_options* o) {
@@ -279,6 +283,7 @@ int mcba_pnp_ransac(const mcba_pnp_problem* P, const mcba_pnp_options* opt, int 
   PnpArgs a; std::memset(&a, 0, sizeof(a));
   const size_t no = (size_t)P->n_obs, nb = (size_t)P->n_bobs, nc = (size_t)P->n_cam;
   char* d_all = nullptr; cudaStream_t stream = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  bool shared_obs = false; float *c_u = nullptr, *c_v = nullptr; int32_t* c_pt = nullptr;
   // one device allocation, carved up (256-byte aligned pieces)
   size_t off = 0;
   auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
@@ -291,15 +296,20 @@ int mcba_pnp_ransac(const mcba_pnp_problem* P, const mcba_pnp_options* opt, int 
   PCU(cudaMalloc((void**)&d_all, off));
   PCU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   PCU(cudaEventCreate(&e0)); PCU(cudaEventCreate(&e1));
-  PCU(cudaMemcpyAsync(d_all + o_u, P->u, no * 4, cudaMemcpyHostToDevice, stream));
-  PCU(cudaMemcpyAsync(d_all + o_v, P->v, no * 4, cudaMemcpyHostToDevice, stream));
-  PCU(cudaMemcpyAsync(d_all + o_pt, P->pt_idx, no * 4, cudaMemcpyHostToDevice, stream));
+  // corners already resident (mcba_obs_register, mcba.h): shared with the bundle adjustment that follows, no upload
+  shared_obs = mcba::obs_cache_acquire(P->u, P->v, P->pt_idx, P->n_obs, device, &c_u, &c_v, &c_pt);
+  if (!shared_obs) {
+    PCU(cudaMemcpyAsync(d_all + o_u, P->u, no * 4, cudaMemcpyHostToDevice, stream));
+    PCU(cudaMemcpyAsync(d_all + o_v, P->v, no * 4, cudaMemcpyHostToDevice, stream));
+    PCU(cudaMemcpyAsync(d_all + o_pt, P->pt_idx, no * 4, cudaMemcpyHostToDevice, stream));
+  }
   PCU(cudaMemcpyAsync(d_all + o_pts, P->pts_xyz, (size_t)P->n_pts * 12, cudaMemcpyHostToDevice, stream));
   PCU(cudaMemcpyAsync(d_all + o_bp, P->bobs_ptr, (nb + 1) * 8, cudaMemcpyHostToDevice, stream));
   PCU(cudaMemcpyAsync(d_all + o_bc, P->bobs_cam, nb * 4, cudaMemcpyHostToDevice, stream));
   PCU(cudaMemcpyAsync(d_all + o_cm, P->cam_model, nc * 4, cudaMemcpyHostToDevice, stream));
   PCU(cudaMemcpyAsync(d_all + o_in, P->intrinsics, nc * 72, cudaMemcpyHostToDevice, stream));
-  a.u = (const float*)(d_all + o_u); a.v = (const float*)(d_all + o_v); a.pt = (const int32_t*)(d_all + o_pt);
+  a.u = shared_obs ? c_u : (const float*)(d_all + o_u); a.v = shared_obs ? c_v : (const float*)(d_all + o_v);
+  a.pt = shared_obs ? c_pt : (const int32_t*)(d_all + o_pt);
   a.pts = (const float*)(d_all + o_pts); a.bobs_ptr = (const long long*)(d_all + o_bp); a.bobs_cam = (const int32_t*)(d_all + o_bc);
   a.cam_model = (const int32_t*)(d_all + o_cm); a.intr = (const double*)(d_all + o_in); a.wintr = (double*)(d_all + o_wi);
   a.ab = (double2*)(d_all + o_ab); a.w = (double2*)(d_all + o_w); a.ok = (uint8_t*)(d_all + o_ok); a.mask = (uint8_t*)(d_all + o_mask);
@@ -336,6 +346,7 @@ int mcba_pnp_ransac(const mcba_pnp_problem* P, const mcba_pnp_options* opt, int 
   PCU(cudaEventElapsedTime(&ms, e0, e1));
   res->kernel_ms = ms;
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(stream); cudaFree(d_all);
+  if (shared_obs) mcba::obs_cache_release(c_u);
   res->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return MCBA_OK;
 fail:
@@ -343,6 +354,7 @@ fail:
   if (e1) cudaEventDestroy(e1);
   if (stream) cudaStreamDestroy(stream);
   if (d_all) cudaFree(d_all);
+  if (shared_obs) mcba::obs_cache_release(c_u);
   cudaGetLastError();
   return MCBA_ERR_CUDA;
 }

@@ -10,7 +10,6 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.abspath(os.path.join(_HERE, "..", "..", ".."))
 LIB_PATH = os.path.join(REPO, "mc-calib_b200", "csrc", "libmcba.so")
-ORACLE_PATH = os.path.join(REPO, "oracle", "liboracle.so")
 
 c_f32p = C.POINTER(C.c_float)
 c_f64p = C.POINTER(C.c_double)
@@ -166,6 +165,9 @@ def load_lib():
     L.mcba_default_options.restype = None
     L.mcba_create.argtypes = [vpp, C.POINTER(mcba_problem), C.c_int]
     L.mcba_set_stage.argtypes = [vp, C.c_int]
+    L.mcba_obs_register.argtypes = [c_f32p, c_f32p, c_i32p, C.c_int64, C.c_int]
+    L.mcba_obs_release.argtypes = [c_f32p, C.c_int]
+    L.mcba_schur_reduce_mode.argtypes = [vp]
     L.mcba_nccl_unique_id.argtypes = [vp]
     L.mcba_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.mcba_solve.argtypes = [vp, C.POINTER(mcba_params), C.POINTER(mcba_options), C.POINTER(mcba_summary),
@@ -199,6 +201,20 @@ class McbaError(RuntimeError):
     pass
 
 
+def obs_register(problem, device=0):
+    """Upload u / v / pt_idx once; later Handle(problem) / pnp.ransac calls on the same arrays reuse the device copy."""
+    rc = load_lib().mcba_obs_register(_ptr(problem.u, c_f32p), _ptr(problem.v, c_f32p), _ptr(problem.pt_idx, c_i32p),
+                                      problem.n_obs, device)
+    if rc != 0:
+        raise McbaError(f"mcba_obs_register failed rc={rc}")
+
+
+def obs_release(problem, device=0):
+    rc = load_lib().mcba_obs_release(_ptr(problem.u, c_f32p), device)
+    if rc != 0:
+        raise McbaError(f"mcba_obs_release failed rc={rc} (unknown arrays, or a live handle still uses them)")
+
+
 class Handle:
     """RAII wrapper of a libmcba handle; mirrors the call sequence of a reference refine* stage:
     build the problem (mcba_create) then solve (mcba_solve)."""
@@ -226,6 +242,9 @@ class Handle:
     def comm_init(self, rank, n_ranks, uid_bytes):
         buf = C.create_string_buffer(bytes(uid_bytes), 128)
         self._check(self.lib.mcba_comm_init(self.h, rank, n_ranks, buf), "mcba_comm_init")
+
+    def schur_reduce_mode(self):
+        return {0: "single", 1: "nccl", 2: "p2p"}[self.lib.mcba_schur_reduce_mode(self.h)]
 
     def solve(self, params, opt=None, trace_cap=2048):
         opt = opt or default_options()

@@ -193,9 +193,32 @@ def _frame_poses(s, rng, n):
     return (R0 * Rw).as_rotvec(), R0.apply(tw) + s.cam_world[0, 3:]
 
 
-def generate_observations(s, frame_lo=0, frame_hi=None, noise=0.3, outlier_frac=0.01, outlier_sigma=20.0):
-    """Observations of frames [frame_lo, frame_hi) -> dict of flat arrays (bobs sorted by frame, cam, board)."""
+def _generate_span(args):
+    s, lo, hi, noise, outlier_frac, outlier_sigma = args
+    return generate_observations(s, lo, hi, noise, outlier_frac, outlier_sigma)
+
+
+def generate_observations(s, frame_lo=0, frame_hi=None, noise=0.3, outlier_frac=0.01, outlier_sigma=20.0, workers=1):
+    """Observations of frames [frame_lo, frame_hi) -> dict of flat arrays (bobs sorted by frame, cam, board).
+    workers > 1: the RNG chunks are independent, so spans of chunks are generated in forked worker processes and
+    concatenated - bit-identical to the serial result."""
     frame_hi = s.n_frames if frame_hi is None else frame_hi
+    c_lo, c_hi = frame_lo // CHUNK, (frame_hi + CHUNK - 1) // CHUNK
+    if workers > 1 and c_hi - c_lo >= 4:
+        import multiprocessing as mp
+        nspan = min(workers * 2, c_hi - c_lo)
+        cuts = [c_lo + (c_hi - c_lo) * i // nspan for i in range(nspan + 1)]
+        spans = [(s, max(frame_lo, cuts[i] * CHUNK), min(frame_hi, cuts[i + 1] * CHUNK), noise, outlier_frac, outlier_sigma)
+                 for i in range(nspan) if cuts[i + 1] > cuts[i]]
+        with mp.get_context("fork").Pool(workers) as pool:
+            parts = pool.map(_generate_span, spans)
+        o = Scene()
+        o.frame_lo, o.frame_hi = frame_lo, frame_hi
+        for k in ("bobs_frame", "bobs_cam", "bobs_board", "u", "v", "pt_idx", "obj_gt", "obj_init"):
+            setattr(o, k, np.concatenate([getattr(p, k) for p in parts]))
+        cnt = np.concatenate([np.diff(p.bobs_ptr) for p in parts])
+        o.bobs_ptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+        return o
     n_cam, n_board, P = s.n_cam, s.n_board, s.P
     keep = s.cfg["keep"]
     out = dict(frame=[], cam=[], board=[], cnt=[], u=[], v=[], pt=[], obj_rv=[], obj_t=[], obj_init=[])

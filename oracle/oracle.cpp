@@ -668,6 +668,7 @@ int oracle_solve(const mcba_problem* prob, mcba_params* params, const mcba_optio
   };
 
   // Init
+  const std::vector<double> x_start(W.x);
   double x_norm = norm2(W.x);
   double radius = opt->initial_trust_region_radius, decrease_factor = 2.0;
   bool reuse_diagonal = false;
@@ -782,8 +783,9 @@ int oracle_solve(const mcba_problem* prob, mcba_params* params, const mcba_optio
     }
   }
 
-  // Minimizer returns the best point seen (parameters_ = x at minimum cost).
-  write_back(W, best_x, params);
+  // Minimizer returns the best point seen (parameters_ = x at minimum cost); ceres::Solve (solver.cc, Minimize) then
+  // copies it to the user's parameter blocks only if the summary is usable - on FAILURE the ORIGINAL values are restored.
+  write_back(W, termination == MCBA_FAILURE ? x_start : best_x, params);
   S.termination = termination;
   S.num_iterations = n_rows;
   S.final_cost = minimum_cost;

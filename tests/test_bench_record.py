@@ -45,7 +45,7 @@ def test_committed_gpu_records(name, n):
 
 def test_reference_arm_runs_on_the_cpu():
     out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                          "--ref-frames", "12"], capture_output=True, text=True, timeout=600)
+                          "--frames-per-gpu", "12"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     d = json.loads(out.stdout.strip().splitlines()[-1])
     for k in BASE + ["impl", "e2e", "cpu_baseline"]:
@@ -53,4 +53,5 @@ def test_reference_arm_runs_on_the_cpu():
     assert d["impl"] == "reference" and d["unit"] == "Mobs/s" and d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
-    assert d["cpu_baseline"]["full_shard_upper_bound"]["value"] > d["value"]
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["single_thread_value"] > 0
+    assert d["config"]["frames"] == 12 and d["config"]["observations"] == d["cpu_baseline"]["observations_timed"]   # same config, same shard

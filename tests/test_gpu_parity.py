@@ -310,3 +310,108 @@ def test_empty_problem(oracle):
     rc, so, to = oracle.solve(e, po)
     assert (summ.termination, summ.num_iterations) == (so.termination, so.num_iterations) == (0, 1)
     assert summ.final_cost == 0.0 and np.array_equal(p.pose, init.pose)
+
+
+def test_active_blocks_with_exactly_zero_rotation(oracle, c2):
+    """The reference value-initialises a pose that was never set (std::map::operator[], CameraGroup.cpp:445-451): an
+    ACTIVE camera / board / object block with omega == 0 exactly takes AngleAxisRotatePoint's small-angle branch
+    (R = I + [w]x, dR/dw = -[p]x). Device prep_block (mcba_math.cuh) against the oracle's dual numbers, then a solve."""
+    prob, init, gt = stage_problem(c2, 5)
+    p = init.copy()
+    p.cam_pose[1, :3] = 0.0          # active (non-reference) camera, zero rotation, non-zero translation
+    p.board_pose[2, :3] = 0.0        # active board
+    p.pose[5, :3] = 0.0              # an e-block
+    p.cam_pose[2, :] = 0.0           # a fully zero active pose (what operator[] creates)
+    h = mcba.Handle(prob)
+    cost, res, jac = h.eval(p)
+    rc, ocost, ores, ojac, _ = oracle.eval(prob, p)
+    assert rc == 0 and np.isfinite(jac).all()
+    assert abs(cost - ocost) <= 1e-12 * abs(ocost)
+    assert np.abs(res - ores).max() <= 1e-9 * max(1.0, np.abs(ores).max())
+    assert rel(jac, ojac) <= 1e-11
+    h.close()
+    g, o = _solve_both(prob, p, oracle)
+    _assert_same_solution(prob, g, o)
+
+
+def test_kannala_point_exactly_on_the_optical_axis(oracle):
+    """r = 0: the functor's `r > 1e-8 ? theta_d / r : 1` guard (OptimizationCeres.h:472-477) selects the constant, so
+    the NaN partials of sqrt(0) in Ceres' Jets never reach the residual: the Jacobian is finite (d/dk = 0, the pose and
+    focal columns those of xd = a). Same on the device and in the oracle."""
+    pts = np.array([[0, 0, 0], [0.1, 0, 0], [0, 0.1, 0], [0.1, 0.1, 0], [0.05, 0.02, 0]], np.float32)
+    intr = np.array([[600.0, 600, 960, 540, -0.02, 3e-3, -1e-3, 2e-4, 0]])
+    pose = np.array([[0.0, 0, 0, 0, 0, 2.0], [0.1, -0.2, 0.05, 0, 0, 1.5]])      # frame 0: corner 0 projects to r = 0 exactly
+    uv = np.array([[961.0, 541.0]] * 10, np.float32)
+    prob = mcba.Problem(1, uv[:, 0], uv[:, 1], np.tile(np.arange(5), 2), [0, 5, 10], [0, 0], [0, 1], [0, 0], pts, [1], 2, 0)
+    p = mcba.Params(np.zeros((1, 6)), pose, np.zeros((0, 6)), intr)
+    h = mcba.Handle(prob)
+    cost, res, jac = h.eval(p)
+    h.close()
+    rc, ocost, ores, ojac, _ = oracle.eval(prob, p)
+    assert rc == 0 and np.isfinite(jac).all() and np.isfinite(ojac).all()
+    assert np.array_equal(jac[0, :, 10:14], np.zeros((2, 4)))        # d/d(k1..k4) of the on-axis corner
+    assert np.abs(res - ores).max() <= 1e-10 and rel(jac, ojac) <= 1e-11
+
+
+def test_failure_returns_the_start_point(oracle):
+    """ceres::Solve leaves the ORIGINAL parameter values in place when the summary is not usable (FAILURE)."""
+    import lm_cases
+    prob, p0, opt, _ = lm_cases.make_case("invalid_failure_c2_s5")
+    pg = p0.copy()
+    h = mcba.Handle(prob)
+    sg, _ = h.solve(pg, opt)
+    h.close()
+    assert sg.termination == 2
+    for name in ("cam_pose", "pose", "board_pose", "intrinsics"):
+        assert np.array_equal(getattr(pg, name), getattr(p0, name)), name
+
+
+def test_full_config3_against_the_committed_oracle_fixture():
+    """BASELINE configs[2] in full (16-camera ring, 5 boards, 5 000 frames, 10 188 613 observations) on ONE B200: stage 4
+    then stage 5 (calibrate.cpp:60-64) against tests/golden/full_c3.json (the CPU oracle, 160 s on 8 threads):
+    identical accept / reject sequence and termination, costs within 1e-9, RMS within 1e-6 px, f-blocks within 1e-6."""
+    import json, os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "full_c3.json")))
+    prob, init, gt, s, o = synth.config_problem("c3", 4)
+    assert prob.n_obs == gold["observations"]
+    p = init.copy()
+    p.intrinsics[:] = s.intr_init
+    h = mcba.Handle(prob)
+    for st in gold["stages"]:
+        if st["stage"] == 5:
+            h.set_stage(5)
+        summ, tr = h.solve(p)
+        assert [(r.iteration, r.step_is_valid, r.step_is_successful) for r in tr] == \
+               [(r["iteration"], r["valid"], r["successful"]) for r in st["trace"]]
+        assert summ.termination == st["termination"]
+        for a, b in zip(tr, st["trace"]):
+            assert abs(a.cost - b["cost"]) <= 1e-9 * b["cost"]
+            assert abs(a.trust_region_radius - b["radius"]) <= 1e-6 * b["radius"]
+        assert abs(summ.rms_px - st["rms_px"]) <= 1e-6
+        for name in ("cam_pose", "board_pose", "intrinsics"):
+            a, b = getattr(p, name), np.array(st[name])
+            assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max(), (st["stage"], name)
+    h.close()
+
+
+def test_registered_observations_are_shared_between_pose_init_and_bundle_adjustment():
+    """mcba_obs_register: one device copy of the corners serves mcba_pnp_ransac and mcba_create; results unchanged."""
+    from mcba import pnp
+    s = synth.make_scene("c2", n_frames=40)
+    o = synth.generate_observations(s)
+    prob, init, gt = synth.make_problem(s, o, 5)
+    p1, _, _ = synth.make_problem(s, o, 1)
+    p1.u, p1.v, p1.pt_idx = prob.u, prob.v, prob.pt_idx           # the same host arrays, as in the reference's BoardObs
+    P = pnp.PnpProblem(p1, s.intr_gt)
+    opt = pnp.default_options(threshold_px=10.0, max_iterations=200, seed=3)
+    r0 = pnp.ransac(P, opt)
+    pa = init.copy(); h = mcba.Handle(prob); sa, ta = h.solve(pa); h.close()
+    mcba.obs_register(prob)
+    r1 = pnp.ransac(P, opt)
+    pb = init.copy(); h = mcba.Handle(prob); sb, tb = h.solve(pb)
+    with pytest.raises(mcba.McbaError):
+        mcba.obs_release(prob)                                     # a live handle still reads the shared copy
+    h.close()
+    mcba.obs_release(prob)
+    assert np.array_equal(r0.pose, r1.pose) and np.array_equal(r0.inlier_mask, r1.inlier_mask)
+    assert trace_tuple(ta) == trace_tuple(tb) and np.array_equal(pa.intrinsics, pb.intrinsics)
