@@ -291,26 +291,40 @@ __global__ void __launch_bounds__(192) k_eblock_assemble(const int4* __restrict_
   for (int e = tid; e < 6 * ldz; e += blockDim.x) W[e] = 0.0;
   __syncthreads();
   const int b0 = pose_bobs_ptr[o], b1 = pose_bobs_ptr[o + 1];
+  // every thread owns one entry of the record and walks the e-block's board observations in order (fixed summation
+  // order); the loads of EA_U records are issued together - one dependent HBM round trip per record otherwise
+  constexpr int EA_U = 8;
   if (tid < 6 * C::WF) {
     const int j = tid / 6, k = tid % 6;                   // local f column j, e-row k: consecutive threads read consecutive
     const int off = C::cidx(j, C::E0 + k);                // doubles of the record's f x e part (CI_FE + 6 j + k = CI_FE + tid)
-    for (int b = b0; b < b1; ++b) {
-      const int4 rec = bobs[b];
-      const int gcol = (j < C::B0) ? rec.y * Wc + j : n_cam * Wc + rec.w * Wb + (j - C::B0);
-      W[k * ldz + gcol] += brec[(size_t)b * C::NCOMP + off];
+    for (int b = b0; b < b1; b += EA_U) {
+      double v[EA_U]; int gc[EA_U];
+#pragma unroll
+      for (int u = 0; u < EA_U; ++u)
+        if (b + u < b1) {
+          const int4 rec = bobs[b + u];
+          gc[u] = (j < C::B0) ? rec.y * Wc + j : n_cam * Wc + rec.w * Wb + (j - C::B0);
+          v[u] = brec[(size_t)(b + u) * C::NCOMP + off];
+        }
+#pragma unroll
+      for (int u = 0; u < EA_U; ++u)
+        if (b + u < b1) W[k * ldz + gc[u]] += v[u];
     }
-  } else if (tid < 6 * C::WF + 36) {
-    const int e = tid - 6 * C::WF, p = e / 6, r = e % 6;
-    const int off = C::cidx(C::E0 + min(p, r), C::E0 + max(p, r));
-    double s = 0.0;
-    for (int b = b0; b < b1; ++b) s += brec[(size_t)b * C::NCOMP + off];
-    Hoo[(size_t)o * 36 + e] = s;
   } else if (tid < 6 * C::WF + 42) {
-    const int k = tid - 6 * C::WF - 36;
-    const int off = C::cidx(C::E0 + k, C::R0);
+    const int e = tid - 6 * C::WF;
+    int off;
+    if (e < 36) { const int p = e / 6, r = e % 6; off = C::cidx(C::E0 + min(p, r), C::E0 + max(p, r)); }
+    else off = C::cidx(C::E0 + (e - 36), C::R0);
     double s = 0.0;
-    for (int b = b0; b < b1; ++b) s += brec[(size_t)b * C::NCOMP + off];
-    W[k * ldz + n_f] = s;
+    for (int b = b0; b < b1; b += EA_U) {
+      double v[EA_U];
+#pragma unroll
+      for (int u = 0; u < EA_U; ++u) v[u] = (b + u < b1) ? brec[(size_t)(b + u) * C::NCOMP + off] : 0.0;
+#pragma unroll
+      for (int u = 0; u < EA_U; ++u) if (b + u < b1) s += v[u];
+    }
+    if (e < 36) Hoo[(size_t)o * 36 + e] = s;
+    else W[(e - 36) * ldz + n_f] = s;
   }
   __syncthreads();
   double* dst = Wt + (size_t)o * 6 * ldz;
@@ -338,7 +352,14 @@ __global__ void __launch_bounds__(256) k_pair_reduce(const PairChunk* __restrict
   // entry t of a pair record is entry t of the compact per-bobs record (f x f upper, then f x r): contiguous reads
   const PairChunk ch = chunks[blockIdx.x];
   double s = 0.0;
-  for (int i = ch.begin; i < ch.end; ++i) s += brec[(size_t)pair_bobs[i] * C::NCOMP + t];
+  constexpr int PU = 8;   // loads of PU records in flight per thread; summation order unchanged
+  for (int i = ch.begin; i < ch.end; i += PU) {
+    double v[PU];
+#pragma unroll
+    for (int u = 0; u < PU; ++u) v[u] = (i + u < ch.end) ? brec[(size_t)pair_bobs[i + u] * C::NCOMP + t] : 0.0;
+#pragma unroll
+    for (int u = 0; u < PU; ++u) if (i + u < ch.end) s += v[u];
+  }
   partial[(size_t)blockIdx.x * PR::NE + t] = s;
 }
 template <int STAGE>
@@ -451,14 +472,25 @@ __global__ void __launch_bounds__(128) k_eblock_factor(const double* __restrict_
   }
   const double* W = Wt + (size_t)o * 6 * ldz;
   double* Zo = Z + (size_t)o * 6 * ldz;
-  for (int j = threadIdx.x; j < ldz; j += blockDim.x) {
-    double w[6];
-    const double sf = (j < n_f) ? scale_f[j] : 1.0;
+  constexpr int EF_U = 4;   // columns per thread in flight (their loads are issued before the first substitution)
+  for (int j0 = threadIdx.x; j0 < ldz; j0 += EF_U * blockDim.x) {
+    double w[EF_U][6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) w[k] = (j <= n_f) ? se[k] * W[k * ldz + j] * sf : 0.0;
-    if (ok) chol6_fwd(L, w);
+    for (int u = 0; u < EF_U; ++u) {
+      const int j = j0 + u * blockDim.x;
+      const double sf = (j < n_f) ? scale_f[j] : 1.0;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) Zo[k * ldz + j] = ok ? w[k] : 0.0;
+      for (int k = 0; k < 6; ++k) w[u][k] = (j <= n_f) ? se[k] * W[k * ldz + j] * sf : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < EF_U; ++u) {
+      const int j = j0 + u * blockDim.x;
+      if (j < ldz) {
+        if (ok) chol6_fwd(L, w[u]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) Zo[k * ldz + j] = ok ? w[u][k] : 0.0;
+      }
+    }
   }
 }
 
