@@ -178,6 +178,12 @@ int mcba_timer_stop(void *handle, double *ms);       /* second event + elapsed d
 /* Test hook: copy an internal device buffer (normal-equation blocks, reduced system, scaling) to the host.
  * Names: "FF" "gf" "S" "rhs" "zf" "ZtZ" "Hoo" "Wt" "Z" "brec" "scale_e" "scale_f" "diag_e" "diag_f". */
 int mcba_debug_fetch(void *handle, const char *name, double *out, int64_t cap, int64_t *n_out);
+/* Test / benchmark hook: factor and solve one dense symmetric positive definite system with the reduced-system
+ * kernels alone. S_host is (n+1) x n row-major (matrix rows, then the right-hand side as row n); z_out [n] = solution,
+ * L_out [(n+1) x n] = the factor in the lower triangle (row n = L^-1 rhs). variant 0: grid-synchronous kernel,
+ * 1: dataflow kernel (one CTA per 64x64 tile), -1: the solver's own choice. ms_out = mean kernel time over iters. */
+int mcba_debug_cholesky(void *handle, int n, const double *S_host, double *z_out, double *L_out, int variant,
+                        int iters, double *ms_out, int *fail_out);
 
 #ifdef __cplusplus
 }

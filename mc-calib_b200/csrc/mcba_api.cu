@@ -10,6 +10,7 @@
 #include "mcba_kernels.cuh"
 #include "mcba_lm.cuh"
 #include "mcba_batched.cuh"
+#include "mcba_chol_tiles.cuh"
 
 #include <dlfcn.h>
 #include <algorithm>
@@ -89,6 +90,7 @@ struct Handle {
   int syrk_nt = 0, syrk_tiles = 0, syrk_nsplit = 0; int64_t syrk_rows_per_split = 0;
   int chol_grid = 1, n_sm = 148;
   long long* d_chol_prof = nullptr;
+  unsigned* d_ct_flags = nullptr; double *d_ct_dinv = nullptr, *d_ct_pbuf = nullptr; unsigned ct_epoch = 0; int ct_capacity = 0;   // k_chol_tiles
   // batched independent problems (config 5)
   bool batched = false;
   const uint8_t* obs_gate = nullptr;
@@ -489,6 +491,17 @@ static int eval_jacobian(Handle* H, bool first) {
 static int cholesky_reduced(Handle* H) {
   Timed t(H, KF_CHOL);
   int n = H->n_f;
+  // dataflow kernel (one CTA per 64x64 tile of the factor) whenever all tiles fit on the device at once
+  static const bool tiles_off_env = []() { const char* e = getenv("MCBA_CHOL_TILES"); return e && atoi(e) == 0; }();
+  bool tiles_off = tiles_off_env;
+  if (const char* once = getenv("MCBA_CHOL_TILES_ONCE")) tiles_off = atoi(once) == 0;   // mcba_debug_cholesky
+  if (!tiles_off && n > 0 && ct_num_tiles(n) <= H->ct_capacity && (n + CT_B - 1) / CT_B <= CT_MAXNT) {
+    CholTilesArgs a{H->d_S, n, H->d_zf, H->d_fail, H->d_ct_flags, ++H->ct_epoch, H->d_ct_dinv, H->d_ct_pbuf};
+    void* args[] = {&a};
+    ++H->n_launches;
+    CU(cudaLaunchCooperativeKernel((void*)k_chol_tiles, dim3(ct_num_tiles(n)), dim3(CT_THREADS), args, CT_SMEM, H->stream));
+    return MCBA_OK;
+  }
   if (n > 2 * CC_B * CC_LD) { H->err = "reduced system too large for the cooperative Cholesky (n_f > 8704)"; return MCBA_ERR_INVALID; }
   double* S = H->d_S; double* z = H->d_zf; int* fail = H->d_fail;
   static const bool want_prof = getenv("MCBA_CHOL_PROF") != nullptr;
@@ -864,7 +877,7 @@ void mcba_destroy(void* h) {
   dfree(H, &H->d_FF); dfree(H, &H->d_gf); dfree(H, &H->d_S); dfree(H, &H->d_rhs); dfree(H, &H->d_zf); dfree(H, &H->d_ZtZ); dfree(H, &H->d_hz);
   dfree(H, &H->d_syrk_partial); dfree(H, &H->d_pair_partial); dfree(H, &H->d_pair_rec); dfree(H, &H->d_part_e);
   dfree(H, &H->d_red_scratch); dfree(H, &H->d_scalars); dfree(H, &H->d_gather); dfree(H, &H->d_fail);
-  dfree(H, &H->d_jmat); dfree(H, &H->d_resmat);
+  dfree(H, &H->d_jmat); dfree(H, &H->d_resmat); dfree(H, &H->d_ct_flags); dfree(H, &H->d_ct_dinv); dfree(H, &H->d_ct_pbuf);
   dfree(H, &H->d_cam_ptr); dfree(H, &H->d_lm); dfree(H, &H->d_gate_jac); dfree(H, &H->d_active); dfree(H, &H->d_cam_fail); dfree(H, &H->d_n_active);
   dfree(H, &H->d_cam_sc); dfree(H, &H->d_cam_cost);
   for (int w = 0; w < 2; ++w) { dfree(H, &H->d_cam_pose[w]); dfree(H, &H->d_pose[w]); dfree(H, &H->d_board[w]); dfree(H, &H->d_intr[w]); }
@@ -972,6 +985,11 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   { int per_sm = 0; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chol_coop, CC_THREADS, CC_SMEM));
     if (per_sm < 1 || !coop) { H->err = "cooperative launch unavailable"; return MCBA_ERR_CUDA; }
     H->chol_grid = H->n_sm; }
+  CU(cudaFuncSetAttribute(k_chol_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
+  { int per_sm = 0; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chol_tiles, CT_THREADS, CT_SMEM));
+    H->ct_capacity = std::min(CT_MAXT, per_sm * H->n_sm); }
+  if (dalloc(H, &H->d_ct_flags, (size_t)2 * CT_MAXT + 64) || dalloc(H, &H->d_ct_dinv, (size_t)CT_MAXNT * 512) || dalloc(H, &H->d_ct_pbuf, (size_t)CT_MAXT * 64)) return MCBA_ERR_CUDA;
+  CU(cudaMemsetAsync(H->d_ct_flags, 0, ((size_t)2 * CT_MAXT + 64) * sizeof(unsigned), H->stream));
   mcba_default_options(&H->opt);
   mark("small allocs");
   const int rc = setup_stage(H, P->stage);
@@ -1305,6 +1323,41 @@ int mcba_reprojection_errors(void* h, const mcba_params* p, double* err) {
   cudaFreeAsync(d_err, H->stream);
   if (e != cudaSuccess) { H->err = cudaGetErrorString(e); return MCBA_ERR_CUDA; }
   return MCBA_OK;
+}
+
+// Test / benchmark hook: factor and solve one dense system with the reduced-system kernels on their own.
+// S_host is (n+1) x n row-major (symmetric matrix, then the rhs row). variant 0 = k_chol_coop, 1 = k_chol_tiles,
+// -1 = what the solver would pick. Returns the mean kernel time over `iters` runs (the system is re-uploaded each time).
+int mcba_debug_cholesky(void* h, int n, const double* S_host, double* z_out, double* L_out, int variant, int iters, double* ms_out, int* fail_out) {
+  Handle* H = (Handle*)h; if (!H || n <= 0 || !S_host) return MCBA_ERR_INVALID;
+  CU(cudaSetDevice(H->device));
+  double *S_keep = H->d_S, *z_keep = H->d_zf; const int n_keep = H->n_f;
+  double *dS = nullptr, *dz = nullptr;
+  CU(cudaMalloc((void**)&dS, (size_t)(n + 1) * n * sizeof(double))); CU(cudaMalloc((void**)&dz, (size_t)n * sizeof(double)));
+  H->d_S = dS; H->d_zf = dz; H->n_f = n;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double total = 0; int rc = MCBA_OK;
+  if (variant == 0) setenv("MCBA_CHOL_TILES_ONCE", "0", 1); else if (variant == 1) setenv("MCBA_CHOL_TILES_ONCE", "1", 1); else unsetenv("MCBA_CHOL_TILES_ONCE");
+  for (int it = 0; it < std::max(1, iters) && rc == MCBA_OK; ++it) {
+    cudaMemcpyAsync(dS, S_host, (size_t)(n + 1) * n * sizeof(double), cudaMemcpyHostToDevice, H->stream);
+    cudaMemsetAsync(H->d_fail, 0, sizeof(int), H->stream);
+    cudaEventRecord(e0, H->stream);
+    rc = cholesky_reduced(H);
+    cudaEventRecord(e1, H->stream);
+    if (cudaStreamSynchronize(H->stream) != cudaSuccess) { H->err = cudaGetErrorString(cudaGetLastError()); rc = MCBA_ERR_CUDA; break; }
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); total += ms;
+  }
+  unsetenv("MCBA_CHOL_TILES_ONCE");
+  if (rc == MCBA_OK) {
+    if (z_out) cudaMemcpy(z_out, dz, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+    if (L_out) cudaMemcpy(L_out, dS, (size_t)(n + 1) * n * sizeof(double), cudaMemcpyDeviceToHost);
+    if (fail_out) cudaMemcpy(fail_out, H->d_fail, sizeof(int), cudaMemcpyDeviceToHost);
+    if (ms_out) *ms_out = total / std::max(1, iters);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(dS); cudaFree(dz);
+  H->d_S = S_keep; H->d_zf = z_keep; H->n_f = n_keep;
+  flush_timers(H);
+  return rc;
 }
 
 // Debug/test hook: copy an internal device buffer to the host. Names: "FF","gf","S","rhs","zf","ZtZ","Hoo","Wt","Z","brec","scale_e","scale_f","diag_e","diag_f"

@@ -193,6 +193,7 @@ def load_lib():
     L.mcba_timer_start.argtypes = [vp]
     L.mcba_timer_stop.argtypes = [vp, c_f64p]
     L.mcba_debug_fetch.argtypes = [vp, C.c_char_p, c_f64p, C.c_int64, C.POINTER(C.c_int64)]
+    L.mcba_debug_cholesky.argtypes = [vp, C.c_int, c_f64p, c_f64p, c_f64p, C.c_int, C.c_int, c_f64p, C.POINTER(C.c_int)]
     _lib = L
     return L
 
@@ -320,6 +321,16 @@ class Handle:
         self._check(self.lib.mcba_debug_fetch(self.h, name.encode(), _ptr(out, c_f64p), n.value, C.byref(n)),
                     "mcba_debug_fetch")
         return out
+
+    def debug_cholesky(self, A, rhs, variant=-1, iters=1):
+        """Solve A z = rhs with the reduced-system kernels alone -> (z, L, mean kernel ms, fail flag)."""
+        n = len(rhs)
+        S = np.ascontiguousarray(np.vstack([np.asarray(A, np.float64), np.asarray(rhs, np.float64)[None, :]]))
+        z, L = np.zeros(n), np.zeros((n + 1, n))
+        ms, fail = C.c_double(), C.c_int()
+        self._check(self.lib.mcba_debug_cholesky(self.h, n, _ptr(S, c_f64p), _ptr(z, c_f64p), _ptr(L, c_f64p), variant, iters,
+                                                 C.byref(ms), C.byref(fail)), "mcba_debug_cholesky")
+        return z, L, ms.value, fail.value
 
     def reset_kernel_stats(self):
         self.lib.mcba_reset_kernel_stats(self.h)
