@@ -161,6 +161,11 @@ int mcba_jacobian_width(int stage);
 /* Per-observation reprojection error sqrt(du^2+dv^2) at the given parameters (unrobustified), the quantity
  * Calibration::computeAvgReprojectionError averages (McCalib/src/McCalib.cpp:2168-2245). */
 int mcba_reprojection_errors(void *handle, const mcba_params *params, double *err /* [n_obs] */);
+/* The same errors as the reference's OUTPUTS hold them, i.e. with its intermediate roundings: object-frame points
+ * after the object pose stored as cv::Point3f (transform3DPts, McCalib/src/geometrytools.cpp:328-352), projections
+ * returned as cv::Point2f by cv::projectPoints, float difference, double sqrt stored in a float
+ * (computeDistanceBetweenPoints, McCalib/src/McCalib.cpp:2150-2160). Use on a stage-3 packing (Object3D::pts_3d_). */
+int mcba_reprojection_errors_f32(void *handle, const mcba_params *params, float *err /* [n_obs] */);
 
 void mcba_destroy(void *handle);
 const char *mcba_last_error(void *handle);

@@ -90,7 +90,7 @@ struct Handle {
   int syrk_nt = 0, syrk_tiles = 0, syrk_nsplit = 0; int64_t syrk_rows_per_split = 0;
   int chol_grid = 1, n_sm = 148;
   long long* d_chol_prof = nullptr;
-  unsigned* d_ct_flags = nullptr; double *d_ct_dinv = nullptr, *d_ct_pbuf = nullptr; unsigned ct_epoch = 0; int ct_capacity = 0;   // k_chol_tiles
+  unsigned* d_ct_flags = nullptr; double *d_ct_dinv = nullptr, *d_ct_pbuf = nullptr; unsigned ct_epoch = 0; int ct_capacity = 0; long long* d_ct_prof = nullptr;   // k_chol_tiles
   // batched independent problems (config 5)
   bool batched = false;
   const uint8_t* obs_gate = nullptr;
@@ -496,7 +496,10 @@ static int cholesky_reduced(Handle* H) {
   bool tiles_off = tiles_off_env;
   if (const char* once = getenv("MCBA_CHOL_TILES_ONCE")) tiles_off = atoi(once) == 0;   // mcba_debug_cholesky
   if (!tiles_off && n > 0 && ct_num_tiles(n) <= H->ct_capacity && (n + CT_B - 1) / CT_B <= CT_MAXNT) {
-    CholTilesArgs a{H->d_S, n, H->d_zf, H->d_fail, H->d_ct_flags, ++H->ct_epoch, H->d_ct_dinv, H->d_ct_pbuf};
+    static const bool ct_prof = getenv("MCBA_CHOL_PROF") != nullptr;
+    if (ct_prof && !H->d_ct_prof) { CU(cudaMalloc((void**)&H->d_ct_prof, (size_t)CT_MAXT * 8 * sizeof(long long))); }
+    if (ct_prof) CU(cudaMemsetAsync(H->d_ct_prof, 0, (size_t)CT_MAXT * 8 * sizeof(long long), H->stream));
+    CholTilesArgs a{H->d_S, n, H->d_zf, H->d_fail, H->d_ct_flags, ++H->ct_epoch, H->d_ct_dinv, H->d_ct_pbuf, H->d_ct_prof};
     void* args[] = {&a};
     ++H->n_launches;
     CU(cudaLaunchCooperativeKernel((void*)k_chol_tiles, dim3(ct_num_tiles(n)), dim3(CT_THREADS), args, CT_SMEM, H->stream));
@@ -1304,26 +1307,30 @@ int mcba_eval(void* h, const mcba_params* p, const mcba_options* opt, double* co
   return std::isfinite(c) ? MCBA_OK : MCBA_ERR_NUMERIC;
 }
 
-int mcba_reprojection_errors(void* h, const mcba_params* p, double* err) {
-  Handle* H = (Handle*)h; if (!H || !err) return MCBA_ERR_INVALID;
+static int reprojection_errors(void* h, const mcba_params* p, double* err, float* err_ref) {
+  Handle* H = (Handle*)h; if (!H || (!err && !err_ref)) return MCBA_ERR_INVALID;
   CU(cudaSetDevice(H->device));
   int rc;
   if ((rc = upload_params(H, p))) return rc;
   if ((rc = launch_prep(H, 0))) return rc;
-  double* d_err = nullptr;
-  if (dalloc(H, &d_err, (size_t)H->npad)) return MCBA_ERR_CUDA;
+  double* d_err = nullptr; float* d_ref = nullptr;
+  if (err_ref ? dalloc(H, &d_ref, (size_t)H->npad) : dalloc(H, &d_err, (size_t)H->npad)) return MCBA_ERR_CUDA;
   ObsArgs a = obs_args(H, 0, 0.0);
   if (H->nb > 0) {
     ++H->n_launches;
-    DISPATCH_STAGE(H->stage, (k_reproj_err<ST><<<grid_for(H, H->nb, 8), OBS_WARPS * 32, OBS_WARPS * CTX_SIZE * 8, H->stream>>>(a, d_err)));
+    DISPATCH_STAGE(H->stage, (k_reproj_err<ST><<<grid_for(H, H->nb, 8), OBS_WARPS * 32, OBS_WARPS * CTX_SIZE * 8, H->stream>>>(a, d_err, d_ref)));
   }
   cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpyAsync(err, d_err, H->n_obs * sizeof(double), cudaMemcpyDeviceToHost, H->stream);
+  if (e == cudaSuccess) e = err_ref ? cudaMemcpyAsync(err_ref, d_ref, H->n_obs * sizeof(float), cudaMemcpyDeviceToHost, H->stream)
+                                    : cudaMemcpyAsync(err, d_err, H->n_obs * sizeof(double), cudaMemcpyDeviceToHost, H->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(H->stream);
-  cudaFreeAsync(d_err, H->stream);
+  if (d_err) cudaFreeAsync(d_err, H->stream);
+  if (d_ref) cudaFreeAsync(d_ref, H->stream);
   if (e != cudaSuccess) { H->err = cudaGetErrorString(e); return MCBA_ERR_CUDA; }
   return MCBA_OK;
 }
+int mcba_reprojection_errors(void* h, const mcba_params* p, double* err) { return reprojection_errors(h, p, err, nullptr); }
+int mcba_reprojection_errors_f32(void* h, const mcba_params* p, float* err) { return reprojection_errors(h, p, nullptr, err); }
 
 // Test / benchmark hook: factor and solve one dense system with the reduced-system kernels on their own.
 // S_host is (n+1) x n row-major (symmetric matrix, then the rhs row). variant 0 = k_chol_coop, 1 = k_chol_tiles,
@@ -1374,6 +1381,13 @@ int mcba_debug_fetch(void* h, const char* name, double* out, int64_t cap, int64_
   else if (s == "Z") { src = H->d_Z; n = np * 6 * ldz; } else if (s == "brec") { src = H->d_brec; n = (int64_t)H->nb * stage_dims(H->stage).NCOMP; }
   else if (s == "scale_e") { src = H->d_scale_e; n = np * 6; } else if (s == "scale_f") { src = H->d_scale_f; n = nf; }
   else if (s == "diag_e") { src = H->d_diag_e; n = np * 6; } else if (s == "diag_f") { src = H->d_diag_f; n = nf; }
+  else if (s == "chol_prof") {   // %globaltimer stamps of the last k_chol_tiles launch, as doubles (ns)
+    if (!H->d_ct_prof) { H->err = "run with MCBA_CHOL_PROF=1"; return MCBA_ERR_INVALID; }
+    n = (int64_t)CT_MAXT * 8;
+    if (n_out) *n_out = n;
+    if (out) { std::vector<long long> t(n); CU(cudaStreamSynchronize(H->stream)); CU(cudaMemcpy(t.data(), H->d_ct_prof, n * sizeof(long long), cudaMemcpyDeviceToHost)); for (int64_t i = 0; i < std::min(n, cap); ++i) out[i] = (double)t[i]; }
+    return MCBA_OK;
+  }
   else { H->err = "unknown buffer"; return MCBA_ERR_INVALID; }
   if (n_out) *n_out = n;
   if (out) { CU(cudaStreamSynchronize(H->stream)); CU(cudaMemcpy(out, src, std::min(n, cap) * sizeof(double), cudaMemcpyDeviceToHost)); }

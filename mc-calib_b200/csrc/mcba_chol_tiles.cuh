@@ -33,6 +33,7 @@ struct CholTilesArgs {
   unsigned epoch;
   double* dinv;           // [CT_MAXNT][512] inverses of the 8x8 diagonal blocks of L(j,j)
   double* pbuf;           // [CT_MAXT][64] backward-substitution contributions
+  long long* prof;        // optional [CT_MAXT][8] %globaltimer stamps per tile (MCBA_CHOL_PROF)
 };
 
 __device__ __forceinline__ void ct_post(unsigned* f, unsigned epoch) {
@@ -47,6 +48,17 @@ __device__ __forceinline__ bool ct_wait(const unsigned* f, unsigned epoch, int* 
     if (v == epoch) return true;
     if (clock64() - t0 > CT_TIMEOUT) { atomicExch(fail, 2); return false; }
   }
+}
+__device__ __forceinline__ long long ct_now() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define CT_STAMP(k) do { if (a.prof && tid == 0) a.prof[(size_t)my_tile * 8 + (k)] = ct_now(); } while (0)
+// 1/d for a positive, comfortably normal d: hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps; the pivot
+// recurrence of the diagonal-block factorisation hangs on this latency (64 dependent pivots per tile).
+__device__ __forceinline__ double ct_rcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0); x = fma(x, e, x);
+  e = fma(-d, x, 1.0); x = fma(x, e, x);
+  return x;
 }
 __host__ __device__ inline int ct_tile_id(int i, int j, int NT) { return j * (NT + 1) - j * (j - 1) / 2 + (i - j); }
 __host__ __device__ inline int ct_num_tiles(int n) { const int NT = (n + CT_B - 1) / CT_B; return NT * (NT + 3) / 2; }
@@ -92,6 +104,7 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_chol_tiles(CholTilesArgs a) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
   bool alive = true;
+  CT_STAMP(0);
   // ---- 1. left-looking updates
   for (int k = 0; k < tj; ++k) {
     if (tid == 0) alive = ct_wait(ready + ct_tile_id(ti, k, NT), epoch, a.fail);
@@ -128,6 +141,7 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_chol_tiles(CholTilesArgs a) {
     }
   }
   __syncthreads();
+  CT_STAMP(1);
   // ---- 2. X = A - acc into T0 (identity padding beyond the valid part of a diagonal tile)
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -142,82 +156,116 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_chol_tiles(CholTilesArgs a) {
       }
   __syncthreads();
   if (is_diag) {
-    // ---- potrf of the 64x64 block: D = T0 (lower part), factor -> T1, right-looking in 8-wide sub-panels
+    // ---- potrf of the 64x64 block: D = T0 (lower part), factor -> T1, right-looking in 8-wide sub-panels.
+    // Per sub-panel: (b1) warp 0 factors the 8x8 diagonal block in registers, every lane redundantly (no shuffles on the
+    // pivot chain), in the square-root-free form: pivot recurrence d_{j+1} = a_{j+1,j+1} - a_{j+1,j}^2 / d_j with a
+    // Newton reciprocal (one MUFU + 4 DFMA) as the only long-latency link; lanes 8..15 turn it into a column of the
+    // block's inverse; (b2) one thread per row below solves its 8 entries; (c) DMMA trailing update, where warp 0
+    // takes the NEXT diagonal block first and goes straight on to factor it while the other warps finish the update.
+    double* F8 = red;                                         // [8][8] unit-lower entries t[r][k] (k < r); diagonal: 1/sqrt(d)
+    for (int e = tid; e < CT_B * CT_B; e += CT_THREADS) { const int r = e >> 6, c = e & 63; if (c > r) T1[r * CT_LD + c] = 0.0; }
     for (int c0 = 0; c0 < CT_B; c0 += 8) {
-      if (tid < CT_B - c0 || (tid >= 64 && tid < 72)) {
-        double l[8][8], inv[8];
+      if (warp == 0) {
+        if (c0 > 0) {                                         // next diagonal block's share of the previous trailing update
+          double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const double f = T1[(c0 + g) * CT_LD + c0 - 8 + 4 * s2 + q];
+            dmma884(d0, d1, f, f);
+          }
+          double2* p = reinterpret_cast<double2*>(T0 + (c0 + g) * CT_LD + c0 + 2 * q);
+          double2 cur = *p; cur.x -= d0; cur.y -= d1; *p = cur;
+          __syncwarp();
+        }
+        double m[8][8], dd[8], si[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r)
 #pragma unroll
-          for (int c = 0; c <= r; ++c) l[r][c] = T0[(c0 + r) * CT_LD + c0 + c];
+          for (int c = 0; c <= r; ++c) m[r][c] = T0[(c0 + r) * CT_LD + c0 + c];
         bool bad = false;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const double d = l[j][j];
+          const double d = m[j][j];
+          dd[j] = d;
           const bool b = !(d > 0.0) || !(d < DBL_MAX);
           bad = bad || b;
-          inv[j] = b ? 1.0 : rsqrt(d);
-          l[j][j] = d * inv[j];
+          const bool fast = d > 1e-280 && d < 1e280;
+          double tr[8];
+          if (fast) {
+            const double rj = ct_rcp(d);
+            if (j < 7) m[j + 1][j + 1] = fma(-(m[j + 1][j] * m[j + 1][j]), rj, m[j + 1][j + 1]);   // next pivot first
 #pragma unroll
-          for (int r = j + 1; r < 8; ++r) l[r][j] *= inv[j];
+            for (int r = j + 1; r < 8; ++r) tr[r] = m[r][j] * rj;
+          } else {                                            // tiny / huge / invalid pivot: through 1/sqrt(d), no overflow of 1/d
+            const double sj = b ? 1.0 : rsqrt(d);
+#pragma unroll
+            for (int r = j + 1; r < 8; ++r) tr[r] = (m[r][j] * sj) * sj;
+            if (j < 7) m[j + 1][j + 1] = fma(-tr[j + 1], m[j + 1][j], m[j + 1][j + 1]);
+          }
 #pragma unroll
           for (int r = j + 1; r < 8; ++r)
 #pragma unroll
-            for (int c = j + 1; c <= r; ++c) l[r][c] -= l[r][j] * l[c][j];
+            for (int c = j + 1; c <= r; ++c)
+              if (!(r == j + 1 && c == j + 1)) m[r][c] = fma(-tr[r], m[c][j], m[r][c]);
+#pragma unroll
+          for (int r = j + 1; r < 8; ++r) m[r][j] = tr[r];
         }
-        if (tid < CT_B - c0) {
-          const int i = c0 + tid;
-          double x[8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            double t = T0[i * CT_LD + c0 + c];
+        for (int j = 0; j < 8; ++j) { const bool b = !(dd[j] > 0.0) || !(dd[j] < DBL_MAX); si[j] = b ? 1.0 : rsqrt(dd[j]); }
+        if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < c; ++k) t -= x[k] * l[c][k];
-            x[c] = (c0 + c <= i) ? t * inv[c] : 0.0;
-          }
+          for (int r = 0; r < 8; ++r)
 #pragma unroll
-          for (int c = 0; c < 8; ++c) T1[i * CT_LD + c0 + c] = x[c];
-          if (tid == 0) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) invd[c0 + c] = inv[c];
-            if (bad) atomicExch(a.fail, 1);
-          }
-        } else {
-          const int cc = tid - 64;                            // column cc of the inverse of the 8x8 block
+            for (int c = 0; c <= r; ++c) F8[r * 8 + c] = (c == r) ? si[r] : m[r][c];
+          if (bad) atomicExch(a.fail, 1);
+        } else if (lane >= 8 && lane < 16) {
+          const int cc = lane - 8;                            // column cc of the inverse of the 8x8 Cholesky block
           double y[8];
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
             double t = (r == cc) ? 1.0 : 0.0;
 #pragma unroll
-            for (int k = 0; k < r; ++k) t -= l[r][k] * y[k];
-            y[r] = t * inv[r];
+            for (int k = 0; k < r; ++k) t -= (m[r][k] * (dd[k] * si[k])) * y[k];     // L[r][k] = t[r][k] * sqrt(d_k)
+            y[r] = t * si[r];
           }
 #pragma unroll
           for (int r = 0; r < 8; ++r) Dinv[(c0 >> 3) * 64 + r * 8 + cc] = y[r];
         }
       }
-      if (c0 == 0 && tid >= 72) {
-        // rows above the first sub-panel's reach: clear the strictly upper part of the factor once
-        for (int e = tid - 72; e < CT_B * CT_B; e += CT_THREADS - 72) { const int r = e >> 6, c = e & 63; if (c > r && c >= 8) T1[r * CT_LD + c] = 0.0; }
-      }
       __syncthreads();
-      const int m = 7 - (c0 >> 3);                            // trailing 8x8 tiles per side
-      const int ntile = m * (m + 1) / 2;
-      for (int t = warp; t < ntile; t += CT_THREADS / 32) {
-        int rt = 0, rr = t;
-        while (rr >= rt + 1) { rr -= rt + 1; ++rt; }
-        const int R = c0 + 8 + 8 * rt, Cc = c0 + 8 + 8 * rr;
-        double d0 = 0.0, d1 = 0.0;
+      if (tid < CT_B - c0) {                                  // (b2) row i of the sub-panel: v_c = D_ic - sum_k v_k t_ck, L_ic = v_c / sqrt(d_c)
+        const int i = c0 + tid;
+        double v[8];
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
-          dmma884(d0, d1, T1[(R + g) * CT_LD + c0 + 4 * s + q], T1[(Cc + g) * CT_LD + c0 + 4 * s + q]);
-        double2* p = reinterpret_cast<double2*>(T0 + (R + g) * CT_LD + Cc + 2 * q);
-        double2 cur = *p;
-        cur.x -= d0; cur.y -= d1;
-        *p = cur;
+        for (int c = 0; c < 8; ++c) {
+          double t = T0[i * CT_LD + c0 + c];
+#pragma unroll
+          for (int k = 0; k < c; ++k) t = fma(-v[k], F8[c * 8 + k], t);
+          v[c] = t;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) T1[i * CT_LD + c0 + c] = (c0 + c <= i) ? v[c] * F8[c * 9] : 0.0;
       }
       __syncthreads();
+      // (c) trailing update on the 8x8 tiles below/right; tile (0,0) - the next diagonal block - is warp 0's, above
+      const int m8 = 7 - (c0 >> 3);
+      const int ntile = m8 * (m8 + 1) / 2;
+      if (warp > 0)
+        for (int t = warp; t < ntile; t += CT_THREADS / 32 - 1) {
+          int rt = 0, rr = t;
+          while (rr >= rt + 1) { rr -= rt + 1; ++rt; }
+          const int R = c0 + 8 + 8 * rt, Cc = c0 + 8 + 8 * rr;
+          double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2)
+            dmma884(d0, d1, T1[(R + g) * CT_LD + c0 + 4 * s2 + q], T1[(Cc + g) * CT_LD + c0 + 4 * s2 + q]);
+          double2* p = reinterpret_cast<double2*>(T0 + (R + g) * CT_LD + Cc + 2 * q);
+          double2 cur = *p; cur.x -= d0; cur.y -= d1; *p = cur;
+        }
+      // no barrier here: warp 0 loops straight into the next diagonal block; the barrier after (b1) covers the update
     }
+    __syncthreads();
+    CT_STAMP(2);
     // publish L(j,j) (in place in S) and the 8x8 inverses
     for (int e = tid; e < CT_B * CT_B; e += CT_THREADS) {
       const int r = e >> 6, c = e & 63;
@@ -227,10 +275,12 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_chol_tiles(CholTilesArgs a) {
     __threadfence();
     __syncthreads();
     if (tid == 0) ct_post(ready + my_tile, epoch);
+    CT_STAMP(3);
   } else {
     // ---- trsm: X <- X L(j,j)^-T. Each warp owns 8 rows and walks the 8 column blocks; no CTA-wide barrier inside.
     if (tid == 0) alive = ct_wait(ready + ct_tile_id(tj, tj, NT), epoch, a.fail);
     __syncthreads();
+    CT_STAMP(4);
     {
       double vb[16];
 #pragma unroll
@@ -243,6 +293,7 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_chol_tiles(CholTilesArgs a) {
       for (int e = tid; e < 512; e += CT_THREADS) Dinv[e] = __ldcg(a.dinv + (size_t)tj * 512 + e);
     }
     __syncthreads();
+    CT_STAMP(5);
     const int R = 8 * warp;
     for (int b = 0; b < 8; ++b) {
       double c0a = 0.0, c1a = 0.0, c0b = 0.0, c1b = 0.0;      // two accumulators: half the dependent DMMA chain
@@ -264,6 +315,7 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_chol_tiles(CholTilesArgs a) {
       __syncwarp();
     }
     __syncthreads();
+    CT_STAMP(2);
     for (int e = tid; e < CT_B * CT_B; e += CT_THREADS) {
       const int r = e >> 6, c = e & 63;
       if (r < rv && c < cv) S[(size_t)(row0 + r) * n + col0 + c] = T0[r * CT_LD + c];
@@ -271,13 +323,16 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_chol_tiles(CholTilesArgs a) {
     __threadfence();
     __syncthreads();
     if (tid == 0) ct_post(ready + my_tile, epoch);
+    CT_STAMP(3);
   }
   if (is_rhs) return;
   // ---- 3. backward substitution
   if (!is_diag) {
+    if (ti == tj + 1) return;            // the owner of (j,j) applies L(j+1,j)^T z_{j+1} itself from its own copy of the tile
     // contribution of this tile: p = L(i,j)^T z_i
     if (tid == 0) alive = ct_wait(zready + ti, epoch, a.fail);
     __syncthreads();
+    CT_STAMP(6);
     if (tid < CT_B) zv[tid] = (tid < rv) ? __ldcg(a.z + row0 + tid) : 0.0;
     __syncthreads();
     {
@@ -292,9 +347,26 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_chol_tiles(CholTilesArgs a) {
     __threadfence();
     __syncthreads();
     if (tid == 0) ct_post(pready + my_tile, epoch);
+    CT_STAMP(7);
     return;
   }
-  // diagonal owner: w = y_j - sum_{i>j} p(i,j) in the fixed order i = NT-1 .. j+1, then L(j,j)^T z_j = w
+  // diagonal owner: w = y_j - sum_{i>j} L(i,j)^T z_i in the fixed order i = NT-1 .. j+1, then L(j,j)^T z_j = w.
+  // The contributions of the tiles further down arrive early (their z_i are long published when z_{j+1} is); the one of
+  // the sub-diagonal tile is the critical one: this CTA keeps its own copy of L(j+1,j) in T0 (loaded while idle) and
+  // applies it as soon as z_{j+1} is visible - no second hop through another CTA.
+  const int rv1 = (tj + 1 < NT) ? min(CT_B, n - (tj + 1) * CT_B) : 0;
+  if (tj + 1 < NT) {
+    if (tid == 0) alive = ct_wait(ready + ct_tile_id(tj + 1, tj, NT), epoch, a.fail);
+    __syncthreads();
+    double vb[16];
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const int e = tid + it * CT_THREADS, r = e >> 6, c = e & 63;
+      vb[it] = (r < rv1 && c < cv) ? __ldcg(S + (size_t)((tj + 1) * CT_B + r) * n + col0 + c) : 0.0;
+    }
+#pragma unroll
+    for (int it = 0; it < 16; ++it) { const int e = tid + it * CT_THREADS; T0[(e >> 6) * CT_LD + (e & 63)] = vb[it]; }
+  }
   if (tid == 0) {
     alive = ct_wait(ready + ct_tile_id(NT, tj, NT), epoch, a.fail);
     for (int i = NT - 1; i >= tj + 2; --i) alive = ct_wait(pready + ct_tile_id(i, tj, NT), epoch, a.fail) && alive;
@@ -313,29 +385,50 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_chol_tiles(CholTilesArgs a) {
     }
   }
   if (tj + 1 < NT) {
-    if (tid == 0) alive = ct_wait(pready + ct_tile_id(tj + 1, tj, NT), epoch, a.fail);
+    if (tid == 0) alive = ct_wait(zready + tj + 1, epoch, a.fail);
     __syncthreads();
-    if (tid < CT_B) w -= __ldcg(a.pbuf + (size_t)ct_tile_id(tj + 1, tj, NT) * 64 + tid);
+    if (tid < CT_B) zv[tid] = (tid < rv1) ? __ldcg(a.z + (tj + 1) * CT_B + tid) : 0.0;
+    __syncthreads();
+    {
+      const int c = tid & 63, kq = tid >> 6;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int r = 0; r < 16; r += 2) {
+        const int rr = kq * 16 + r;
+        s0 = fma(T0[rr * CT_LD + c], zv[rr], s0);
+        s1 = fma(T0[(rr + 1) * CT_LD + c], zv[rr + 1], s1);
+      }
+      red[kq * 64 + c] = s0 + s1;
+    }
+    __syncthreads();
+    if (tid < CT_B) w -= (red[tid] + red[64 + tid]) + (red[128 + tid] + red[192 + tid]);
   }
   if (tid < CT_B) wv[tid] = w;
   __syncthreads();
+  CT_STAMP(6);
   if (warp == 0) {
     for (int b = 7; b >= 0; --b) {
       if (lane < 8) {                                         // z_b = Linv_bb^T w_b
-        double s = 0.0;
+        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s += (k >= lane) ? Dinv[b * 64 + k * 8 + lane] * wv[8 * b + k] : 0.0;
-        zv[8 * b + lane] = s;
+        for (int k = 0; k < 8; k += 2) {
+          s0 = fma((k >= lane) ? Dinv[b * 64 + k * 8 + lane] : 0.0, wv[8 * b + k], s0);
+          s1 = fma((k + 1 >= lane) ? Dinv[b * 64 + (k + 1) * 8 + lane] : 0.0, wv[8 * b + k + 1], s1);
+        }
+        zv[8 * b + lane] = s0 + s1;
       }
       __syncwarp();
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int c = lane + 32 * half;
         if (c < 8 * b) {
-          double s = wv[c];
+          double s0 = wv[c], s1 = 0.0;
 #pragma unroll
-          for (int r = 0; r < 8; ++r) s -= T1[(8 * b + r) * CT_LD + c] * zv[8 * b + r];
-          wv[c] = s;
+          for (int r = 0; r < 8; r += 2) {
+            s0 = fma(-T1[(8 * b + r) * CT_LD + c], zv[8 * b + r], s0);
+            s1 = fma(-T1[(8 * b + r + 1) * CT_LD + c], zv[8 * b + r + 1], s1);
+          }
+          wv[c] = s0 + s1;
         }
       }
       __syncwarp();
@@ -345,6 +438,7 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_chol_tiles(CholTilesArgs a) {
     __threadfence();
     __syncwarp();
     if (lane == 0) ct_post(zready + tj, epoch);
+    CT_STAMP(7);
   }
   (void)alive;
 }

@@ -218,8 +218,9 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, (MODE == MODE_FUSED || MODE ==
 }
 
 // Unrobustified per-observation reprojection error sqrt(du^2+dv^2) (McCalib.cpp:2168-2245 averages these).
+// err_ref != nullptr: the same error with the reference's float roundings (obs_error_ref), what its output files hold.
 template <int STAGE>
-__global__ void __launch_bounds__(OBS_WARPS * 32) k_reproj_err(ObsArgs a, double* __restrict__ err) {
+__global__ void __launch_bounds__(OBS_WARPS * 32) k_reproj_err(ObsArgs a, double* __restrict__ err, float* __restrict__ err_ref) {
   typedef StageTraits<STAGE> ST;
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -239,6 +240,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) k_reproj_err(ObsArgs a, double
     for (int i = obs_begin + lane; i < obs_end; i += 32) {
       const double* p3 = a.pts + 3 * (size_t)a.pt[i];
       const double X0[3] = {p3[0], p3[1], p3[2]};
+      if (err_ref) { err_ref[i] = obs_error_ref(ctx, a.cam_model[cam], X0, a.u[i], a.v[i]); continue; }
       double ru, rv;
       obs_cost(ctx, a.cam_model[cam], X0, (double)a.u[i], (double)a.v[i], 0.0, ru, rv);
       err[i] = sqrt(ru * ru + rv * rv);

@@ -265,6 +265,33 @@ MCBA_HD double obs_cost(const double* ctx, int model, const double* X0, double u
   return hr;
 }
 
+// Reprojection error of one corner with the reference's intermediate roundings (the error outputs of MC-Calib, not its
+// cost functors): the object-pose transform is stored in cv::Point3f (transform3DPts, McCalib/src/geometrytools.cpp:
+// 328-352: t + r1 x + r2 y + r3 z evaluated in double, assigned to float), cv::projectPoints / cv::fisheye::projectPoints
+// compute in double from those float points and return cv::Point2f, and computeDistanceBetweenPoints
+// (McCalib/src/McCalib.cpp:2150-2160) subtracts the two cv::Point2f in float, squares and adds in double (std::pow
+// promotes), takes the double sqrt and stores a float.
+MCBA_HD float obs_error_ref(const double* ctx, int model, const double* X0, float u, float v) {
+  double X1[3], X3[3];
+  mat3_vec_add(ctx + CTX_RB, X0, ctx + CTX_TB, X1);
+  const double* R = ctx + CTX_RO; const double* t = ctx + CTX_TO;
+  double X2[3];
+  for (int i = 0; i < 3; ++i) X2[i] = (double)(float)(t[i] + R[3 * i] * X1[0] + R[3 * i + 1] * X1[1] + R[3 * i + 2] * X1[2]);
+  mat3_vec_add(ctx + CTX_RC, X2, ctx + CTX_TC, X3);
+  const double iz = 1.0 / X3[2];
+  Distort d;
+  distort<false>(model, ctx + CTX_IN, X3[0] * iz, X3[1] * iz, d);
+  const double* in = ctx + CTX_IN;
+  const float pu = (float)(in[0] * d.xd + in[2]), pv = (float)(in[1] * d.yd + in[3]);
+#ifdef __CUDA_ARCH__
+  const float dx = __fsub_rn(u, pu), dy = __fsub_rn(v, pv);
+#else
+  const volatile float dxv = u - pu, dyv = v - pv;
+  const float dx = dxv, dy = dyv;
+#endif
+  return (float)sqrt((double)dx * (double)dx + (double)dy * (double)dy);
+}
+
 // Residual + Jacobian of one corner. Emits loss-corrected columns through sink.put(local_col, ju, jv)
 // in the local order of Cols<STAGE>, the corrected residual as column R0, and returns 1/2 rho.
 template <int STAGE, class Sink>

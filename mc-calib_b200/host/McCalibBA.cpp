@@ -386,11 +386,12 @@ void Calibration::refineAllCameraGroupAndObjectsAndIntrinsic() {
 }
 
 // Per-corner reprojection errors of every object observation of every camera group, through libmcba
-// (mcba_reprojection_errors on the stage-3 packing: Object3D::pts_3d_ -> object pose -> camera pose -> projection),
-// evaluated in fp64; the reference rounds the transformed points to float once more (geometrytools.cpp:346-352), a
-// ~1e-4 px difference. One record per object observation, in the reference's walking order.
+// (mcba_reprojection_errors_f32 on the stage-3 packing: Object3D::pts_3d_ -> object pose -> camera pose -> projection)
+// with the reference's own intermediate roundings (transform3DPts stores cv::Point3f, geometrytools.cpp:328-352;
+// cv::projectPoints returns cv::Point2f; computeDistanceBetweenPoints stores floats, McCalib.cpp:2150-2160), so the
+// files below hold the values the reference writes. One record per object observation, in the reference's walking order.
 namespace {
-struct ObsErrors { int group, frame, camera; std::vector<double> err; };
+struct ObsErrors { int group, frame, camera, object; std::vector<float> err; };
 bool collectReprojectionErrors(Calibration& calib, std::vector<ObsErrors>& out) {
   for (const auto& it : calib.cam_group_) {
     CameraGroup& g = *it.second;
@@ -417,7 +418,7 @@ bool collectReprojectionErrors(Calibration& calib, std::vector<ObsErrors>& out) 
           }
           pk.beginBobs(cs, ps->second, (int)recs.size());   // the board slot is unused in stage 3: carry the record id through the sort
           for (size_t i = 0; i < oo->pts_id_.size(); ++i) pk.addObs(oo->pts_2d_[i], pk.board_pt_base[-1 - object->obj_id_] + oo->pts_id_[i]);
-          recs.push_back(ObsErrors{g.cam_group_idx_, frame->frame_idx_, oo->camera_id_, {}});
+          recs.push_back(ObsErrors{g.cam_group_idx_, frame->frame_idx_, oo->camera_id_, oo->object_3d_id_, {}});
         }
       }
     }
@@ -428,10 +429,10 @@ bool collectReprojectionErrors(Calibration& calib, std::vector<ObsErrors>& out) 
     std::fill(pk.bobs_board.begin(), pk.bobs_board.end(), 0);
     mcba_problem P = pk.problem();
     void* h = nullptr;
-    std::vector<double> err(pk.u.size());
+    std::vector<float> err(pk.u.size());
     mcba_params X = pk.params();
     int rc = mcba_create(&h, &P, g_cuda_device);
-    if (rc == MCBA_OK) rc = mcba_reprojection_errors(h, &X, err.data());
+    if (rc == MCBA_OK) rc = mcba_reprojection_errors_f32(h, &X, err.data());
     if (rc != MCBA_OK) { g_last_error = mcba_last_error(h); mcba_destroy(h); return false; }
     mcba_destroy(h);
     for (size_t b = 0; b + 1 < pk.bobs_ptr.size(); ++b)
@@ -448,7 +449,7 @@ double Calibration::computeAvgReprojectionError() {
   std::vector<ObsErrors> recs;
   if (!collectReprojectionErrors(*this, recs)) return std::numeric_limits<double>::quiet_NaN();
   double total = 0.0;
-  for (const auto& r : recs) { double s = 0.0; for (double e : r.err) s += e; total += s / (double)r.err.size(); }
+  for (const auto& r : recs) { double s = 0.0; for (float e : r.err) s += (double)e; total += s / (double)r.err.size(); }   // cv::mean
   return recs.empty() ? 0.0 : total / (double)recs.size();
 }
 
@@ -468,25 +469,54 @@ bool Calibration::saveReprojectionErrorToFile(const std::string& path) {
     for (size_t i = 0; i < v.size(); ++i) f << v[i] << (i + 1 < v.size() ? ", " : "");
     f << " ]\n";
   };
+  auto matf = [&](const char* indent, const char* name, const std::vector<float>& v) {
+    f << indent << name << ": !!opencv-matrix\n" << indent << "   rows: " << v.size() << "\n" << indent << "   cols: 1\n" << indent
+      << "   dt: f\n" << indent << "   data: [ ";
+    for (size_t i = 0; i < v.size(); ++i) f << v[i] << (i + 1 < v.size() ? ", " : "");
+    f << " ]\n";
+  };
+  auto empty_mat = [&](const char* indent, const char* name) {   // what cv::FileStorage writes for an empty cv::Mat
+    f << indent << name << ": !!opencv-matrix\n" << indent << "   rows: 0\n" << indent << "   cols: 0\n" << indent << "   dt: u\n" << indent << "   data: []\n";
+  };
   std::vector<double> frame_list;   // the reference never clears it between groups (McCalib.cpp:2255): kept
   size_t k = 0;
   for (const auto& it : cam_group_) {
-    f << "camera_group_" << it.second->cam_group_idx_ << ":\n";
-    while (k < recs.size() && recs[k].group == it.second->cam_group_idx_) {
-      const int frame = recs[k].frame;
+    const CameraGroup& g = *it.second;
+    f << "camera_group_" << g.cam_group_idx_ << ":\n";
+    for (const auto& it_frame : g.frames_) {                  // every frame of the group, with or without observations
+      auto frame_ptr = it_frame.second.lock();
+      if (!frame_ptr) continue;
+      const int frame = frame_ptr->frame_idx_;
       f << "   frame_" << frame << ":\n";
       frame_list.push_back(frame);
       std::vector<double> camera_list;
-      for (; k < recs.size() && recs[k].group == it.second->cam_group_idx_ && recs[k].frame == frame; ++k) {
+      for (; k < recs.size() && recs[k].group == g.cam_group_idx_ && recs[k].frame == frame; ++k) {
         camera_list.push_back(recs[k].camera);
         f << "      camera_" << recs[k].camera << ":\n         nb_pts: " << recs[k].err.size() << "\n";
-        mat("         ", "error_list", "f", recs[k].err);
+        matf("         ", "error_list", recs[k].err);
       }
-      mat("      ", "camera_list", "i", camera_list);
+      if (camera_list.empty()) empty_mat("      ", "camera_list"); else mat("      ", "camera_list", "i", camera_list);
     }
-    mat("   ", "frame_list", "i", frame_list);
+    if (frame_list.empty()) empty_mat("   ", "frame_list"); else mat("   ", "frame_list", "i", frame_list);
   }
   return true;
+}
+
+// CameraGroup::reproErrorCameraGroup (McCalib/src/CameraGroup.cpp:285-358), for every group
+// (Calibration::reproErrorAllCamGroup, McCalib.cpp:1866-1869; called at apps/calibrate/src/calibrate.cpp:66): the mean
+// error of each object observation - the reference only logs them (LOG_DEBUG); here they are returned as well.
+// float accumulation of float errors, as the reference's `float sum_error`.
+std::vector<Calibration::ObsMeanError> Calibration::reproErrorAllCamGroup() {
+  g_cuda_device = cuda_device_;
+  std::vector<ObsMeanError> out;
+  std::vector<ObsErrors> recs;
+  if (!collectReprojectionErrors(*this, recs)) return out;
+  for (const auto& r : recs) {
+    float sum_error = 0.f;
+    for (float e : r.err) sum_error += e;
+    out.push_back(ObsMeanError{r.group, r.frame, r.camera, r.object, sum_error / (float)r.err.size(), (int)r.err.size()});
+  }
+  return out;
 }
 
 // calibrated_objects_data.yml (McCalib.cpp:406-446): per object a 5 x N float matrix [X; Y; Z; board_id; pts_id].
@@ -556,7 +586,7 @@ bool Calibration::loadConfig(const std::string& yaml_path) {
 }
 
 // calibrated_cameras_data.yml (McCalib.cpp:374-404): camera_matrix, distortion_vector, distortion_type, camera_group,
-// camera_pose_matrix = inverse of relative_camera_pose_ (McCalib.cpp:398-399), as OpenCV FileStorage matrices.
+// img_width, img_height, camera_pose_matrix = inverse of relative_camera_pose_ (McCalib.cpp:398-399), as OpenCV FileStorage matrices.
 bool Calibration::saveCamerasParams(const std::string& path) const {
   std::ofstream f(path);
   if (!f) return false;
@@ -574,6 +604,7 @@ bool Calibration::saveCamerasParams(const std::string& path) const {
       f << "   distortion_vector: !!opencv-matrix\n      rows: 1\n      cols: " << nd << "\n      dt: d\n      data: [ ";
       for (int k = 0; k < nd; ++k) f << in[4 + k] << (k + 1 < nd ? ", " : " ]\n");
       f << "   distortion_type: " << cam->distortion_model_ << "\n   camera_group: " << it_g.first << "\n";
+      f << "   img_width: " << cam->im_cols_ << "\n   img_height: " << cam->im_rows_ << "\n";   // McCalib.cpp:395-396
       const Pose6 inv = invertPose(it_g.second->relative_camera_pose_.at(cam->cam_idx_));
       double R[9]; rotVecToMat(inv.data(), R);
       f << "   camera_pose_matrix: !!opencv-matrix\n      rows: 4\n      cols: 4\n      dt: d\n      data: [ ";

@@ -165,6 +165,8 @@ public:
   void refineAllCameraGroupAndObjects();               // McCalib.cpp:1876-1887
   void refineAllCameraGroupAndObjectsAndIntrinsic();   // McCalib.cpp:2348-2359
   double computeAvgReprojectionError();                // McCalib.cpp:2168-2245 (mean of per-observation means)
+  struct ObsMeanError { int group, frame, camera, object; float mean_error; int nb_pts; };
+  std::vector<ObsMeanError> reproErrorAllCamGroup();   // McCalib.cpp:1866-1869 -> CameraGroup::reproErrorCameraGroup (CameraGroup.cpp:285-358)
   bool saveCamerasParams(const std::string& path) const;   // calibrated_cameras_data.yml layout of McCalib.cpp:374-404
   bool save3DObj(const std::string& path) const;           // calibrated_objects_data.yml, McCalib.cpp:406-446
   bool save3DObjPose(const std::string& path) const;       // calibrated_objects_pose_data.yml, McCalib.cpp:452-483

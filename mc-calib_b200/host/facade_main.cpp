@@ -143,5 +143,11 @@ int main(int argc, char** argv) {
   calib.save3DObj(std::string(argv[3]) + ".objects.yml");
   calib.save3DObjPose(std::string(argv[3]) + ".objects_pose.yml");
   calib.saveReprojectionErrorToFile(std::string(argv[3]) + ".reprojection_error.yml");
+  {   // Calibration::reproErrorAllCamGroup (apps/calibrate/src/calibrate.cpp:66): mean error per object observation
+    std::ofstream ro(std::string(argv[3]) + ".repro_obs.txt");
+    ro.precision(9);
+    for (const auto& r : calib.reproErrorAllCamGroup())
+      ro << r.group << " " << r.frame << " " << r.camera << " " << r.object << " " << r.mean_error << " " << r.nb_pts << "\n";
+  }
   return 0;
 }

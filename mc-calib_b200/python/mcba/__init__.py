@@ -179,6 +179,7 @@ def load_lib():
     L.mcba_eval.argtypes = [vp, C.POINTER(mcba_params), C.POINTER(mcba_options), c_f64p, c_f64p, c_f64p]
     L.mcba_jacobian_width.argtypes = [C.c_int]
     L.mcba_reprojection_errors.argtypes = [vp, C.POINTER(mcba_params), c_f64p]
+    L.mcba_reprojection_errors_f32.argtypes = [vp, C.POINTER(mcba_params), c_f32p]
     L.mcba_destroy.argtypes = [vp]
     L.mcba_destroy.restype = None
     L.mcba_last_error.argtypes = [vp]
@@ -293,6 +294,13 @@ class Handle:
         cp = params.c()
         self._check(self.lib.mcba_reprojection_errors(self.h, C.byref(cp), _ptr(err, c_f64p)),
                     "mcba_reprojection_errors")
+        return err
+
+    def reprojection_errors_f32(self, params):
+        err = np.zeros(self.problem.n_obs, np.float32)
+        cp = params.c()
+        self._check(self.lib.mcba_reprojection_errors_f32(self.h, C.byref(cp), _ptr(err, c_f32p)),
+                    "mcba_reprojection_errors_f32")
         return err
 
     def kernel_stats(self):

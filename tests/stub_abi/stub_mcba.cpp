@@ -10,6 +10,7 @@
 
 #include "../../include/mcba_pnp.h"
 #include "../../oracle/oracle.h"
+#include "../../mc-calib_b200/csrc/mcba_math.cuh"
 
 extern "C" int pnptest_ransac(int n, const float* u, const float* v, const float* xyz, int model, const double* intr,
                               double thresh, int it, double p, int refine, int refine_it, unsigned long long seed,
@@ -98,6 +99,30 @@ int mcba_reprojection_errors(void* h, const mcba_params* params, double* err) {
   const int rc = oracle_eval(&S->P, params, &o, &cost, r.data(), nullptr, &g);
   if (rc) return rc;
   for (int64_t i = 0; i < S->P.n_obs; ++i) err[i] = std::sqrt(r[2 * i] * r[2 * i] + r[2 * i + 1] * r[2 * i + 1]);
+  return MCBA_OK;
+}
+
+// the reference-rounded error path on the host: the same MCBA_HD functions the kernel runs (mcba_math.cuh), per corner
+int mcba_reprojection_errors_f32(void* h, const mcba_params* params, float* err) {
+  Stub* S = (Stub*)h; const mcba_problem& P = S->P;
+  const bool has_cam = P.stage >= 3, has_board = P.stage == 2 || P.stage >= 4;
+  for (int64_t b = 0; b < P.n_bobs; ++b) {
+    const int cam = P.bobs_cam[b], o = P.bobs_pose[b], bd = has_board ? P.bobs_board[b] : 0;
+    const bool act_c = has_cam && !(P.cam_is_ref && P.cam_is_ref[cam]);
+    const bool act_b = has_board && !(P.board_is_ref && P.board_is_ref[bd]);
+    double pc[mcba::PREP], po[mcba::PREP], pb[mcba::PREP], ctx[mcba::CTX_SIZE];
+    double zero6[6] = {0, 0, 0, 0, 0, 0};
+    mcba::prep_block(has_cam && params->cam_pose ? params->cam_pose + 6 * cam : zero6, pc);
+    mcba::prep_block(params->pose + 6 * o, po);
+    mcba::prep_block(has_board && params->board_pose ? params->board_pose + 6 * bd : zero6, pb);
+    for (int e = 0; e < mcba::CTX_SIZE; ++e)
+      if (e < mcba::CTX_NO || e >= mcba::CTX_IN) ctx[e] = mcba::ctx_entry_a(e, pc, act_c, po, pb, act_b, params->intrinsics + 9 * cam);
+    for (int64_t i = P.bobs_ptr[b]; i < P.bobs_ptr[b + 1]; ++i) {
+      const float* p3 = P.pts_xyz + 3 * (size_t)P.pt_idx[i];
+      const double X0[3] = {p3[0], p3[1], p3[2]};
+      err[i] = mcba::obs_error_ref(ctx, P.cam_model[cam], X0, P.u[i], P.v[i]);
+    }
+  }
   return MCBA_OK;
 }
 

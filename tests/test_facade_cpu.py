@@ -69,6 +69,25 @@ def test_final_flow_packs_and_scatters_like_the_direct_call(bins, tmp_path, scen
     fs.release()
 
 
+def test_error_outputs_hold_the_reference_values(bins, tmp_path, scene):
+    """reprojection_error_data.yml, reproErrorAllCamGroup and computeAvgReprojectionError against the reference's own
+    arithmetic (OpenCV projection of float points, float stores: tests/ref_errors.py), key by key with cv::FileStorage;
+    one frame has no observation at all and must still be listed (McCalib.cpp:2262-2270 walks the group's frames)."""
+    import copy
+    import ref_errors
+    s, o = scene
+    o2 = copy.copy(o)
+    keep = o.bobs_frame != 5
+    cnt = np.diff(o.bobs_ptr)
+    obs_keep = np.repeat(keep, cnt)
+    o2.bobs_frame, o2.bobs_cam, o2.bobs_board = o.bobs_frame[keep], o.bobs_cam[keep], o.bobs_board[keep]
+    o2.bobs_ptr = np.concatenate([[0], np.cumsum(cnt[keep])]).astype(np.int64)
+    o2.u, o2.v, o2.pt_idx = o.u[obs_keep], o.v[obs_keep], o.pt_idx[obs_keep]
+    got = run(bins[0], tmp_path, s, o2, "final")
+    n_exact, n_all = ref_errors.check_error_files(got["out"], s, o2, got, o.frame_hi - o.frame_lo)
+    assert n_all == len(o2.u)
+
+
 def test_intrinsics_flow_batches_the_cameras(bins, tmp_path, scene, oracle):
     """refineIntrinsicAndPoseAllCam hands all cameras to mcba_solve_batched: per camera identical to a single solve."""
     s, o = scene
