@@ -11,6 +11,7 @@
 #include "mcba_lm.cuh"
 #include "mcba_batched.cuh"
 #include "mcba_chol_tiles.cuh"
+#include "mcba_syrk.cuh"
 
 #include <dlfcn.h>
 #include <algorithm>
@@ -77,6 +78,7 @@ struct Handle {
   int4* d_bobs = nullptr; int* d_pose_bobs_ptr = nullptr;
   int32_t* d_cam_model = nullptr; uint8_t *d_cam_is_ref = nullptr, *d_board_is_ref = nullptr;
   // stage-dependent
+  FLayout fl{};   // padded column layout of Wt / Z / ZtZ
   int Wc = 0, Wb = 0, n_f = 0, ldz = 0, n_pair = 0, n_chunks = 0, NT = 0, NE = 0, K = 0;
   int* d_pair_bobs = nullptr; PairChunk* d_chunks = nullptr; int* d_pair_chunk_ptr = nullptr;
   double *d_brec = nullptr, *d_brec_alt = nullptr, *brec_target = nullptr, *d_cost_bobs = nullptr, *d_Hoo = nullptr, *d_Wt = nullptr, *d_Z = nullptr, *d_L = nullptr;
@@ -88,6 +90,7 @@ struct Handle {
   bool obs_shared = false;   // d_u / d_v / d_pt belong to the observation cache (mcba_obs_register)
   double *d_jmat = nullptr, *d_resmat = nullptr;   // lazily allocated
   int syrk_nt = 0, syrk_tiles = 0, syrk_nsplit = 0; int64_t syrk_rows_per_split = 0;
+  unsigned* d_tile_mask = nullptr; int mask_words = 0; bool syrk_sparse = true;   // k_syrk2: which 8-column tiles of Z an e-block touches
   int chol_grid = 1, n_sm = 148;
   long long* d_chol_prof = nullptr;
   unsigned* d_ct_flags = nullptr; double *d_ct_dinv = nullptr, *d_ct_pbuf = nullptr; unsigned ct_epoch = 0; int ct_capacity = 0; long long* d_ct_prof = nullptr;   // k_chol_tiles
@@ -228,7 +231,13 @@ static int setup_stage(Handle* H, int stage) {
   H->Wc = (sd.cam ? 6 : 0) + (sd.intr ? 9 : 0);
   H->Wb = sd.board ? 6 : 0;
   H->n_f = H->n_cam * H->Wc + (sd.board ? H->n_board * H->Wb : 0);
-  H->ldz = ((H->n_f + 1 + 7) / 8) * 8;
+  {
+    const int Wcp = ((H->Wc + 7) / 8) * 8, Wbp = ((H->Wb + 7) / 8) * 8, nbd = sd.board ? H->n_board : 0;
+    const int ncm = H->Wc > 0 ? H->n_cam : 0;     // stage 2 has no per-camera f-block
+    const int rhs_col = ncm * Wcp + nbd * Wbp;
+    H->ldz = rhs_col + 8;
+    H->fl = FLayout{ncm, std::max(1, H->Wc), Wcp, nbd, std::max(1, H->Wb), Wbp, H->n_f, H->ldz, rhs_col};
+  }
   // pair lists: pair = cam * nbp + board (board = 0 when the stage has no board block)
   const int nbp = sd.board ? H->n_board : 1;
   H->n_pair = H->n_cam * nbp;
@@ -256,6 +265,7 @@ static int setup_stage(Handle* H, int stage) {
   if (dalloc(H, &H->d_cost_bobs, (size_t)H->nb)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_Hoo, np * 36) || dalloc(H, &H->d_L, np * 36)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_Wt, np * 6 * ldz) || dalloc(H, &H->d_Z, np * 6 * ldz)) return MCBA_ERR_CUDA;
+  CU(cudaMemsetAsync(H->d_Z, 0, np * 6 * ldz * sizeof(double), H->stream));   // the padding columns are never written
   if (dalloc(H, &H->d_scale_e, np * 6) || dalloc(H, &H->d_diag_e, np * 6)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_scale_f, nf) || dalloc(H, &H->d_diag_f, nf)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_FF, nf * nf) || dalloc(H, &H->d_gf, nf) || dalloc(H, &H->d_S, (nf + 1) * nf)) return MCBA_ERR_CUDA;
@@ -264,14 +274,35 @@ static int setup_stage(Handle* H, int stage) {
   H->syrk_nt = (H->ldz + SY_T - 1) / SY_T;
   H->syrk_tiles = H->syrk_nt * (H->syrk_nt + 1) / 2;
   const int64_t n_rows = 6 * (int64_t)H->n_pose;
+  static const bool syrk_dense_env = []() { const char* e = getenv("MCBA_SYRK_DENSE"); return e && atoi(e) != 0; }();
+  H->syrk_sparse = !syrk_dense_env;
   int syrk_per_sm = 1;
   CU(cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM));
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&syrk_per_sm, k_syrk, SY_THREADS, SY_SMEM);
+  CU(cudaFuncSetAttribute(k_syrk2, cudaFuncAttributeMaxDynamicSharedMemorySize, SY2_SMEM));
+  if (H->syrk_sparse) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&syrk_per_sm, k_syrk2, SY2_THREADS, SY2_SMEM);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&syrk_per_sm, k_syrk, SY_THREADS, SY_SMEM);
+  const int kq = H->syrk_sparse ? SY2_K : SY_K;              // rows per chunk: splits are whole chunks (sparse: whole e-blocks)
   int nsplit = std::max(1, (2 * std::max(1, syrk_per_sm) * H->n_sm) / H->syrk_tiles);   // about two full waves of equal CTAs
   nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(nsplit, (n_rows + 63) / 64));
-  H->syrk_rows_per_split = (((n_rows + nsplit - 1) / nsplit + SY_K - 1) / SY_K) * SY_K;
-  if (H->syrk_rows_per_split == 0) H->syrk_rows_per_split = SY_K;
+  H->syrk_rows_per_split = (((n_rows + nsplit - 1) / nsplit + kq - 1) / kq) * kq;
+  if (H->syrk_rows_per_split == 0) H->syrk_rows_per_split = kq;
   H->syrk_nsplit = (int)std::max<int64_t>(1, (n_rows + H->syrk_rows_per_split - 1) / H->syrk_rows_per_split);
+  {
+    // activity masks: e-block o touches the tiles of the cameras / boards its board observations name, and the rhs block
+    const FLayout& L = H->fl;
+    H->mask_words = (H->ldz / 8 + 31) / 32;
+    std::vector<unsigned> mask((size_t)std::max(1, H->n_pose) * H->mask_words, 0u);
+    auto set_range = [&](int o, int col0, int width) { for (int t = col0 / 8; t < (col0 + width) / 8; ++t) mask[(size_t)o * H->mask_words + (t >> 5)] |= 1u << (t & 31); };
+    for (int o = 0; o < H->n_pose; ++o) set_range(o, L.rhs_col, 8);
+    for (int b = 0; b < H->nb; ++b) {
+      const int o = H->h_bobs_pose[b];
+      if (L.n_cam > 0) set_range(o, H->h_bobs_cam[b] * L.Wcp, L.Wcp);
+      if (L.n_board > 0) set_range(o, L.n_cam * L.Wcp + H->h_bobs_board[b] * L.Wbp, L.Wbp);
+    }
+    if (dalloc(H, &H->d_tile_mask, mask.size())) return MCBA_ERR_CUDA;
+    CU(cudaMemcpyAsync(H->d_tile_mask, mask.data(), mask.size() * sizeof(unsigned), cudaMemcpyHostToDevice, H->stream));
+    CU(cudaStreamSynchronize(H->stream));
+  }
   if (dalloc(H, &H->d_syrk_partial, (size_t)H->syrk_nsplit * H->syrk_tiles * SY_T * SY_T)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_pair_partial, (size_t)H->n_chunks * H->NE)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_pair_rec, (size_t)H->n_pair * H->NE)) return MCBA_ERR_CUDA;
@@ -438,14 +469,14 @@ static int eval_assemble(Handle* H, bool first) {
     Timed t(H, KF_EASSEMBLE);
     ++H->n_launches;
     DISPATCH_STAGE(H->stage, (k_eblock_assemble<ST><<<H->n_pose, 192, 6 * H->ldz * 8, H->stream>>>(
-        H->d_bobs, H->d_pose_bobs_ptr, H->d_brec, H->n_cam, H->Wc, H->Wb, H->n_f, H->ldz, H->d_Hoo, H->d_Wt)));
+        H->d_bobs, H->d_pose_bobs_ptr, H->d_brec, H->fl, H->d_Hoo, H->d_Wt)));
     CHECK_LAUNCH();
   }
   {
     Timed t(H, KF_REDUCE);
     if (H->n_pose > 0) {
       ++H->n_launches;
-      k_eblock_grad<<<(H->n_pose + 127) / 128, 128, 0, H->stream>>>(H->d_pose[H->cur], H->d_Wt, H->d_Hoo, H->n_pose, H->n_f, H->ldz, H->d_part_e);
+      k_eblock_grad<<<(H->n_pose + 127) / 128, 128, 0, H->stream>>>(H->d_pose[H->cur], H->d_Wt, H->d_Hoo, H->n_pose, H->fl.rhs_col, H->ldz, H->d_part_e);
       CHECK_LAUNCH();
     }
     if (ov) CU(cudaStreamWaitEvent(H->stream, H->ev_join, 0));   // F^T F and F^T r are ready
@@ -537,14 +568,17 @@ static int compute_step(Handle* H, LmStep* out) {
   if (H->n_pose > 0) {
     Timed t(H, KF_EFACTOR);
     ++H->n_launches;
-    k_eblock_factor<<<H->n_pose, 128, 0, H->stream>>>(H->d_Hoo, H->d_Wt, H->d_scale_e, H->d_scale_f, H->d_diag_e, H->lm.radius, H->n_f, H->ldz, H->d_L, H->d_Z, H->d_fail);
+    k_eblock_factor<<<H->n_pose, 128, 0, H->stream>>>(H->d_Hoo, H->d_Wt, H->d_scale_e, H->d_scale_f, H->d_diag_e, H->lm.radius, H->fl, H->d_L, H->d_Z, H->d_fail);
     CHECK_LAUNCH();
   }
   {
     Timed t(H, KF_SYRK);
     dim3 grid(H->syrk_tiles, H->syrk_nsplit);
     ++H->n_launches;
-    k_syrk<<<grid, SY_THREADS, SY_SMEM, H->stream>>>(H->d_Z, 6 * (int64_t)H->n_pose, H->ldz, H->syrk_nt, H->syrk_rows_per_split, H->d_syrk_partial);
+    if (H->syrk_sparse)
+      k_syrk2<<<grid, SY2_THREADS, SY2_SMEM, H->stream>>>(H->d_Z, 6 * (int64_t)H->n_pose, H->ldz, H->syrk_nt, H->syrk_rows_per_split, H->d_tile_mask, H->mask_words, H->d_syrk_partial);
+    else
+      k_syrk<<<grid, SY_THREADS, SY_SMEM, H->stream>>>(H->d_Z, 6 * (int64_t)H->n_pose, H->ldz, H->syrk_nt, H->syrk_rows_per_split, H->d_syrk_partial);
     ++H->n_launches;
     if (H->p2p) {   // split-K sum + cross-GPU reduction in one kernel over NVLink peer memory
       P2PArgs pa;
@@ -566,7 +600,7 @@ static int compute_step(Handle* H, LmStep* out) {
     Timed t(H, KF_REDUCED);
     const int n = H->n_f * H->n_f + H->n_f;
     ++H->n_launches;
-    k_build_reduced<<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_FF, H->d_gf, H->d_ZtZ, H->d_scale_f, H->d_diag_f, H->lm.radius, H->n_f, H->ldz, H->d_S, H->d_rhs);
+    k_build_reduced<<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_FF, H->d_gf, H->d_ZtZ, H->d_scale_f, H->d_diag_f, H->lm.radius, H->fl, H->d_S, H->d_rhs);
     CHECK_LAUNCH();
   }
   if ((rc = cholesky_reduced(H))) return rc;
@@ -575,7 +609,7 @@ static int compute_step(Handle* H, LmStep* out) {
     Timed t(H, KF_BACKSUBST);
     if (H->n_pose > 0) {
       ++H->n_launches;
-      k_backsubst<<<(H->n_pose + 7) / 8, 256, 0, H->stream>>>(H->d_Z, H->d_L, H->d_zf, H->d_scale_e, H->d_diag_e, H->lm.radius, H->d_pose[H->cur], H->n_pose, H->n_f, H->ldz, H->d_pose[cand], H->d_part_e);
+      k_backsubst<<<(H->n_pose + 7) / 8, 256, 0, H->stream>>>(H->d_Z, H->d_L, H->d_zf, H->d_scale_e, H->d_diag_e, H->lm.radius, H->d_pose[H->cur], H->n_pose, H->fl, H->d_pose[cand], H->d_part_e);
     }
     ++H->n_launches;
     k_ffz<<<(H->n_f + 7) / 8, 256, 0, H->stream>>>(H->d_FF, H->d_scale_f, H->d_zf, H->n_f, H->d_hz);
@@ -880,7 +914,7 @@ void mcba_destroy(void* h) {
   dfree(H, &H->d_FF); dfree(H, &H->d_gf); dfree(H, &H->d_S); dfree(H, &H->d_rhs); dfree(H, &H->d_zf); dfree(H, &H->d_ZtZ); dfree(H, &H->d_hz);
   dfree(H, &H->d_syrk_partial); dfree(H, &H->d_pair_partial); dfree(H, &H->d_pair_rec); dfree(H, &H->d_part_e);
   dfree(H, &H->d_red_scratch); dfree(H, &H->d_scalars); dfree(H, &H->d_gather); dfree(H, &H->d_fail);
-  dfree(H, &H->d_jmat); dfree(H, &H->d_resmat); dfree(H, &H->d_ct_flags); dfree(H, &H->d_ct_dinv); dfree(H, &H->d_ct_pbuf);
+  dfree(H, &H->d_jmat); dfree(H, &H->d_resmat); dfree(H, &H->d_ct_flags); dfree(H, &H->d_ct_dinv); dfree(H, &H->d_ct_pbuf); dfree(H, &H->d_tile_mask);
   dfree(H, &H->d_cam_ptr); dfree(H, &H->d_lm); dfree(H, &H->d_gate_jac); dfree(H, &H->d_active); dfree(H, &H->d_cam_fail); dfree(H, &H->d_n_active);
   dfree(H, &H->d_cam_sc); dfree(H, &H->d_cam_cost);
   for (int w = 0; w < 2; ++w) { dfree(H, &H->d_cam_pose[w]); dfree(H, &H->d_pose[w]); dfree(H, &H->d_board[w]); dfree(H, &H->d_intr[w]); }

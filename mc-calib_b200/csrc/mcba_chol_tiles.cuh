@@ -164,6 +164,8 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_chol_tiles(CholTilesArgs a) {
     // takes the NEXT diagonal block first and goes straight on to factor it while the other warps finish the update.
     double* F8 = red;                                         // [8][8] unit-lower entries t[r][k] (k < r); diagonal: 1/sqrt(d)
     for (int e = tid; e < CT_B * CT_B; e += CT_THREADS) { const int r = e >> 6, c = e & 63; if (c > r) T1[r * CT_LD + c] = 0.0; }
+    long long cy_b1 = 0, cy_w1 = 0, cy_b2 = 0, cy_w2 = 0, cy_t = clock64();
+#define CY(acc) do { const long long tn = clock64(); acc += tn - cy_t; cy_t = tn; } while (0)
     for (int c0 = 0; c0 < CT_B; c0 += 8) {
       if (warp == 0) {
         if (c0 > 0) {                                         // next diagonal block's share of the previous trailing update
@@ -232,7 +234,9 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_chol_tiles(CholTilesArgs a) {
           for (int r = 0; r < 8; ++r) Dinv[(c0 >> 3) * 64 + r * 8 + cc] = y[r];
         }
       }
+      CY(cy_b1);
       __syncthreads();
+      CY(cy_w1);
       if (tid < CT_B - c0) {                                  // (b2) row i of the sub-panel: v_c = D_ic - sum_k v_k t_ck, L_ic = v_c / sqrt(d_c)
         const int i = c0 + tid;
         double v[8];
@@ -246,7 +250,9 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_chol_tiles(CholTilesArgs a) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) T1[i * CT_LD + c0 + c] = (c0 + c <= i) ? v[c] * F8[c * 9] : 0.0;
       }
+      CY(cy_b2);
       __syncthreads();
+      CY(cy_w2);
       // (c) trailing update on the 8x8 tiles below/right; tile (0,0) - the next diagonal block - is warp 0's, above
       const int m8 = 7 - (c0 >> 3);
       const int ntile = m8 * (m8 + 1) / 2;
@@ -265,6 +271,7 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_chol_tiles(CholTilesArgs a) {
       // no barrier here: warp 0 loops straight into the next diagonal block; the barrier after (b1) covers the update
     }
     __syncthreads();
+    if (a.prof && tid == 0) { a.prof[(size_t)my_tile * 8 + 4] = cy_b1 * 100000 + cy_w1; a.prof[(size_t)my_tile * 8 + 5] = cy_b2 * 100000 + cy_w2; }
     CT_STAMP(2);
     // publish L(j,j) (in place in S) and the 8x8 inverses
     for (int e = tid; e < CT_B * CT_B; e += CT_THREADS) {

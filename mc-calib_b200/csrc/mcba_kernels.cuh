@@ -279,16 +279,31 @@ __global__ void __launch_bounds__(RED_T) k_reduce_rows(const double* __restrict_
   }
 }
 
+// Column layout of the e-block row blocks Wt / Z and of Z^T Z: every camera block is padded to a multiple of 8 columns
+// (Wcp), every board block to Wbp, and the right-hand side has an 8-column block of its own, so that the 8-wide DMMA
+// tiles of the Schur SYRK never straddle two parameter blocks: a tile is then structurally zero for every frame that
+// does not see its camera / board, and the SYRK skips it (k_syrk, activity masks). F^T F, S, z_f stay unpadded.
+struct FLayout {
+  int n_cam, Wc, Wcp, n_board, Wb, Wbp, n_f, ldz, rhs_col;
+  __host__ __device__ int pcol(int j) const {
+    const int ncw = n_cam * Wc;
+    if (j < ncw) { const int c = j / Wc; return c * Wcp + (j - c * Wc); }
+    j -= ncw;
+    const int b = j / Wb;
+    return n_cam * Wcp + b * Wbp + (j - b * Wb);
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // K2a: per e-block sums over its board observations (fixed order): Hoo (6x6 full), and the dense row block
 // Wt[o] = [E^T F (6 x n_f) | E^T r] with leading dimension ldz.
 template <int STAGE>
 __global__ void __launch_bounds__(192) k_eblock_assemble(const int4* __restrict__ bobs, const int* __restrict__ pose_bobs_ptr,
-                                                         const double* __restrict__ brec, int n_cam, int Wc, int Wb,
-                                                         int n_f, int ldz, double* __restrict__ Hoo,
+                                                         const double* __restrict__ brec, FLayout L, double* __restrict__ Hoo,
                                                          double* __restrict__ Wt) {
   typedef Cols<STAGE> C;
   extern __shared__ double W[];   // [6][ldz]
+  const int ldz = L.ldz;
   const int o = blockIdx.x, tid = threadIdx.x;
   for (int e = tid; e < 6 * ldz; e += blockDim.x) W[e] = 0.0;
   __syncthreads();
@@ -305,7 +320,7 @@ __global__ void __launch_bounds__(192) k_eblock_assemble(const int4* __restrict_
       for (int u = 0; u < EA_U; ++u)
         if (b + u < b1) {
           const int4 rec = bobs[b + u];
-          gc[u] = (j < C::B0) ? rec.y * Wc + j : n_cam * Wc + rec.w * Wb + (j - C::B0);
+          gc[u] = (j < C::B0) ? rec.y * L.Wcp + j : L.n_cam * L.Wcp + rec.w * L.Wbp + (j - C::B0);
           v[u] = brec[(size_t)(b + u) * C::NCOMP + off];
         }
 #pragma unroll
@@ -326,7 +341,7 @@ __global__ void __launch_bounds__(192) k_eblock_assemble(const int4* __restrict_
       for (int u = 0; u < EA_U; ++u) if (b + u < b1) s += v[u];
     }
     if (e < 36) Hoo[(size_t)o * 36 + e] = s;
-    else W[(e - 36) * ldz + n_f] = s;
+    else W[(e - 36) * ldz + L.rhs_col] = s;
   }
   __syncthreads();
   double* dst = Wt + (size_t)o * 6 * ldz;
@@ -453,10 +468,11 @@ __global__ void k_eblock_grad(const double* __restrict__ pose, const double* __r
 // copy of the 6x6 in registers (cheaper than a barrier), then handles columns j = tid, tid+T, ...
 __global__ void __launch_bounds__(128) k_eblock_factor(const double* __restrict__ Hoo, const double* __restrict__ Wt,
                                                        const double* __restrict__ scale_e, const double* __restrict__ scale_f,
-                                                       const double* __restrict__ diag_e, double radius, int n_f, int ldz,
+                                                       const double* __restrict__ diag_e, double radius, FLayout Lo,
                                                        double* __restrict__ Lout, double* __restrict__ Z,
                                                        int* __restrict__ fail) {
   const int o = blockIdx.x;
+  const int n_f = Lo.n_f, ldz = Lo.ldz;
   double L[36], se[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) se[k] = scale_e[(size_t)o * 6 + k];
@@ -474,23 +490,25 @@ __global__ void __launch_bounds__(128) k_eblock_factor(const double* __restrict_
   }
   const double* W = Wt + (size_t)o * 6 * ldz;
   double* Zo = Z + (size_t)o * 6 * ldz;
+  // one real column (f index j, then the rhs as j = n_f) per thread and pass; the padding columns of Z stay zero
   constexpr int EF_U = 4;   // columns per thread in flight (their loads are issued before the first substitution)
-  for (int j0 = threadIdx.x; j0 < ldz; j0 += EF_U * blockDim.x) {
-    double w[EF_U][6];
+  for (int j0 = threadIdx.x; j0 <= n_f; j0 += EF_U * blockDim.x) {
+    double w[EF_U][6]; int pc[EF_U];
 #pragma unroll
     for (int u = 0; u < EF_U; ++u) {
       const int j = j0 + u * blockDim.x;
+      pc[u] = (j < n_f) ? Lo.pcol(j) : Lo.rhs_col;
       const double sf = (j < n_f) ? scale_f[j] : 1.0;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) w[u][k] = (j <= n_f) ? se[k] * W[k * ldz + j] * sf : 0.0;
+      for (int k = 0; k < 6; ++k) w[u][k] = (j <= n_f) ? se[k] * W[k * ldz + pc[u]] * sf : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < EF_U; ++u) {
       const int j = j0 + u * blockDim.x;
-      if (j < ldz) {
+      if (j <= n_f) {
         if (ok) chol6_fwd(L, w[u]);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) Zo[k * ldz + j] = ok ? w[u][k] : 0.0;
+        for (int k = 0; k < 6; ++k) Zo[k * ldz + pc[u]] = ok ? w[u][k] : 0.0;
       }
     }
   }
@@ -696,18 +714,19 @@ __global__ void __launch_bounds__(256) k_syrk_sum_p2p(P2PArgs a) {
 // K2e: reduced system. S = s_f F^T F s_f + D_f^2 - Z^T Z (full symmetric, n_f x n_f, ld n_f); rhs = s_f g_f - Z^T y.
 __global__ void k_build_reduced(const double* __restrict__ FF, const double* __restrict__ gf,
                                 const double* __restrict__ ZtZ, const double* __restrict__ scale_f,
-                                const double* __restrict__ diag_f, double radius, int n_f, int ldz,
+                                const double* __restrict__ diag_f, double radius, FLayout L,
                                 double* __restrict__ S, double* __restrict__ rhs) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_f = L.n_f, ldz = L.ldz;
   if (idx < n_f * n_f) {
     const int i = idx / n_f, j = idx % n_f;
     const int lo = min(i, j), hi = max(i, j);
-    double s = scale_f[i] * FF[idx] * scale_f[j] - ZtZ[(size_t)lo * ldz + hi];
+    double s = scale_f[i] * FF[idx] * scale_f[j] - ZtZ[(size_t)L.pcol(lo) * ldz + L.pcol(hi)];
     if (i == j) s += diag_f[i] / radius;
     S[idx] = s;
   } else if (idx < n_f * n_f + n_f) {
     const int i = idx - n_f * n_f;
-    const double v = scale_f[i] * gf[i] - ZtZ[(size_t)i * ldz + n_f];
+    const double v = scale_f[i] * gf[i] - ZtZ[(size_t)L.pcol(i) * ldz + L.rhs_col];
     rhs[i] = v;
     S[(size_t)n_f * n_f + i] = v;   // extra row n_f: the factorisation turns it into L^-1 rhs
   }
@@ -1059,8 +1078,9 @@ __global__ void __launch_bounds__(CC_THREADS) k_chol_coop(double* __restrict__ S
 __global__ void __launch_bounds__(256) k_backsubst(const double* __restrict__ Z, const double* __restrict__ Lall,
                                                    const double* __restrict__ zf, const double* __restrict__ scale_e,
                                                    const double* __restrict__ diag_e, double radius,
-                                                   const double* __restrict__ pose, int n_pose, int n_f, int ldz,
+                                                   const double* __restrict__ pose, int n_pose, FLayout Lo,
                                                    double* __restrict__ pose_cand, double* __restrict__ part) {
+  const int n_f = Lo.n_f, ldz = Lo.ldz;
   // one warp per e-block: q = Z_o z_f by lanes striding the columns (coalesced), xor-shuffle tree (fixed order)
   const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (o >= n_pose) return;
@@ -1068,8 +1088,9 @@ __global__ void __launch_bounds__(256) k_backsubst(const double* __restrict__ Z,
   double q[6] = {0, 0, 0, 0, 0, 0};
   for (int j = lane; j < n_f; j += 32) {
     const double zj = zf[j];
+    const int pc = Lo.pcol(j);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) q[k] += Zo[k * ldz + j] * zj;
+    for (int k = 0; k < 6; ++k) q[k] += Zo[k * ldz + pc] * zj;
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
@@ -1085,7 +1106,7 @@ __global__ void __launch_bounds__(256) k_backsubst(const double* __restrict__ Z,
   double py = 0, pp = 0, pq = 0;
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
-    const double y = Zo[k * ldz + n_f];
+    const double y = Zo[k * ldz + Lo.rhs_col];
     p[k] = y - q[k]; zo[k] = p[k]; py += p[k] * y; pp += p[k] * p[k]; pq += p[k] * q[k];
   }
   chol6_bwd(L, zo);

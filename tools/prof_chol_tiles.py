@@ -31,5 +31,7 @@ for j in range(NT):
     print(line)
 r = t[tid(NT, 0)]
 print("rhs tile col 0:", [round(rel(x), 1) for x in r[:6]])
+d = t[tid(3, 3)]
+print("diag tile 3 potrf cycles: b1 %d  wait1 %d  b2 %d  wait2 %d" % (d[4] // 100000, d[4] % 100000, d[5] // 100000, d[5] % 100000))
 print("first stamp spread (us):", (t[t[:, 0] > 0, 0].max() - t0) / 1e3)
 h.close()
