@@ -90,7 +90,7 @@ struct Handle {
   bool obs_shared = false;   // d_u / d_v / d_pt belong to the observation cache (mcba_obs_register)
   double *d_jmat = nullptr, *d_resmat = nullptr;   // lazily allocated
   int syrk_nt = 0, syrk_tiles = 0, syrk_nsplit = 0; int64_t syrk_rows_per_split = 0;
-  unsigned* d_tile_mask = nullptr; int mask_words = 0; bool syrk_sparse = true;   // k_syrk2: which 8-column tiles of Z an e-block touches
+  unsigned* d_tile_mask = nullptr; int mask_words = 0; bool syrk_sparse = false, syrk_tma = true;   // k_syrk2: which 8-column tiles of Z an e-block touches
   int chol_grid = 1, n_sm = 148;
   long long* d_chol_prof = nullptr;
   unsigned* d_ct_flags = nullptr; double *d_ct_dinv = nullptr, *d_ct_pbuf = nullptr; unsigned ct_epoch = 0; int ct_capacity = 0; long long* d_ct_prof = nullptr;   // k_chol_tiles
@@ -232,10 +232,15 @@ static int setup_stage(Handle* H, int stage) {
   H->Wb = sd.board ? 6 : 0;
   H->n_f = H->n_cam * H->Wc + (sd.board ? H->n_board * H->Wb : 0);
   {
-    const int Wcp = ((H->Wc + 7) / 8) * 8, Wbp = ((H->Wb + 7) / 8) * 8, nbd = sd.board ? H->n_board : 0;
+    // MCBA_SYRK_SPARSE=1: block-sparse Schur SYRK on a layout padded to the DMMA tiles (measured slower than the dense
+    // kernel on the dome: DESIGN.md); default: dense, unpadded
+    static const bool sparse_env = []() { const char* e = getenv("MCBA_SYRK_SPARSE"); return e && atoi(e) != 0; }();
+    H->syrk_sparse = sparse_env;
+    const int nbd = sd.board ? H->n_board : 0;
+    const int Wcp = H->syrk_sparse ? ((H->Wc + 7) / 8) * 8 : H->Wc, Wbp = H->syrk_sparse ? ((H->Wb + 7) / 8) * 8 : H->Wb;
     const int ncm = H->Wc > 0 ? H->n_cam : 0;     // stage 2 has no per-camera f-block
     const int rhs_col = ncm * Wcp + nbd * Wbp;
-    H->ldz = rhs_col + 8;
+    H->ldz = H->syrk_sparse ? rhs_col + 8 : ((rhs_col + 1 + 7) / 8) * 8;
     H->fl = FLayout{ncm, std::max(1, H->Wc), Wcp, nbd, std::max(1, H->Wb), Wbp, H->n_f, H->ldz, rhs_col};
   }
   // pair lists: pair = cam * nbp + board (board = 0 when the stage has no board block)
@@ -265,7 +270,8 @@ static int setup_stage(Handle* H, int stage) {
   if (dalloc(H, &H->d_cost_bobs, (size_t)H->nb)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_Hoo, np * 36) || dalloc(H, &H->d_L, np * 36)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_Wt, np * 6 * ldz) || dalloc(H, &H->d_Z, np * 6 * ldz)) return MCBA_ERR_CUDA;
-  CU(cudaMemsetAsync(H->d_Z, 0, np * 6 * ldz * sizeof(double), H->stream));   // the padding columns are never written
+  CU(cudaMemsetAsync(H->d_Z, 0, np * 6 * ldz * sizeof(double), H->stream));   // padding columns and unobserved blocks are never written
+  CU(cudaMemsetAsync(H->d_Wt, 0, np * 6 * ldz * sizeof(double), H->stream));
   if (dalloc(H, &H->d_scale_e, np * 6) || dalloc(H, &H->d_diag_e, np * 6)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_scale_f, nf) || dalloc(H, &H->d_diag_f, nf)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_FF, nf * nf) || dalloc(H, &H->d_gf, nf) || dalloc(H, &H->d_S, (nf + 1) * nf)) return MCBA_ERR_CUDA;
@@ -274,20 +280,21 @@ static int setup_stage(Handle* H, int stage) {
   H->syrk_nt = (H->ldz + SY_T - 1) / SY_T;
   H->syrk_tiles = H->syrk_nt * (H->syrk_nt + 1) / 2;
   const int64_t n_rows = 6 * (int64_t)H->n_pose;
-  static const bool syrk_dense_env = []() { const char* e = getenv("MCBA_SYRK_DENSE"); return e && atoi(e) != 0; }();
-  H->syrk_sparse = !syrk_dense_env;
+  static const bool syrk_cpasync_env = []() { const char* e = getenv("MCBA_SYRK_CPASYNC"); return e && atoi(e) != 0; }();
+  H->syrk_tma = !syrk_cpasync_env || H->syrk_sparse;         // bulk-copy (TMA) pipeline by default; MCBA_SYRK_CPASYNC=1: round-1 kernel
   int syrk_per_sm = 1;
   CU(cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM));
-  CU(cudaFuncSetAttribute(k_syrk2, cudaFuncAttributeMaxDynamicSharedMemorySize, SY2_SMEM));
-  if (H->syrk_sparse) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&syrk_per_sm, k_syrk2, SY2_THREADS, SY2_SMEM);
+  CU(cudaFuncSetAttribute(k_syrk2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SY2_SMEM));
+  CU(cudaFuncSetAttribute(k_syrk2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SY2_SMEM));
+  if (H->syrk_tma) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&syrk_per_sm, k_syrk2<false>, SY2_THREADS, SY2_SMEM);
   else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&syrk_per_sm, k_syrk, SY_THREADS, SY_SMEM);
-  const int kq = H->syrk_sparse ? SY2_K : SY_K;              // rows per chunk: splits are whole chunks (sparse: whole e-blocks)
+  const int kq = H->syrk_tma ? SY2_K : SY_K;                 // rows per chunk: splits are whole chunks (whole e-blocks for k_syrk2)
   int nsplit = std::max(1, (2 * std::max(1, syrk_per_sm) * H->n_sm) / H->syrk_tiles);   // about two full waves of equal CTAs
   nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(nsplit, (n_rows + 63) / 64));
   H->syrk_rows_per_split = (((n_rows + nsplit - 1) / nsplit + kq - 1) / kq) * kq;
   if (H->syrk_rows_per_split == 0) H->syrk_rows_per_split = kq;
   H->syrk_nsplit = (int)std::max<int64_t>(1, (n_rows + H->syrk_rows_per_split - 1) / H->syrk_rows_per_split);
-  {
+  if (H->syrk_sparse) {
     // activity masks: e-block o touches the tiles of the cameras / boards its board observations name, and the rhs block
     const FLayout& L = H->fl;
     H->mask_words = (H->ldz / 8 + 31) / 32;
@@ -302,6 +309,8 @@ static int setup_stage(Handle* H, int stage) {
     if (dalloc(H, &H->d_tile_mask, mask.size())) return MCBA_ERR_CUDA;
     CU(cudaMemcpyAsync(H->d_tile_mask, mask.data(), mask.size() * sizeof(unsigned), cudaMemcpyHostToDevice, H->stream));
     CU(cudaStreamSynchronize(H->stream));
+  } else {
+    dfree(H, &H->d_tile_mask); H->mask_words = 0;
   }
   if (dalloc(H, &H->d_syrk_partial, (size_t)H->syrk_nsplit * H->syrk_tiles * SY_T * SY_T)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_pair_partial, (size_t)H->n_chunks * H->NE)) return MCBA_ERR_CUDA;
@@ -469,7 +478,7 @@ static int eval_assemble(Handle* H, bool first) {
     Timed t(H, KF_EASSEMBLE);
     ++H->n_launches;
     DISPATCH_STAGE(H->stage, (k_eblock_assemble<ST><<<H->n_pose, 192, 6 * H->ldz * 8, H->stream>>>(
-        H->d_bobs, H->d_pose_bobs_ptr, H->d_brec, H->fl, H->d_Hoo, H->d_Wt)));
+        H->d_bobs, H->d_pose_bobs_ptr, H->d_brec, H->fl, H->d_tile_mask, H->mask_words, H->d_Hoo, H->d_Wt)));
     CHECK_LAUNCH();
   }
   {
@@ -528,8 +537,8 @@ static int cholesky_reduced(Handle* H) {
   if (const char* once = getenv("MCBA_CHOL_TILES_ONCE")) tiles_off = atoi(once) == 0;   // mcba_debug_cholesky
   if (!tiles_off && n > 0 && ct_num_tiles(n) <= H->ct_capacity && (n + CT_B - 1) / CT_B <= CT_MAXNT) {
     static const bool ct_prof = getenv("MCBA_CHOL_PROF") != nullptr;
-    if (ct_prof && !H->d_ct_prof) { CU(cudaMalloc((void**)&H->d_ct_prof, (size_t)CT_MAXT * 8 * sizeof(long long))); }
-    if (ct_prof) CU(cudaMemsetAsync(H->d_ct_prof, 0, (size_t)CT_MAXT * 8 * sizeof(long long), H->stream));
+    if (ct_prof && !H->d_ct_prof) { CU(cudaMalloc((void**)&H->d_ct_prof, (size_t)CT_MAXT * 16 * sizeof(long long))); }
+    if (ct_prof) CU(cudaMemsetAsync(H->d_ct_prof, 0, (size_t)CT_MAXT * 16 * sizeof(long long), H->stream));
     CholTilesArgs a{H->d_S, n, H->d_zf, H->d_fail, H->d_ct_flags, ++H->ct_epoch, H->d_ct_dinv, H->d_ct_pbuf, H->d_ct_prof};
     void* args[] = {&a};
     ++H->n_launches;
@@ -568,7 +577,7 @@ static int compute_step(Handle* H, LmStep* out) {
   if (H->n_pose > 0) {
     Timed t(H, KF_EFACTOR);
     ++H->n_launches;
-    k_eblock_factor<<<H->n_pose, 128, 0, H->stream>>>(H->d_Hoo, H->d_Wt, H->d_scale_e, H->d_scale_f, H->d_diag_e, H->lm.radius, H->fl, H->d_L, H->d_Z, H->d_fail);
+    k_eblock_factor<<<H->n_pose, 128, 0, H->stream>>>(H->d_Hoo, H->d_Wt, H->d_scale_e, H->d_scale_f, H->d_diag_e, H->lm.radius, H->fl, H->d_tile_mask, H->mask_words, H->d_L, H->d_Z, H->d_fail);
     CHECK_LAUNCH();
   }
   {
@@ -576,7 +585,9 @@ static int compute_step(Handle* H, LmStep* out) {
     dim3 grid(H->syrk_tiles, H->syrk_nsplit);
     ++H->n_launches;
     if (H->syrk_sparse)
-      k_syrk2<<<grid, SY2_THREADS, SY2_SMEM, H->stream>>>(H->d_Z, 6 * (int64_t)H->n_pose, H->ldz, H->syrk_nt, H->syrk_rows_per_split, H->d_tile_mask, H->mask_words, H->d_syrk_partial);
+      k_syrk2<true><<<grid, SY2_THREADS, SY2_SMEM, H->stream>>>(H->d_Z, 6 * (int64_t)H->n_pose, H->ldz, H->syrk_nt, H->syrk_rows_per_split, H->d_tile_mask, H->mask_words, H->d_syrk_partial);
+    else if (H->syrk_tma)
+      k_syrk2<false><<<grid, SY2_THREADS, SY2_SMEM, H->stream>>>(H->d_Z, 6 * (int64_t)H->n_pose, H->ldz, H->syrk_nt, H->syrk_rows_per_split, nullptr, 0, H->d_syrk_partial);
     else
       k_syrk<<<grid, SY_THREADS, SY_SMEM, H->stream>>>(H->d_Z, 6 * (int64_t)H->n_pose, H->ldz, H->syrk_nt, H->syrk_rows_per_split, H->d_syrk_partial);
     ++H->n_launches;
@@ -609,7 +620,7 @@ static int compute_step(Handle* H, LmStep* out) {
     Timed t(H, KF_BACKSUBST);
     if (H->n_pose > 0) {
       ++H->n_launches;
-      k_backsubst<<<(H->n_pose + 7) / 8, 256, 0, H->stream>>>(H->d_Z, H->d_L, H->d_zf, H->d_scale_e, H->d_diag_e, H->lm.radius, H->d_pose[H->cur], H->n_pose, H->fl, H->d_pose[cand], H->d_part_e);
+      k_backsubst<<<(H->n_pose + 7) / 8, 256, 0, H->stream>>>(H->d_Z, H->d_L, H->d_zf, H->d_scale_e, H->d_diag_e, H->lm.radius, H->d_pose[H->cur], H->n_pose, H->fl, H->d_tile_mask, H->mask_words, H->d_pose[cand], H->d_part_e);
     }
     ++H->n_launches;
     k_ffz<<<(H->n_f + 7) / 8, 256, 0, H->stream>>>(H->d_FF, H->d_scale_f, H->d_zf, H->n_f, H->d_hz);
@@ -1417,7 +1428,7 @@ int mcba_debug_fetch(void* h, const char* name, double* out, int64_t cap, int64_
   else if (s == "diag_e") { src = H->d_diag_e; n = np * 6; } else if (s == "diag_f") { src = H->d_diag_f; n = nf; }
   else if (s == "chol_prof") {   // %globaltimer stamps of the last k_chol_tiles launch, as doubles (ns)
     if (!H->d_ct_prof) { H->err = "run with MCBA_CHOL_PROF=1"; return MCBA_ERR_INVALID; }
-    n = (int64_t)CT_MAXT * 8;
+    n = (int64_t)CT_MAXT * 16;
     if (n_out) *n_out = n;
     if (out) { std::vector<long long> t(n); CU(cudaStreamSynchronize(H->stream)); CU(cudaMemcpy(t.data(), H->d_ct_prof, n * sizeof(long long), cudaMemcpyDeviceToHost)); for (int64_t i = 0; i < std::min(n, cap); ++i) out[i] = (double)t[i]; }
     return MCBA_OK;

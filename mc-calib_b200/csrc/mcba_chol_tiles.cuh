@@ -50,16 +50,7 @@ __device__ __forceinline__ bool ct_wait(const unsigned* f, unsigned epoch, int* 
   }
 }
 __device__ __forceinline__ long long ct_now() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-#define CT_STAMP(k) do { if (a.prof && tid == 0) a.prof[(size_t)my_tile * 8 + (k)] = ct_now(); } while (0)
-// 1/d for a positive, comfortably normal d: hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps; the pivot
-// recurrence of the diagonal-block factorisation hangs on this latency (64 dependent pivots per tile).
-__device__ __forceinline__ double ct_rcp(double d) {
-  double x;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
-  double e = fma(-d, x, 1.0); x = fma(x, e, x);
-  e = fma(-d, x, 1.0); x = fma(x, e, x);
-  return x;
-}
+#define CT_STAMP(k) do { if (a.prof && tid == 0) a.prof[(size_t)my_tile * 16 + (k)] = ct_now(); } while (0)
 __host__ __device__ inline int ct_tile_id(int i, int j, int NT) { return j * (NT + 1) - j * (j - 1) / 2 + (i - j); }
 __host__ __device__ inline int ct_num_tiles(int n) { const int NT = (n + CT_B - 1) / CT_B; return NT * (NT + 3) / 2; }
 
@@ -156,122 +147,82 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_chol_tiles(CholTilesArgs a) {
       }
   __syncthreads();
   if (is_diag) {
-    // ---- potrf of the 64x64 block: D = T0 (lower part), factor -> T1, right-looking in 8-wide sub-panels.
-    // Per sub-panel: (b1) warp 0 factors the 8x8 diagonal block in registers, every lane redundantly (no shuffles on the
-    // pivot chain), in the square-root-free form: pivot recurrence d_{j+1} = a_{j+1,j+1} - a_{j+1,j}^2 / d_j with a
-    // Newton reciprocal (one MUFU + 4 DFMA) as the only long-latency link; lanes 8..15 turn it into a column of the
-    // block's inverse; (b2) one thread per row below solves its 8 entries; (c) DMMA trailing update, where warp 0
-    // takes the NEXT diagonal block first and goes straight on to factor it while the other warps finish the update.
-    double* F8 = red;                                         // [8][8] unit-lower entries t[r][k] (k < r); diagonal: 1/sqrt(d)
-    for (int e = tid; e < CT_B * CT_B; e += CT_THREADS) { const int r = e >> 6, c = e & 63; if (c > r) T1[r * CT_LD + c] = 0.0; }
-    long long cy_b1 = 0, cy_w1 = 0, cy_b2 = 0, cy_w2 = 0, cy_t = clock64();
-#define CY(acc) do { const long long tn = clock64(); acc += tn - cy_t; cy_t = tn; } while (0)
+    // ---- potrf of the 64x64 block: D = T0 (lower part), factor -> T1, right-looking in 8-wide sub-panels
     for (int c0 = 0; c0 < CT_B; c0 += 8) {
-      if (warp == 0) {
-        if (c0 > 0) {                                         // next diagonal block's share of the previous trailing update
-          double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-          for (int s2 = 0; s2 < 2; ++s2) {
-            const double f = T1[(c0 + g) * CT_LD + c0 - 8 + 4 * s2 + q];
-            dmma884(d0, d1, f, f);
-          }
-          double2* p = reinterpret_cast<double2*>(T0 + (c0 + g) * CT_LD + c0 + 2 * q);
-          double2 cur = *p; cur.x -= d0; cur.y -= d1; *p = cur;
-          __syncwarp();
-        }
-        double m[8][8], dd[8], si[8];
+      if (tid < CT_B - c0 || (tid >= 64 && tid < 72)) {
+        double l[8][8], inv[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r)
 #pragma unroll
-          for (int c = 0; c <= r; ++c) m[r][c] = T0[(c0 + r) * CT_LD + c0 + c];
+          for (int c = 0; c <= r; ++c) l[r][c] = T0[(c0 + r) * CT_LD + c0 + c];
         bool bad = false;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const double d = m[j][j];
-          dd[j] = d;
+          const double d = l[j][j];
           const bool b = !(d > 0.0) || !(d < DBL_MAX);
           bad = bad || b;
-          const bool fast = d > 1e-280 && d < 1e280;
-          double tr[8];
-          if (fast) {
-            const double rj = ct_rcp(d);
-            if (j < 7) m[j + 1][j + 1] = fma(-(m[j + 1][j] * m[j + 1][j]), rj, m[j + 1][j + 1]);   // next pivot first
+          inv[j] = b ? 1.0 : rsqrt(d);
+          l[j][j] = d * inv[j];
 #pragma unroll
-            for (int r = j + 1; r < 8; ++r) tr[r] = m[r][j] * rj;
-          } else {                                            // tiny / huge / invalid pivot: through 1/sqrt(d), no overflow of 1/d
-            const double sj = b ? 1.0 : rsqrt(d);
-#pragma unroll
-            for (int r = j + 1; r < 8; ++r) tr[r] = (m[r][j] * sj) * sj;
-            if (j < 7) m[j + 1][j + 1] = fma(-tr[j + 1], m[j + 1][j], m[j + 1][j + 1]);
-          }
+          for (int r = j + 1; r < 8; ++r) l[r][j] *= inv[j];
 #pragma unroll
           for (int r = j + 1; r < 8; ++r)
 #pragma unroll
-            for (int c = j + 1; c <= r; ++c)
-              if (!(r == j + 1 && c == j + 1)) m[r][c] = fma(-tr[r], m[c][j], m[r][c]);
-#pragma unroll
-          for (int r = j + 1; r < 8; ++r) m[r][j] = tr[r];
+            for (int c = j + 1; c <= r; ++c) l[r][c] -= l[r][j] * l[c][j];
         }
+        if (tid < CT_B - c0) {
+          const int i = c0 + tid;
+          double x[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { const bool b = !(dd[j] > 0.0) || !(dd[j] < DBL_MAX); si[j] = b ? 1.0 : rsqrt(dd[j]); }
-        if (lane == 0) {
+          for (int c = 0; c < 8; ++c) {
+            double t = T0[i * CT_LD + c0 + c];
 #pragma unroll
-          for (int r = 0; r < 8; ++r)
+            for (int k = 0; k < c; ++k) t -= x[k] * l[c][k];
+            x[c] = (c0 + c <= i) ? t * inv[c] : 0.0;
+          }
 #pragma unroll
-            for (int c = 0; c <= r; ++c) F8[r * 8 + c] = (c == r) ? si[r] : m[r][c];
-          if (bad) atomicExch(a.fail, 1);
-        } else if (lane >= 8 && lane < 16) {
-          const int cc = lane - 8;                            // column cc of the inverse of the 8x8 Cholesky block
+          for (int c = 0; c < 8; ++c) T1[i * CT_LD + c0 + c] = x[c];
+          if (tid == 0) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) invd[c0 + c] = inv[c];
+            if (bad) atomicExch(a.fail, 1);
+          }
+        } else {
+          const int cc = tid - 64;                            // column cc of the inverse of the 8x8 block
           double y[8];
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
             double t = (r == cc) ? 1.0 : 0.0;
 #pragma unroll
-            for (int k = 0; k < r; ++k) t -= (m[r][k] * (dd[k] * si[k])) * y[k];     // L[r][k] = t[r][k] * sqrt(d_k)
-            y[r] = t * si[r];
+            for (int k = 0; k < r; ++k) t -= l[r][k] * y[k];
+            y[r] = t * inv[r];
           }
 #pragma unroll
           for (int r = 0; r < 8; ++r) Dinv[(c0 >> 3) * 64 + r * 8 + cc] = y[r];
         }
       }
-      CY(cy_b1);
-      __syncthreads();
-      CY(cy_w1);
-      if (tid < CT_B - c0) {                                  // (b2) row i of the sub-panel: v_c = D_ic - sum_k v_k t_ck, L_ic = v_c / sqrt(d_c)
-        const int i = c0 + tid;
-        double v[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          double t = T0[i * CT_LD + c0 + c];
-#pragma unroll
-          for (int k = 0; k < c; ++k) t = fma(-v[k], F8[c * 8 + k], t);
-          v[c] = t;
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) T1[i * CT_LD + c0 + c] = (c0 + c <= i) ? v[c] * F8[c * 9] : 0.0;
+      if (c0 == 0 && tid >= 72) {
+        // rows above the first sub-panel's reach: clear the strictly upper part of the factor once
+        for (int e = tid - 72; e < CT_B * CT_B; e += CT_THREADS - 72) { const int r = e >> 6, c = e & 63; if (c > r && c >= 8) T1[r * CT_LD + c] = 0.0; }
       }
-      CY(cy_b2);
       __syncthreads();
-      CY(cy_w2);
-      // (c) trailing update on the 8x8 tiles below/right; tile (0,0) - the next diagonal block - is warp 0's, above
-      const int m8 = 7 - (c0 >> 3);
-      const int ntile = m8 * (m8 + 1) / 2;
-      if (warp > 0)
-        for (int t = warp; t < ntile; t += CT_THREADS / 32 - 1) {
-          int rt = 0, rr = t;
-          while (rr >= rt + 1) { rr -= rt + 1; ++rt; }
-          const int R = c0 + 8 + 8 * rt, Cc = c0 + 8 + 8 * rr;
-          double d0 = 0.0, d1 = 0.0;
+      const int m = 7 - (c0 >> 3);                            // trailing 8x8 tiles per side
+      const int ntile = m * (m + 1) / 2;
+      for (int t = warp; t < ntile; t += CT_THREADS / 32) {
+        int rt = 0, rr = t;
+        while (rr >= rt + 1) { rr -= rt + 1; ++rt; }
+        const int R = c0 + 8 + 8 * rt, Cc = c0 + 8 + 8 * rr;
+        double d0 = 0.0, d1 = 0.0;
 #pragma unroll
-          for (int s2 = 0; s2 < 2; ++s2)
-            dmma884(d0, d1, T1[(R + g) * CT_LD + c0 + 4 * s2 + q], T1[(Cc + g) * CT_LD + c0 + 4 * s2 + q]);
-          double2* p = reinterpret_cast<double2*>(T0 + (R + g) * CT_LD + Cc + 2 * q);
-          double2 cur = *p; cur.x -= d0; cur.y -= d1; *p = cur;
-        }
-      // no barrier here: warp 0 loops straight into the next diagonal block; the barrier after (b1) covers the update
+        for (int s = 0; s < 2; ++s)
+          dmma884(d0, d1, T1[(R + g) * CT_LD + c0 + 4 * s + q], T1[(Cc + g) * CT_LD + c0 + 4 * s + q]);
+        double2* p = reinterpret_cast<double2*>(T0 + (R + g) * CT_LD + Cc + 2 * q);
+        double2 cur = *p;
+        cur.x -= d0; cur.y -= d1;
+        *p = cur;
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    if (a.prof && tid == 0) { a.prof[(size_t)my_tile * 8 + 4] = cy_b1 * 100000 + cy_w1; a.prof[(size_t)my_tile * 8 + 5] = cy_b2 * 100000 + cy_w2; }
     CT_STAMP(2);
     // publish L(j,j) (in place in S) and the 8x8 inverses
     for (int e = tid; e < CT_B * CT_B; e += CT_THREADS) {

@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(RED_T) k_reduce_rows(const double* __restrict_
 struct FLayout {
   int n_cam, Wc, Wcp, n_board, Wb, Wbp, n_f, ldz, rhs_col;
   __host__ __device__ int pcol(int j) const {
+    if (Wcp == Wc && Wbp == Wb) return j;                  // unpadded (dense SYRK): identity
     const int ncw = n_cam * Wc;
     if (j < ncw) { const int c = j / Wc; return c * Wcp + (j - c * Wc); }
     j -= ncw;
@@ -299,18 +300,28 @@ struct FLayout {
 // Wt[o] = [E^T F (6 x n_f) | E^T r] with leading dimension ldz.
 template <int STAGE>
 __global__ void __launch_bounds__(192) k_eblock_assemble(const int4* __restrict__ bobs, const int* __restrict__ pose_bobs_ptr,
-                                                         const double* __restrict__ brec, FLayout L, double* __restrict__ Hoo,
-                                                         double* __restrict__ Wt) {
+                                                         const double* __restrict__ brec, FLayout L,
+                                                         const unsigned* __restrict__ tile_mask, int mask_words,
+                                                         double* __restrict__ Hoo, double* __restrict__ Wt) {
   typedef Cols<STAGE> C;
   extern __shared__ double W[];   // [6][ldz]
   const int ldz = L.ldz;
   const int o = blockIdx.x, tid = threadIdx.x;
-  for (int e = tid; e < 6 * ldz; e += blockDim.x) W[e] = 0.0;
+  // only the 8-column tiles of the blocks this e-block observes are ever non-zero (tile_mask, static per stage): the
+  // others are neither cleared here nor written to Wt, which was zeroed once when it was allocated
+  const unsigned* mk = tile_mask ? tile_mask + (size_t)o * mask_words : nullptr;
+  for (int c = tid; c < ldz; c += blockDim.x) {
+    const int t = c >> 3;
+    if (!mk || ((mk[t >> 5] >> (t & 31)) & 1u)) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) W[k * ldz + c] = 0.0;
+    }
+  }
   __syncthreads();
   const int b0 = pose_bobs_ptr[o], b1 = pose_bobs_ptr[o + 1];
   // every thread owns one entry of the record and walks the e-block's board observations in order (fixed summation
   // order); the loads of EA_U records are issued together - one dependent HBM round trip per record otherwise
-  constexpr int EA_U = 8;
+  constexpr int EA_U = 1;   // records in flight per thread (8 measured slower: 127 vs 115 us; the kernel is not latency-bound)
   if (tid < 6 * C::WF) {
     const int j = tid / 6, k = tid % 6;                   // local f column j, e-row k: consecutive threads read consecutive
     const int off = C::cidx(j, C::E0 + k);                // doubles of the record's f x e part (CI_FE + 6 j + k = CI_FE + tid)
@@ -345,7 +356,13 @@ __global__ void __launch_bounds__(192) k_eblock_assemble(const int4* __restrict_
   }
   __syncthreads();
   double* dst = Wt + (size_t)o * 6 * ldz;
-  for (int e = tid; e < 6 * ldz; e += blockDim.x) dst[e] = W[e];
+  for (int c = tid; c < ldz; c += blockDim.x) {
+    const int t = c >> 3;
+    if (!mk || ((mk[t >> 5] >> (t & 31)) & 1u)) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) dst[k * ldz + c] = W[k * ldz + c];
+    }
+  }
 }
 
 // K2b: per (camera[,board]) pair, fixed-order sum over the pair's board observations of the f x f upper
@@ -469,9 +486,11 @@ __global__ void k_eblock_grad(const double* __restrict__ pose, const double* __r
 __global__ void __launch_bounds__(128) k_eblock_factor(const double* __restrict__ Hoo, const double* __restrict__ Wt,
                                                        const double* __restrict__ scale_e, const double* __restrict__ scale_f,
                                                        const double* __restrict__ diag_e, double radius, FLayout Lo,
+                                                       const unsigned* __restrict__ tile_mask, int mask_words,
                                                        double* __restrict__ Lout, double* __restrict__ Z,
                                                        int* __restrict__ fail) {
   const int o = blockIdx.x;
+  const unsigned* mk = tile_mask ? tile_mask + (size_t)o * mask_words : nullptr;   // columns outside the observed blocks are zero in Wt and stay zero in Z
   const int n_f = Lo.n_f, ldz = Lo.ldz;
   double L[36], se[6];
 #pragma unroll
@@ -491,21 +510,22 @@ __global__ void __launch_bounds__(128) k_eblock_factor(const double* __restrict_
   const double* W = Wt + (size_t)o * 6 * ldz;
   double* Zo = Z + (size_t)o * 6 * ldz;
   // one real column (f index j, then the rhs as j = n_f) per thread and pass; the padding columns of Z stay zero
-  constexpr int EF_U = 4;   // columns per thread in flight (their loads are issued before the first substitution)
+  constexpr int EF_U = 1;   // columns per thread in flight (4 measured slower: 127 vs 105 us, register pressure)
   for (int j0 = threadIdx.x; j0 <= n_f; j0 += EF_U * blockDim.x) {
     double w[EF_U][6]; int pc[EF_U];
 #pragma unroll
     for (int u = 0; u < EF_U; ++u) {
       const int j = j0 + u * blockDim.x;
       pc[u] = (j < n_f) ? Lo.pcol(j) : Lo.rhs_col;
+      if (mk && j <= n_f && !((mk[pc[u] >> 8] >> ((pc[u] >> 3) & 31)) & 1u)) pc[u] = -1;      // inactive tile: skip
       const double sf = (j < n_f) ? scale_f[j] : 1.0;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) w[u][k] = (j <= n_f) ? se[k] * W[k * ldz + pc[u]] * sf : 0.0;
+      for (int k = 0; k < 6; ++k) w[u][k] = (j <= n_f && pc[u] >= 0) ? se[k] * W[k * ldz + pc[u]] * sf : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < EF_U; ++u) {
       const int j = j0 + u * blockDim.x;
-      if (j <= n_f) {
+      if (j <= n_f && pc[u] >= 0) {
         if (ok) chol6_fwd(L, w[u]);
 #pragma unroll
         for (int k = 0; k < 6; ++k) Zo[k * ldz + pc[u]] = ok ? w[u][k] : 0.0;
@@ -1079,6 +1099,7 @@ __global__ void __launch_bounds__(256) k_backsubst(const double* __restrict__ Z,
                                                    const double* __restrict__ zf, const double* __restrict__ scale_e,
                                                    const double* __restrict__ diag_e, double radius,
                                                    const double* __restrict__ pose, int n_pose, FLayout Lo,
+                                                   const unsigned* __restrict__ tile_mask, int mask_words,
                                                    double* __restrict__ pose_cand, double* __restrict__ part) {
   const int n_f = Lo.n_f, ldz = Lo.ldz;
   // one warp per e-block: q = Z_o z_f by lanes striding the columns (coalesced), xor-shuffle tree (fixed order)
@@ -1086,9 +1107,11 @@ __global__ void __launch_bounds__(256) k_backsubst(const double* __restrict__ Z,
   if (o >= n_pose) return;
   const double* Zo = Z + (size_t)o * 6 * ldz;
   double q[6] = {0, 0, 0, 0, 0, 0};
+  const unsigned* mk = tile_mask ? tile_mask + (size_t)o * mask_words : nullptr;
   for (int j = lane; j < n_f; j += 32) {
-    const double zj = zf[j];
     const int pc = Lo.pcol(j);
+    if (mk && !((mk[pc >> 8] >> ((pc >> 3) & 31)) & 1u)) continue;      // structurally zero tile of Z_o
+    const double zj = zf[j];
 #pragma unroll
     for (int k = 0; k < 6; ++k) q[k] += Zo[k * ldz + pc] * zj;
   }

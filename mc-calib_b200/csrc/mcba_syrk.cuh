@@ -48,7 +48,28 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                ::"r"(sm_addr(dst)), "l"(src), "r"(bytes), "r"(sm_addr(bar)) : "memory");
 }
 
+// Four DMMAs (a 2 x 2 group of 8x8 sub-tiles) behind ONE warp-uniform branch. `go` is the same on every lane (it comes
+// from activity words all lanes read from the same shared-memory address); bra.uni tells ptxas so: it keeps a real
+// branch instead of predicating every mma.sync (which costs a WARPSYNC + a register shuffle per instruction).
+__device__ __forceinline__ void dmma_group4(double& a0, double& a1, double& b0, double& b1, double& c0, double& c1,
+                                            double& d0, double& d1, double fa0, double fa1, double fb0, double fb1, unsigned go) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.eq.u32 p, %12, 0;\n\t"
+      "@p bra.uni DMMA_SKIP;\n\t"
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%8}, {%10}, {%0,%1};\n\t"
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%2,%3}, {%8}, {%11}, {%2,%3};\n\t"
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%4,%5}, {%9}, {%10}, {%4,%5};\n\t"
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%6,%7}, {%9}, {%11}, {%6,%7};\n\t"
+      "DMMA_SKIP:\n\t"
+      "}\n"
+      : "+d"(a0), "+d"(a1), "+d"(b0), "+d"(b1), "+d"(c0), "+d"(c1), "+d"(d0), "+d"(d1)
+      : "d"(fa0), "d"(fa1), "d"(fb0), "d"(fb1), "r"(go));
+}
+
 // tile_mask: [n_pose][mask_words] one bit per 8-column tile of Z (bit t of word t/32)
+template <bool SPARSE>
 __global__ void __launch_bounds__(SY2_THREADS, 1) k_syrk2(const double* __restrict__ Z, int64_t n_rows, int ldz, int nt,
                                                           int64_t rows_per_split, const unsigned* __restrict__ tile_mask,
                                                           int mask_words, double* __restrict__ partial) {
@@ -84,7 +105,7 @@ __global__ void __launch_bounds__(SY2_THREADS, 1) k_syrk2(const double* __restri
       double* Bs = As + SY2_K * SY_LD;
       const int64_t rbase = r0 + (int64_t)c * SY2_K;
       const int valid = (int)min((int64_t)SY2_K, r1 - rbase);
-      if (lane < 4) {                                          // activity of the chunk's four e-blocks for this CTA's strips
+      if (SPARSE && lane < 4) {                                // activity of the chunk's four e-blocks for this CTA's strips
         const int64_t o = rbase / 6 + lane;
         unsigned mr = 0, mc = 0;
         if (o * 6 < r1) {
@@ -123,6 +144,20 @@ __global__ void __launch_bounds__(SY2_THREADS, 1) k_syrk2(const double* __restri
     if (!skip) {
       const double* As = sy_sm + (size_t)s * SY2_STAGE_DOUBLES;
       const double* Bp = diag ? As : As + SY2_K * SY_LD;
+      if (!SPARSE) {
+#pragma unroll
+        for (int ks = 0; ks < SY2_K / 4; ++ks) {
+          double fa[4], fb[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) fa[i] = As[(4 * ks + q) * SY_LD + wm + 8 * i + g];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) fb[j] = Bp[(4 * ks + q) * SY_LD + wn + 8 * j + g];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+        }
+      } else {
 #pragma unroll
       for (int p = 0; p < 2; ++p) {                            // two pairs of e-blocks per chunk
         const unsigned ra0 = (smask[s * 8 + (2 * p) * 2] >> sh_r) & 0xFu, cb0 = (smask[s * 8 + (2 * p) * 2 + 1] >> sh_c) & 0xFFu;
@@ -142,12 +177,18 @@ __global__ void __launch_bounds__(SY2_THREADS, 1) k_syrk2(const double* __restri
           for (int i = 0; i < 4; ++i) fa[i] = ((rany >> i) & 1u) ? As[(4 * ks + q) * SY_LD + wm + 8 * i + g] : 0.0;
 #pragma unroll
           for (int j = 0; j < 8; ++j) fb[j] = ((cany >> j) & 1u) ? Bp[(4 * ks + q) * SY_LD + wn + 8 * j + g] : 0.0;
+          // one warp-uniform branch per group of 2 x 2 sub-tiles (= camera block x camera block at stage 5)
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int rc = 0; rc < 2; ++rc)
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if ((act >> (8 * i + j)) & 1u) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+            for (int cc = 0; cc < 4; ++cc) {
+              const unsigned m4 = (0x3u << (16 * rc + 2 * cc)) | (0x3u << (16 * rc + 8 + 2 * cc));
+              dmma_group4(acc[2 * rc][2 * cc][0], acc[2 * rc][2 * cc][1], acc[2 * rc][2 * cc + 1][0], acc[2 * rc][2 * cc + 1][1],
+                          acc[2 * rc + 1][2 * cc][0], acc[2 * rc + 1][2 * cc][1], acc[2 * rc + 1][2 * cc + 1][0], acc[2 * rc + 1][2 * cc + 1][1],
+                          fa[2 * rc], fa[2 * rc + 1], fb[2 * cc], fb[2 * cc + 1], act & m4);
+            }
         }
+      }
       }
     }
     __syncwarp();

@@ -15,7 +15,7 @@ h = mcba.Handle(prob)
 A, b = spd(n, n)
 h.debug_cholesky(A, b, variant=1, iters=3)
 z, L, ms, fail = h.debug_cholesky(A, b, variant=1, iters=1)
-t = h.debug_fetch("chol_prof").reshape(-1, 8)
+t = h.debug_fetch("chol_prof").reshape(-1, 16)
 NT = (n + 63) // 64
 tid = lambda i, j: j * (NT + 1) - j * (j - 1) // 2 + (i - j)
 t0 = t[t[:, 0] > 0, 0].min()
@@ -33,5 +33,6 @@ r = t[tid(NT, 0)]
 print("rhs tile col 0:", [round(rel(x), 1) for x in r[:6]])
 d = t[tid(3, 3)]
 print("diag tile 3 potrf cycles: b1 %d  wait1 %d  b2 %d  wait2 %d" % (d[4] // 100000, d[4] % 100000, d[5] // 100000, d[5] % 100000))
+print("  b1 split: diag-update %d  loads %d  pivots %d  rsqrt+stores %d" % (d[8], d[9], d[10], d[11]))
 print("first stamp spread (us):", (t[t[:, 0] > 0, 0].max() - t0) / 1e3)
 h.close()
