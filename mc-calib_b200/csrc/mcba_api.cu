@@ -12,6 +12,7 @@
 #include "mcba_batched.cuh"
 #include "mcba_chol_tiles.cuh"
 #include "mcba_syrk.cuh"
+#include "mcba_obs_stream.cuh"
 
 #include <dlfcn.h>
 #include <algorithm>
@@ -323,6 +324,7 @@ static int setup_stage(Handle* H, int stage) {
     const int sm = OBS_WARPS * (CTX_SIZE + Cols<ST>::NC * TS) * 8;
     CU(cudaFuncSetAttribute(k_observations<ST, MODE_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     CU(cudaFuncSetAttribute(k_observations<ST, MODE_FROM_J>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    CU(cudaFuncSetAttribute(k_observations_stream<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, OBS_WARPS * (2 * CTX_SIZE + Cols<ST>::NC * TS) * 8));
     CU(cudaFuncSetAttribute(k_eblock_assemble<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * H->ldz * 8));
   });
   return MCBA_OK;
@@ -374,6 +376,21 @@ template <int MODE> static int launch_obs(Handle* H, int which, double huber_a) 
   const int fam = MODE == MODE_FUSED ? KF_FUSED : MODE == MODE_MATERIALIZE ? KF_MATERIALIZE : MODE == MODE_FROM_J ? KF_FROM_J : KF_COST;
   Timed t(H, fam);
   ObsArgs a = obs_args(H, which, huber_a);
+  // MCBA_K1_STREAM=1: the streaming kernel packs the tail of one board observation and the head of the next into one
+  // warp pass (25 % fewer Jacobian passes on 48-corner boards). Measured SLOWER than one observation per pass sequence
+  // (0.96 vs 0.88 ms): kept as an opt-in experiment, parity-tested
+  static const bool stream_env = []() { const char* e = getenv("MCBA_K1_STREAM"); return e && atoi(e) != 0; }();
+  if (MODE == MODE_FUSED && stream_env && !a.gate) {
+    DISPATCH_STAGE(H->stage, {
+      const int sm = OBS_WARPS * (2 * CTX_SIZE + Cols<ST>::NC * TS) * 8;
+      const int per_sm = std::min(3, std::max(1, (227 * 1024) / (sm + 1024)));
+      const int grid = std::max(1, std::min((H->nb + 2 * OBS_WARPS - 1) / (2 * OBS_WARPS), H->n_sm * per_sm));
+      ++H->n_launches;
+      k_observations_stream<ST><<<grid, OBS_WARPS * 32, sm, H->stream>>>(a);
+    });
+    CHECK_LAUNCH();
+    return MCBA_OK;
+  }
   DISPATCH_STAGE(H->stage, {
     constexpr bool ACC = (MODE == MODE_FUSED || MODE == MODE_FROM_J);
     const int sm = OBS_WARPS * (CTX_SIZE + (ACC ? Cols<ST>::NC * TS : 0)) * 8;
