@@ -86,6 +86,7 @@ struct Handle {
   double *d_scale_e = nullptr, *d_diag_e = nullptr, *d_scale_f = nullptr, *d_diag_f = nullptr;
   double *d_FF = nullptr, *d_gf = nullptr, *d_S = nullptr, *d_rhs = nullptr, *d_zf = nullptr, *d_ZtZ = nullptr, *d_hz = nullptr;
   double *d_syrk_partial = nullptr, *d_pair_partial = nullptr, *d_pair_rec = nullptr, *d_part_e = nullptr;
+  double *pair_in = nullptr, *pair_out = nullptr;   // where k_pair_final writes / k_ff_assemble reads (d_pair_rec, or the exported buffer)
   double *d_red_scratch = nullptr, *d_scalars = nullptr, *d_gather = nullptr;
   int* d_fail = nullptr;
   bool obs_shared = false;   // d_u / d_v / d_pt belong to the observation cache (mcba_obs_register)
@@ -113,6 +114,9 @@ struct Handle {
   unsigned long long* d_p2p_flags = nullptr; unsigned int* d_p2p_counter = nullptr; int* d_p2p_err = nullptr;
   double* d_p2p_stage = nullptr; bool ZtZ_pooled = false;
   double* peer_stage[P2P_MAX_RANKS] = {nullptr}; double* peer_ZtZ[P2P_MAX_RANKS] = {nullptr}; unsigned long long* peer_flags[P2P_MAX_RANKS] = {nullptr};
+  // pair records and phase scalars over the same mechanism: one more exported buffer per rank [pair in | pair out | scalar table x 2]
+  double* d_p2p_x = nullptr; double* peer_x[P2P_MAX_RANKS] = {nullptr}; size_t x_pair = 0; unsigned long long pair_epoch = 0, gather_epoch = 0;
+  unsigned int* d_p2p_counter2 = nullptr;
   std::vector<void*> ipc_opened;
   // LM state
   mcba_options opt;
@@ -316,6 +320,7 @@ static int setup_stage(Handle* H, int stage) {
   if (dalloc(H, &H->d_syrk_partial, (size_t)H->syrk_nsplit * H->syrk_tiles * SY_T * SY_T)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_pair_partial, (size_t)H->n_chunks * H->NE)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_pair_rec, (size_t)H->n_pair * H->NE)) return MCBA_ERR_CUDA;
+  H->pair_in = H->d_pair_rec; H->pair_out = H->d_pair_rec;
   if (dalloc(H, &H->d_part_e, np * 4)) return MCBA_ERR_CUDA;
   dfree(H, &H->d_jmat); dfree(H, &H->d_resmat);
   H->have_scale = false;
@@ -413,6 +418,18 @@ static int gather_scalars(Handle* H, const double* d_local, int m, std::vector<d
   host.assign((size_t)m * H->n_ranks, 0.0);
   if (H->n_ranks == 1) {
     CU(cudaMemcpyAsync(host.data(), d_local, m * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+  } else if (H->p2p && m <= P2P_GATHER_W) {
+    { Timed t(H, KF_NCCL);
+      P2PGatherArgs ga;
+      const size_t tab = 2 * H->x_pair;
+      for (int r = 0; r < P2P_MAX_RANKS; ++r) { ga.table[r] = H->peer_x[r] ? H->peer_x[r] + tab : nullptr; ga.flags[r] = H->peer_flags[r]; }
+      ga.local = d_local; ga.m = m; ga.rank = H->rank; ga.n_ranks = H->n_ranks; ga.epoch = ++H->gather_epoch; ga.err = H->d_p2p_err;
+      ++H->n_launches;
+      k_gather_p2p<<<1, 256, 0, H->stream>>>(ga);
+      CU(cudaGetLastError()); }
+    const double* tabp = H->d_p2p_x + 2 * H->x_pair + (H->gather_epoch & 1ull) * P2P_MAX_RANKS * P2P_GATHER_W;
+    for (int r = 0; r < H->n_ranks; ++r)
+      CU(cudaMemcpyAsync(host.data() + (size_t)r * m, tabp + (size_t)r * P2P_GATHER_W, m * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
   } else {
     { Timed t(H, KF_NCCL);
       const int rc = g_nccl.AllGather(d_local, H->d_gather, m, NCCL_DOUBLE, H->comm, H->stream);
@@ -463,7 +480,7 @@ static int eval_assemble(Handle* H, bool first) {
   // F^T F / F^T r assembly (pair reduction -> [allreduce] -> dense F^T F; stream_b). They meet before k_fstep.
   // (single GPU only for now: with ranks the pair-record allreduce would move to stream_b as well, which has not been
   // measured on a multi-GPU box yet; there everything stays on the main stream, in this order)
-  const bool ov = H->stream_b != nullptr && H->n_ranks == 1;
+  const bool ov = H->stream_b != nullptr && (H->n_ranks == 1 || H->p2p);
   cudaStream_t sb = ov ? H->stream_b : H->stream;
   if (ov) { CU(cudaEventRecord(H->ev_fork, H->stream)); CU(cudaStreamWaitEvent(H->stream_b, H->ev_fork, 0)); }
   {
@@ -475,10 +492,18 @@ static int eval_assemble(Handle* H, bool first) {
     }
     const int n = H->n_pair * H->NE;
     ++H->n_launches;
-    DISPATCH_STAGE(H->stage, (k_pair_final<ST><<<(n + 255) / 256, 256, 0, sb>>>(H->d_pair_chunk_ptr, H->n_pair, H->d_pair_partial, H->d_pair_rec)));
+    DISPATCH_STAGE(H->stage, (k_pair_final<ST><<<(n + 255) / 256, 256, 0, sb>>>(H->d_pair_chunk_ptr, H->n_pair, H->d_pair_partial, H->pair_in)));
     CHECK_LAUNCH();
   }
-  if (H->n_ranks > 1) {   // the only NCCL call of this phase; the next one (scalar gather) comes after the join
+  if (H->n_ranks > 1 && H->p2p) {   // sum of the pair records across ranks over peer memory (k_allreduce_p2p)
+    Timed t(H, KF_NCCL, sb);
+    P2PVecArgs va;
+    for (int r = 0; r < P2P_MAX_RANKS; ++r) { va.in[r] = H->peer_x[r]; va.out[r] = H->peer_x[r] ? H->peer_x[r] + H->x_pair : nullptr; va.flags[r] = H->peer_flags[r]; }
+    va.n = H->n_pair * H->NE; va.rank = H->rank; va.n_ranks = H->n_ranks; va.epoch = ++H->pair_epoch; va.counter = H->d_p2p_counter2; va.err = H->d_p2p_err;
+    ++H->n_launches;   // no grid-wide barrier inside (the CTAs only wait for other ranks' flags): an ordinary launch
+    k_allreduce_p2p<<<std::min(H->n_sm, std::max(1, (va.n / H->n_ranks + 255) / 256)), 256, 0, sb>>>(va);
+    CHECK_LAUNCH();
+  } else if (H->n_ranks > 1) {   // NCCL fallback
     Timed t(H, KF_NCCL, sb);
     const int nrc = g_nccl.AllReduce(H->d_pair_rec, H->d_pair_rec, (size_t)H->n_pair * H->NE, NCCL_DOUBLE, NCCL_SUM, H->comm, sb);
     if (nrc != 0) { H->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?"); return MCBA_ERR_NCCL; }
@@ -487,7 +512,7 @@ static int eval_assemble(Handle* H, bool first) {
     Timed t(H, KF_PAIR, sb);
     const int n = H->n_f * H->n_f + H->n_f;
     ++H->n_launches;
-    DISPATCH_STAGE(H->stage, (k_ff_assemble<ST><<<(n + 255) / 256, 256, 0, sb>>>(H->d_pair_rec, H->n_cam, H->n_board, H->Wc, H->Wb, H->n_f, H->d_FF, H->d_gf)));
+    DISPATCH_STAGE(H->stage, (k_ff_assemble<ST><<<(n + 255) / 256, 256, 0, sb>>>(H->pair_out, H->n_cam, H->n_board, H->Wc, H->Wb, H->n_f, H->d_FF, H->d_gf)));
     CHECK_LAUNCH();
   }
   if (ov) CU(cudaEventRecord(H->ev_join, H->stream_b));
@@ -699,7 +724,7 @@ static int download_params(Handle* H, mcba_params* p) {
 // (through the NCCL communicator), open the peers' handles and keep the pointer tables. Collective: every rank calls it
 // (mcba_comm_init, and mcba_set_stage after the buffers were reallocated). Falls back to the NCCL allreduce
 // (p2p = false) if anything is refused on any rank; MCBA_P2P=0 disables it.
-struct IpcRecord { cudaIpcMemHandle_t h[3]; long long off[3]; int ok; int pad; };
+struct IpcRecord { cudaIpcMemHandle_t h[4]; long long off[4]; int ok; int pad; };
 // Buffers whose CUDA IPC handles go to other ranks are never cudaFree'd while the process lives: freeing an exported
 // allocation before every importer has closed its mapping is undefined behaviour, and mcba_destroy is not a
 // collective. They are recycled through this process-wide pool instead (one allocation of >= 2 MB each, so that an IPC
@@ -734,6 +759,7 @@ static int close_p2p(Handle* H) {
 static void release_exported(Handle* H) {
   g_export_pool.release(H->d_p2p_stage); H->d_p2p_stage = nullptr;
   g_export_pool.release(H->d_p2p_flags); H->d_p2p_flags = nullptr;
+  g_export_pool.release(H->d_p2p_x); H->d_p2p_x = nullptr; H->pair_in = H->d_pair_rec; H->pair_out = H->d_pair_rec;
   if (H->ZtZ_pooled) { g_export_pool.release(H->d_ZtZ); H->d_ZtZ = nullptr; H->ZtZ_pooled = false; }
 }
 static int setup_p2p(Handle* H) {
@@ -745,28 +771,32 @@ static int setup_p2p(Handle* H) {
   static range_fn get_range = []() -> range_fn { void* l = dlopen("libcuda.so.1", RTLD_NOW); return l ? (range_fn)dlsym(l, "cuMemGetAddressRange_v2") : nullptr; }();
   const int N = H->n_ranks;
   if (!H->d_p2p_counter) {
-    if (dalloc(H, &H->d_p2p_counter, (size_t)2) || dalloc(H, &H->d_p2p_err, (size_t)1)) return MCBA_ERR_CUDA;
-    CU(cudaMemset(H->d_p2p_counter, 0, 2 * sizeof(unsigned int))); CU(cudaMemset(H->d_p2p_err, 0, sizeof(int)));
+    if (dalloc(H, &H->d_p2p_counter, (size_t)2) || dalloc(H, &H->d_p2p_counter2, (size_t)2) || dalloc(H, &H->d_p2p_err, (size_t)1)) return MCBA_ERR_CUDA;
+    CU(cudaMemset(H->d_p2p_counter, 0, 2 * sizeof(unsigned int))); CU(cudaMemset(H->d_p2p_counter2, 0, 2 * sizeof(unsigned int))); CU(cudaMemset(H->d_p2p_err, 0, sizeof(int)));
   }
   // exported buffers come from the pool and are cleared BEFORE their handles are published (a peer may start writing
   // flags as soon as it has opened them); the epochs restart with them
-  g_export_pool.release(H->d_p2p_stage); g_export_pool.release(H->d_p2p_flags);
+  g_export_pool.release(H->d_p2p_stage); g_export_pool.release(H->d_p2p_flags); g_export_pool.release(H->d_p2p_x);
+  H->x_pair = (((size_t)H->n_pair * H->NE + 31) / 32) * 32;
+  const size_t x_doubles = 2 * H->x_pair + (size_t)2 * P2P_MAX_RANKS * P2P_GATHER_W;
+  H->d_p2p_x = (double*)g_export_pool.acquire(H->device, x_doubles * sizeof(double));
   const size_t zz_bytes = (size_t)H->ldz * H->ldz * sizeof(double);
   H->d_p2p_stage = (double*)g_export_pool.acquire(H->device, (size_t)H->syrk_tiles * SY_T * SY_T * sizeof(double));
-  H->d_p2p_flags = (unsigned long long*)g_export_pool.acquire(H->device, (size_t)2 * P2P_MAX_RANKS * sizeof(unsigned long long));
+  H->d_p2p_flags = (unsigned long long*)g_export_pool.acquire(H->device, (size_t)P2P_FLAG_SLOTS * P2P_MAX_RANKS * sizeof(unsigned long long));
   if (!H->ZtZ_pooled) {
     double* zz = (double*)g_export_pool.acquire(H->device, zz_bytes);
     if (zz) { dfree(H, &H->d_ZtZ); H->d_ZtZ = zz; H->ZtZ_pooled = true; }
   }
-  if (!H->d_p2p_stage || !H->d_p2p_flags || !H->ZtZ_pooled) { H->err = "cudaMalloc(exported buffers)"; return MCBA_ERR_CUDA; }
+  if (!H->d_p2p_stage || !H->d_p2p_flags || !H->d_p2p_x || !H->ZtZ_pooled) { H->err = "cudaMalloc(exported buffers)"; return MCBA_ERR_CUDA; }
   CU(cudaMemset(H->d_ZtZ, 0, zz_bytes));   // the lower triangle is never written
-  CU(cudaMemset(H->d_p2p_flags, 0, (size_t)2 * P2P_MAX_RANKS * sizeof(unsigned long long)));
+  CU(cudaMemset(H->d_p2p_flags, 0, (size_t)P2P_FLAG_SLOTS * P2P_MAX_RANKS * sizeof(unsigned long long)));
+  CU(cudaMemset(H->d_p2p_x, 0, x_doubles * sizeof(double)));
   CU(cudaDeviceSynchronize());
-  H->p2p_epoch = 0;
+  H->p2p_epoch = 0; H->pair_epoch = 0; H->gather_epoch = 0;
   IpcRecord mine; std::memset(&mine, 0, sizeof(mine));
-  void* ptrs[3] = {H->d_p2p_stage, H->d_ZtZ, H->d_p2p_flags};
+  void* ptrs[4] = {H->d_p2p_stage, H->d_ZtZ, H->d_p2p_flags, H->d_p2p_x};
   mine.ok = get_range ? 1 : 0;
-  for (int k = 0; k < 3 && mine.ok; ++k) {
+  for (int k = 0; k < 4 && mine.ok; ++k) {
     unsigned long long base = 0; size_t size = 0;
     if (get_range(&base, &size, (unsigned long long)ptrs[k]) != 0) { mine.ok = 0; break; }
     mine.off[k] = (long long)((unsigned long long)ptrs[k] - base);
@@ -783,11 +813,11 @@ static int setup_p2p(Handle* H) {
   cudaFreeAsync(d_send, H->stream); cudaFreeAsync(d_recv, H->stream);
   bool ok = true;
   for (int r = 0; r < N; ++r) ok = ok && all[r].ok;
-  for (int r = 0; r < P2P_MAX_RANKS; ++r) { H->peer_stage[r] = nullptr; H->peer_ZtZ[r] = nullptr; H->peer_flags[r] = nullptr; }
+  for (int r = 0; r < P2P_MAX_RANKS; ++r) { H->peer_stage[r] = nullptr; H->peer_ZtZ[r] = nullptr; H->peer_flags[r] = nullptr; H->peer_x[r] = nullptr; }
   for (int r = 0; r < N && ok; ++r) {
-    if (r == H->rank) { H->peer_stage[r] = H->d_p2p_stage; H->peer_ZtZ[r] = H->d_ZtZ; H->peer_flags[r] = H->d_p2p_flags; continue; }
-    void* opened[3] = {nullptr, nullptr, nullptr};
-    for (int k = 0; k < 3 && ok; ++k) {
+    if (r == H->rank) { H->peer_stage[r] = H->d_p2p_stage; H->peer_ZtZ[r] = H->d_ZtZ; H->peer_flags[r] = H->d_p2p_flags; H->peer_x[r] = H->d_p2p_x; continue; }
+    void* opened[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < 4 && ok; ++k) {
       bool dup = false;   // two buffers may live in the same underlying allocation
       for (int q = 0; q < k; ++q) if (std::memcmp(&all[r].h[q], &all[r].h[k], sizeof(cudaIpcMemHandle_t)) == 0) { opened[k] = opened[q]; dup = true; }
       if (dup) continue;
@@ -798,6 +828,7 @@ static int setup_p2p(Handle* H) {
     H->peer_stage[r] = (double*)((char*)opened[0] + all[r].off[0]);
     H->peer_ZtZ[r] = (double*)((char*)opened[1] + all[r].off[1]);
     H->peer_flags[r] = (unsigned long long*)((char*)opened[2] + all[r].off[2]);
+    H->peer_x[r] = (double*)((char*)opened[3] + all[r].off[3]);
   }
   // every rank must take the same path: agree through a sum over ranks of the local verdict
   double verdict = ok ? 1.0 : 0.0;
@@ -809,6 +840,7 @@ static int setup_p2p(Handle* H) {
   { int per_sm = 0; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_syrk_sum_p2p, 256, 0));
     H->p2p_grid = std::min(2, std::max(1, per_sm)) * H->n_sm; }
   H->p2p = true;
+  H->pair_in = H->d_p2p_x; H->pair_out = H->d_p2p_x + H->x_pair;   // the pair records live in the exported buffer from now on
   return MCBA_OK;
 }
 
@@ -929,7 +961,7 @@ void mcba_destroy(void* h) {
   close_p2p(H);
   release_exported(H);
   if (H->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(H->comm);
-  dfree(H, &H->d_p2p_counter); dfree(H, &H->d_p2p_err);
+  dfree(H, &H->d_p2p_counter); dfree(H, &H->d_p2p_counter2); dfree(H, &H->d_p2p_err);
   for (auto& p : H->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : H->free_events) cudaEventDestroy(e);
   if (H->tm_a) { cudaEventDestroy(H->tm_a); cudaEventDestroy(H->tm_b); }

@@ -731,6 +731,68 @@ __global__ void __launch_bounds__(256) k_syrk_sum_p2p(P2PArgs a) {
   }
 }
 
+// The other two exchanges of an LM iteration over the same peer-memory mechanism (no NCCL on the iteration path):
+// k_allreduce_p2p  sum of the pair records (F^T F blocks, F^T r; 1.3 MB on the dome) across ranks: every rank's input
+//                  vector is peer-mapped; rank r sums slice r from all ranks in rank order (bit-identical results
+//                  everywhere) and stores it into every rank's output vector; flag slots P2P_CH_PAIR, +1.
+// k_gather_p2p     the 12 scalars of a phase (cost, norms, model-cost pieces, failure flag): every rank writes its row
+//                  into every rank's table; double-buffered by the parity of the epoch; flag slot P2P_CH_GATHER.
+constexpr int P2P_CH_PAIR = 2, P2P_CH_GATHER = 4, P2P_FLAG_SLOTS = 6, P2P_GATHER_W = 16;
+struct P2PVecArgs {
+  double* in[P2P_MAX_RANKS]; double* out[P2P_MAX_RANKS]; unsigned long long* flags[P2P_MAX_RANKS];
+  int n, rank, n_ranks; unsigned long long epoch; unsigned int* counter; int* err;
+};
+__global__ void __launch_bounds__(256) k_allreduce_p2p(P2PVecArgs a) {
+  __shared__ int ok_s;
+  volatile unsigned long long* my_flags = a.flags[a.rank];
+  // the input was written by the previous kernel of this stream: publish it, then wait for everybody's
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      for (int p = 0; p < a.n_ranks; ++p) ((volatile unsigned long long*)a.flags[p])[P2P_CH_PAIR * P2P_MAX_RANKS + a.rank] = a.epoch;
+    }
+    ok_s = p2p_wait(my_flags + P2P_CH_PAIR * P2P_MAX_RANKS, a.n_ranks, a.epoch, a.err) ? 1 : 0;
+  }
+  __syncthreads();
+  if (ok_s) {
+    const int slice = (a.n + a.n_ranks - 1) / a.n_ranks;
+    const int lo = slice * a.rank, hi = min(a.n, lo + slice);
+    for (int idx = lo + blockIdx.x * blockDim.x + threadIdx.x; idx < hi; idx += gridDim.x * blockDim.x) {
+      double v[P2P_MAX_RANKS];
+#pragma unroll
+      for (int p = 0; p < P2P_MAX_RANKS; ++p) v[p] = (p < a.n_ranks) ? __ldcg(a.in[p] + idx) : 0.0;
+      double s = v[0];
+#pragma unroll
+      for (int p = 1; p < P2P_MAX_RANKS; ++p) if (p < a.n_ranks) s += v[p];
+#pragma unroll
+      for (int p = 0; p < P2P_MAX_RANKS; ++p) if (p < a.n_ranks) a.out[p][idx] = s;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(a.counter, 1u) == gridDim.x - 1) {
+    a.counter[0] = 0;
+    __threadfence_system();
+    for (int p = 0; p < a.n_ranks; ++p) ((volatile unsigned long long*)a.flags[p])[(P2P_CH_PAIR + 1) * P2P_MAX_RANKS + a.rank] = a.epoch;
+    p2p_wait(my_flags + (P2P_CH_PAIR + 1) * P2P_MAX_RANKS, a.n_ranks, a.epoch, a.err);
+  }
+}
+struct P2PGatherArgs {
+  double* table[P2P_MAX_RANKS]; unsigned long long* flags[P2P_MAX_RANKS];
+  const double* local; int m, rank, n_ranks; unsigned long long epoch; int* err;
+};
+__global__ void __launch_bounds__(256) k_gather_p2p(P2PGatherArgs a) {
+  const int region = (int)(a.epoch & 1ull) * P2P_MAX_RANKS * P2P_GATHER_W;
+  for (int t = threadIdx.x; t < a.m * a.n_ranks; t += blockDim.x) {
+    const int p = t / a.m, i = t % a.m;
+    a.table[p][region + a.rank * P2P_GATHER_W + i] = a.local[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < a.n_ranks) ((volatile unsigned long long*)a.flags[threadIdx.x])[P2P_CH_GATHER * P2P_MAX_RANKS + a.rank] = a.epoch;
+  if (threadIdx.x == 0) p2p_wait((volatile unsigned long long*)a.flags[a.rank] + P2P_CH_GATHER * P2P_MAX_RANKS, a.n_ranks, a.epoch, a.err);
+}
+
 // K2e: reduced system. S = s_f F^T F s_f + D_f^2 - Z^T Z (full symmetric, n_f x n_f, ld n_f); rhs = s_f g_f - Z^T y.
 __global__ void k_build_reduced(const double* __restrict__ FF, const double* __restrict__ gf,
                                 const double* __restrict__ ZtZ, const double* __restrict__ scale_f,
