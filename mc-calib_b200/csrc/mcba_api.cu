@@ -127,6 +127,13 @@ struct Handle {
   std::vector<mcba_trace_row> trace;
   std::vector<double> x0_cam, x0_pose, x0_board, x0_intr;   // start point of the solve in flight (returned on FAILURE)
   int64_t n_obs_global = 0;
+  // CUDA graphs of the two per-iteration launch sequences (single-rank handles): key = 2 * cur + brec_par
+  bool use_graph = false, capturing = false; int brec_par = 0;
+  cudaGraphExec_t g_step[4] = {nullptr, nullptr, nullptr, nullptr}, g_asm[4] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t g_step_launches[4] = {0, 0, 0, 0}, g_asm_launches[4] = {0, 0, 0, 0};
+  mcba_options graph_opt; bool graph_opt_valid = false;
+  double* h_pin = nullptr;      // pinned host: [0] radius, [8 .. 8 + SC_N) the scalars of the last phase
+  double* d_radius = nullptr; unsigned* d_ct_epoch = nullptr;
   // timing
   struct Pending { int fam; cudaEvent_t a, b; };
   std::vector<Pending> pending; std::vector<cudaEvent_t> free_events;
@@ -156,8 +163,9 @@ static void flush_timers(Handle* H) {
 }
 struct Timed {   // RAII: brackets the launches of one kernel family with CUDA events on the stream they are issued to
   Handle* H; int fam; cudaEvent_t a; cudaStream_t st;
-  Timed(Handle* h, int f, cudaStream_t s = nullptr) : H(h), fam(f), st(s ? s : h->stream) { a = get_event(H); cudaEventRecord(a, st); }
-  ~Timed() { cudaEvent_t b = get_event(H); cudaEventRecord(b, st); H->pending.push_back({fam, a, b}); if (H->pending.size() > 4096) flush_timers(H); }
+  bool on;
+  Timed(Handle* h, int f, cudaStream_t s = nullptr) : H(h), fam(f), st(s ? s : h->stream), on(!h->use_graph) { if (on) { a = get_event(H); cudaEventRecord(a, st); } }
+  ~Timed() { if (!on) return; cudaEvent_t b = get_event(H); cudaEventRecord(b, st); H->pending.push_back({fam, a, b}); if (H->pending.size() > 4096) flush_timers(H); }
 };
 
 // Device memory comes from the device's default stream-ordered pool, with the release threshold lifted: what
@@ -227,8 +235,10 @@ static int setup_batched(Handle* H) {
   return MCBA_OK;
 }
 
+static void drop_graphs(Handle* H);
 static int setup_stage(Handle* H, int stage) {
   if (H->batched) return setup_batched(H);
+  drop_graphs(H);   // every buffer the captured launches point to is reallocated below
   const StageDims sd = stage_dims(stage);
   if (sd.K == 0) { H->err = "stage must be 1..5"; return MCBA_ERR_INVALID; }
   if (sd.board && H->n_board <= 0) { H->err = "stage needs board blocks but n_board == 0"; return MCBA_ERR_INVALID; }
@@ -473,7 +483,41 @@ static int eval_observations(Handle* H, int which, double* target) {
   return reduce_rows(H, H->d_cost_bobs, H->nb, 1, 1, H->d_scalars + SC_COST);
 }
 
-static int eval_assemble(Handle* H, bool first) {
+static void drop_graphs(Handle* H) {
+  for (int k = 0; k < 4; ++k) {
+    if (H->g_step[k]) { cudaGraphExecDestroy(H->g_step[k]); H->g_step[k] = nullptr; }
+    if (H->g_asm[k]) { cudaGraphExecDestroy(H->g_asm[k]); H->g_asm[k] = nullptr; }
+  }
+}
+// Run `launch` once through stream capture and keep the instantiated graph in *slot; later calls replay it.
+// Falls back to direct launches (use_graph = false) if the capture is refused.
+template <class F> static int run_graphed(Handle* H, cudaGraphExec_t* slot, int64_t* n_nodes, F launch) {
+  if (!*slot) {
+    const int64_t l0 = H->n_launches;
+    H->capturing = true;
+    cudaError_t e = cudaStreamBeginCapture(H->stream, cudaStreamCaptureModeThreadLocal);
+    int rc = MCBA_OK;
+    if (e == cudaSuccess) rc = launch();
+    cudaGraph_t g = nullptr;
+    if (e == cudaSuccess) e = cudaStreamEndCapture(H->stream, &g);
+    H->capturing = false;
+    if (e == cudaSuccess && rc == MCBA_OK && g) e = cudaGraphInstantiate(slot, g, 0);
+    if (g) cudaGraphDestroy(g);
+    if (e != cudaSuccess || rc != MCBA_OK || !*slot) {     // not capturable here: direct launches from now on
+      cudaGetLastError();
+      *slot = nullptr; H->use_graph = false; drop_graphs(H);
+      H->n_launches = l0;
+      return launch();
+    }
+    *n_nodes = H->n_launches - l0;
+    H->n_launches = l0;
+  }
+  H->n_launches += *n_nodes;
+  CU(cudaGraphLaunch(*slot, H->stream));
+  return MCBA_OK;
+}
+
+static int eval_assemble_launch(Handle* H, bool first) {
   int rc;
   const StageDims sd = stage_dims(H->stage);
   // Two independent readers of the per-board-observation records: the e-block assembly (main stream) and the
@@ -542,13 +586,28 @@ static int eval_assemble(Handle* H, bool first) {
     ++H->n_launches;
     k_scale_diag<<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_Hoo, H->n_pose, H->d_FF, H->n_f, 1, H->opt.jacobi_scaling, H->opt.min_lm_diagonal, H->opt.max_lm_diagonal, H->d_scale_e, H->d_scale_f, H->d_diag_e, H->d_diag_f);
     CHECK_LAUNCH();
-    H->have_scale = true;
-    H->lm.reuse_diagonal = 1;   // the diagonal was just computed from this Jacobian
-  } else {
-    H->lm.reuse_diagonal = 0;
   }
+  if (H->n_ranks == 1) CU(cudaMemcpyAsync(H->h_pin + 8, H->d_scalars, SC_N * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+  return MCBA_OK;
+}
+
+static int eval_assemble(Handle* H, bool first) {
+  int rc;
+  const bool with_scale = first || !H->have_scale;
+  if (H->use_graph && !with_scale) {
+    const int key = 2 * H->cur + H->brec_par;
+    rc = run_graphed(H, &H->g_asm[key], &H->g_asm_launches[key], [&]() { return eval_assemble_launch(H, false); });
+  } else {
+    rc = eval_assemble_launch(H, with_scale);
+  }
+  if (rc) return rc;
+  if (with_scale) { H->have_scale = true; H->lm.reuse_diagonal = 1; }   // the diagonal was just computed from this Jacobian
+  else H->lm.reuse_diagonal = 0;
   std::vector<double> hs;
-  if ((rc = gather_scalars(H, H->d_scalars, SC_N, hs))) return rc;
+  if (H->n_ranks == 1) {
+    CU(cudaStreamSynchronize(H->stream));
+    hs.assign(H->h_pin + 8, H->h_pin + 8 + SC_N);
+  } else if ((rc = gather_scalars(H, H->d_scalars, SC_N, hs))) return rc;
   double cost = 0, xe2 = 0, gmax = 0;
   for (int r = 0; r < H->n_ranks; ++r) {
     const double* s = &hs[(size_t)r * SC_N];
@@ -581,7 +640,9 @@ static int cholesky_reduced(Handle* H) {
     static const bool ct_prof = getenv("MCBA_CHOL_PROF") != nullptr;
     if (ct_prof && !H->d_ct_prof) { CU(cudaMalloc((void**)&H->d_ct_prof, (size_t)CT_MAXT * 16 * sizeof(long long))); }
     if (ct_prof) CU(cudaMemsetAsync(H->d_ct_prof, 0, (size_t)CT_MAXT * 16 * sizeof(long long), H->stream));
-    CholTilesArgs a{H->d_S, n, H->d_zf, H->d_fail, H->d_ct_flags, ++H->ct_epoch, H->d_ct_dinv, H->d_ct_pbuf, H->d_ct_prof};
+    ++H->n_launches;
+    k_bump_epoch<<<1, 1, 0, H->stream>>>(H->d_ct_epoch);
+    CholTilesArgs a{H->d_S, n, H->d_zf, H->d_fail, H->d_ct_flags, H->d_ct_epoch, H->d_ct_dinv, H->d_ct_pbuf, H->d_ct_prof};
     void* args[] = {&a};
     ++H->n_launches;
     CU(cudaLaunchCooperativeKernel((void*)k_chol_tiles, dim3(ct_num_tiles(n)), dim3(CT_THREADS), args, CT_SMEM, H->stream));
@@ -602,24 +663,18 @@ static int cholesky_reduced(Handle* H) {
   return MCBA_OK;
 }
 
-// LevenbergMarquardtStrategy::ComputeStep + SchurComplementSolver + candidate point + candidate cost.
-// Outputs (host): step validity ingredients.
-static int compute_step(Handle* H, LmStep* out) {
+// The launch sequence of one trust-region step (no host synchronisation inside): what a CUDA graph captures.
+// Everything that changes from one iteration to the next reaches the kernels through device memory (the radius) or
+// through the graph key (which parameter copy / tile set is current).
+static int compute_step_launch(Handle* H) {
   int rc;
   const StageDims sd = stage_dims(H->stage);
+  CU(cudaMemcpyAsync(H->d_radius, H->h_pin, sizeof(double), cudaMemcpyHostToDevice, H->stream));
   CU(cudaMemsetAsync(H->d_fail, 0, sizeof(int), H->stream));
-  if (!H->lm.reuse_diagonal) {
-    Timed t(H, KF_REDUCE);
-    const int n = H->n_pose * 6 + H->n_f;
-    ++H->n_launches;
-    k_scale_diag<<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_Hoo, H->n_pose, H->d_FF, H->n_f, 0, H->opt.jacobi_scaling, H->opt.min_lm_diagonal, H->opt.max_lm_diagonal, H->d_scale_e, H->d_scale_f, H->d_diag_e, H->d_diag_f);
-    CHECK_LAUNCH();
-  }
-  H->lm.reuse_diagonal = 1;
   if (H->n_pose > 0) {
     Timed t(H, KF_EFACTOR);
     ++H->n_launches;
-    k_eblock_factor<<<H->n_pose, 128, 0, H->stream>>>(H->d_Hoo, H->d_Wt, H->d_scale_e, H->d_scale_f, H->d_diag_e, H->lm.radius, H->fl, H->d_tile_mask, H->mask_words, H->d_L, H->d_Z, H->d_fail);
+    k_eblock_factor<<<H->n_pose, 128, 0, H->stream>>>(H->d_Hoo, H->d_Wt, H->d_scale_e, H->d_scale_f, H->d_diag_e, H->d_radius, H->fl, H->d_tile_mask, H->mask_words, H->d_L, H->d_Z, H->d_fail);
     CHECK_LAUNCH();
   }
   {
@@ -653,7 +708,7 @@ static int compute_step(Handle* H, LmStep* out) {
     Timed t(H, KF_REDUCED);
     const int n = H->n_f * H->n_f + H->n_f;
     ++H->n_launches;
-    k_build_reduced<<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_FF, H->d_gf, H->d_ZtZ, H->d_scale_f, H->d_diag_f, H->lm.radius, H->fl, H->d_S, H->d_rhs);
+    k_build_reduced<<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_FF, H->d_gf, H->d_ZtZ, H->d_scale_f, H->d_diag_f, H->d_radius, H->fl, H->d_S, H->d_rhs);
     CHECK_LAUNCH();
   }
   if ((rc = cholesky_reduced(H))) return rc;
@@ -662,7 +717,7 @@ static int compute_step(Handle* H, LmStep* out) {
     Timed t(H, KF_BACKSUBST);
     if (H->n_pose > 0) {
       ++H->n_launches;
-      k_backsubst<<<(H->n_pose + 7) / 8, 256, 0, H->stream>>>(H->d_Z, H->d_L, H->d_zf, H->d_scale_e, H->d_diag_e, H->lm.radius, H->d_pose[H->cur], H->n_pose, H->fl, H->d_tile_mask, H->mask_words, H->d_pose[cand], H->d_part_e);
+      k_backsubst<<<(H->n_pose + 7) / 8, 256, 0, H->stream>>>(H->d_Z, H->d_L, H->d_zf, H->d_scale_e, H->d_diag_e, H->d_radius, H->d_pose[H->cur], H->n_pose, H->fl, H->d_tile_mask, H->mask_words, H->d_pose[cand], H->d_part_e);
     }
     ++H->n_launches;
     k_ffz<<<(H->n_f + 7) / 8, 256, 0, H->stream>>>(H->d_FF, H->d_scale_f, H->d_zf, H->n_f, H->d_hz);
@@ -673,12 +728,39 @@ static int compute_step(Handle* H, LmStep* out) {
   if ((rc = reduce_rows(H, H->d_part_e, H->n_pose, 4, 4, H->d_scalars + SC_PE0))) return rc;
   // candidate point: residual + Jacobian tiles into the alternate set (the cost comes with them), see eval_observations
   if ((rc = eval_observations(H, cand, H->d_brec_alt))) return rc;
-  H->cand_has_jac = true;
-  std::vector<double> hs;
   ++H->n_launches;
   k_flag_to_scalar<<<1, 1, 0, H->stream>>>(H->d_fail, H->p2p ? H->d_p2p_err : nullptr, H->d_scalars + SC_FAIL);
   CHECK_LAUNCH();
-  if ((rc = gather_scalars(H, H->d_scalars, SC_N, hs))) return rc;
+  if (H->n_ranks == 1) CU(cudaMemcpyAsync(H->h_pin + 8, H->d_scalars, SC_N * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+  return MCBA_OK;
+}
+
+// LevenbergMarquardtStrategy::ComputeStep + SchurComplementSolver + candidate point + candidate cost.
+// Outputs (host): step validity ingredients.
+static int compute_step(Handle* H, LmStep* out) {
+  int rc;
+  if (!H->lm.reuse_diagonal) {
+    Timed t(H, KF_REDUCE);
+    const int n = H->n_pose * 6 + H->n_f;
+    ++H->n_launches;
+    k_scale_diag<<<(n + 255) / 256, 256, 0, H->stream>>>(H->d_Hoo, H->n_pose, H->d_FF, H->n_f, 0, H->opt.jacobi_scaling, H->opt.min_lm_diagonal, H->opt.max_lm_diagonal, H->d_scale_e, H->d_scale_f, H->d_diag_e, H->d_diag_f);
+    CHECK_LAUNCH();
+  }
+  H->lm.reuse_diagonal = 1;
+  H->h_pin[0] = H->lm.radius;
+  if (H->use_graph) {
+    const int key = 2 * H->cur + H->brec_par;
+    rc = run_graphed(H, &H->g_step[key], &H->g_step_launches[key], [&]() { return compute_step_launch(H); });
+  } else {
+    rc = compute_step_launch(H);
+  }
+  if (rc) return rc;
+  H->cand_has_jac = true;
+  std::vector<double> hs;
+  if (H->n_ranks == 1) {
+    CU(cudaStreamSynchronize(H->stream));
+    hs.assign(H->h_pin + 8, H->h_pin + 8 + SC_N);
+  } else if ((rc = gather_scalars(H, H->d_scalars, SC_N, hs))) return rc;
   double py = 0, he = 0, sn = 0, xn = 0, cost = 0, h_fail = 0;
   for (int r = 0; r < H->n_ranks; ++r) {
     const double* s = &hs[(size_t)r * SC_N];
@@ -974,7 +1056,9 @@ void mcba_destroy(void* h) {
   dfree(H, &H->d_FF); dfree(H, &H->d_gf); dfree(H, &H->d_S); dfree(H, &H->d_rhs); dfree(H, &H->d_zf); dfree(H, &H->d_ZtZ); dfree(H, &H->d_hz);
   dfree(H, &H->d_syrk_partial); dfree(H, &H->d_pair_partial); dfree(H, &H->d_pair_rec); dfree(H, &H->d_part_e);
   dfree(H, &H->d_red_scratch); dfree(H, &H->d_scalars); dfree(H, &H->d_gather); dfree(H, &H->d_fail);
-  dfree(H, &H->d_jmat); dfree(H, &H->d_resmat); dfree(H, &H->d_ct_flags); dfree(H, &H->d_ct_dinv); dfree(H, &H->d_ct_pbuf); dfree(H, &H->d_tile_mask);
+  dfree(H, &H->d_jmat); dfree(H, &H->d_resmat); dfree(H, &H->d_ct_flags); dfree(H, &H->d_ct_dinv); dfree(H, &H->d_ct_pbuf); dfree(H, &H->d_tile_mask); dfree(H, &H->d_ct_epoch); dfree(H, &H->d_radius);
+  drop_graphs(H);
+  if (H->h_pin) { cudaFreeHost(H->h_pin); H->h_pin = nullptr; }
   dfree(H, &H->d_cam_ptr); dfree(H, &H->d_lm); dfree(H, &H->d_gate_jac); dfree(H, &H->d_active); dfree(H, &H->d_cam_fail); dfree(H, &H->d_n_active);
   dfree(H, &H->d_cam_sc); dfree(H, &H->d_cam_cost);
   for (int w = 0; w < 2; ++w) { dfree(H, &H->d_cam_pose[w]); dfree(H, &H->d_pose[w]); dfree(H, &H->d_board[w]); dfree(H, &H->d_intr[w]); }
@@ -1087,6 +1171,10 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
     H->ct_capacity = std::min(CT_MAXT, per_sm * H->n_sm); }
   if (dalloc(H, &H->d_ct_flags, (size_t)2 * CT_MAXT + 64) || dalloc(H, &H->d_ct_dinv, (size_t)CT_MAXNT * 512) || dalloc(H, &H->d_ct_pbuf, (size_t)CT_MAXT * 64)) return MCBA_ERR_CUDA;
   CU(cudaMemsetAsync(H->d_ct_flags, 0, ((size_t)2 * CT_MAXT + 64) * sizeof(unsigned), H->stream));
+  if (dalloc(H, &H->d_ct_epoch, (size_t)1) || dalloc(H, &H->d_radius, (size_t)1)) return MCBA_ERR_CUDA;
+  CU(cudaMemsetAsync(H->d_ct_epoch, 0, sizeof(unsigned), H->stream));
+  CU(cudaMallocHost((void**)&H->h_pin, (8 + SC_N) * sizeof(double)));
+  { const char* e = getenv("MCBA_GRAPH"); H->use_graph = !H->batched && !(e && atoi(e) == 0); }   // replay the per-iteration launch sequences as CUDA graphs
   mcba_default_options(&H->opt);
   mark("small allocs");
   const int rc = setup_stage(H, P->stage);
@@ -1133,6 +1221,7 @@ int mcba_comm_init(void* h, int rank, int n_ranks, const void* uid) {
   if (n_ranks < 1 || rank < 0 || rank >= n_ranks || n_ranks > 64) { H->err = "bad rank / n_ranks"; return MCBA_ERR_INVALID; }
   H->rank = rank; H->n_ranks = n_ranks;
   if (n_ranks == 1) return MCBA_OK;
+  H->use_graph = false; drop_graphs(H);   // with ranks the iteration stays host-launched (the peer-memory exchanges carry per-launch epochs)
   if (!g_nccl.load()) { H->err = "libnccl.so.2 not found"; return MCBA_ERR_NCCL; }
   CU(cudaSetDevice(H->device));
   nccl_uid_t id; std::memcpy(&id, uid, sizeof(id));
@@ -1168,8 +1257,11 @@ int mcba_solve_begin(void* h, const mcba_params* p, const mcba_options* opt) {
   if (H->batched) { H->err = "batched handle: use mcba_solve_batched"; return MCBA_ERR_INVALID; }
   CU(cudaSetDevice(H->device));
   mcba_options o; if (opt) o = *opt; else mcba_default_options(&o);
+  if (H->graph_opt_valid && std::memcmp(&H->graph_opt, &o, sizeof(o)) != 0) drop_graphs(H);   // options are baked into the captured arguments
+  H->graph_opt = o; H->graph_opt_valid = true;
   H->opt = o;
   int rc;
+  if (o.materialize_jacobian && (rc = ensure_jmat(H))) return rc;   // no allocation inside a stream capture
   if ((rc = upload_params(H, p))) return rc;
   H->x0_pose.assign(p->pose, p->pose + (size_t)H->n_pose * 6);
   H->x0_intr.assign(p->intrinsics, p->intrinsics + (size_t)H->n_cam * 9);
@@ -1209,7 +1301,7 @@ int mcba_solve_step(void* h) {
   if (d == LM_TERMINATED) return 0;
   if (d == LM_ACCEPT) {   // HandleSuccessfulStep
     H->cur = 1 - H->cur;
-    if (H->cand_has_jac) { std::swap(H->d_brec, H->d_brec_alt); rc = eval_assemble(H, false); }
+    if (H->cand_has_jac) { std::swap(H->d_brec, H->d_brec_alt); H->brec_par ^= 1; rc = eval_assemble(H, false); }
     else rc = eval_jacobian(H, false);
     if (rc == MCBA_ERR_NUMERIC) { H->lm.termination = MCBA_FAILURE; H->lm.done = 1; return 0; }
     if (rc) return rc;

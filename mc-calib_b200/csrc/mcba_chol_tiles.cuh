@@ -30,7 +30,7 @@ constexpr long long CT_TIMEOUT = 4000000000LL;
 struct CholTilesArgs {
   double* S; int n; double* z; int* fail;
   unsigned* flags;        // [2 * CT_MAXT + 64]: tile ready | partial ready | z ready
-  unsigned epoch;
+  const unsigned* epoch_p; // launch counter in device memory, bumped by k_bump_epoch before every launch (graph replay)
   double* dinv;           // [CT_MAXNT][512] inverses of the 8x8 diagonal blocks of L(j,j)
   double* pbuf;           // [CT_MAXT][64] backward-substitution contributions
   long long* prof;        // optional [CT_MAXT][8] %globaltimer stamps per tile (MCBA_CHOL_PROF)
@@ -54,6 +54,8 @@ __device__ __forceinline__ long long ct_now() { long long t; asm volatile("mov.u
 __host__ __device__ inline int ct_tile_id(int i, int j, int NT) { return j * (NT + 1) - j * (j - 1) / 2 + (i - j); }
 __host__ __device__ inline int ct_num_tiles(int n) { const int NT = (n + CT_B - 1) / CT_B; return NT * (NT + 3) / 2; }
 
+__global__ void k_bump_epoch(unsigned* e) { *e += 1u; }
+
 __global__ void __launch_bounds__(CT_THREADS, 2) k_chol_tiles(CholTilesArgs a) {
   extern __shared__ __align__(16) double sm[];
   double* T0 = sm;                       // [64][68] operand A of the updates, then this CTA's own tile X
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(CT_THREADS, 2) k_chol_tiles(CholTilesArgs a) {
   const int cv = min(CT_B, n - col0);
   double* S = a.S;
   unsigned* ready = a.flags; unsigned* pready = a.flags + CT_MAXT; unsigned* zready = a.flags + 2 * CT_MAXT;
-  const unsigned epoch = a.epoch;
+  const unsigned epoch = *a.epoch_p;
   const int my_tile = ct_tile_id(ti, tj, NT);
   const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;
   // this tile of A, in accumulator-fragment layout (issued now, consumed after the updates)

@@ -485,11 +485,12 @@ __global__ void k_eblock_grad(const double* __restrict__ pose, const double* __r
 // copy of the 6x6 in registers (cheaper than a barrier), then handles columns j = tid, tid+T, ...
 __global__ void __launch_bounds__(128) k_eblock_factor(const double* __restrict__ Hoo, const double* __restrict__ Wt,
                                                        const double* __restrict__ scale_e, const double* __restrict__ scale_f,
-                                                       const double* __restrict__ diag_e, double radius, FLayout Lo,
+                                                       const double* __restrict__ diag_e, const double* __restrict__ radius_p, FLayout Lo,
                                                        const unsigned* __restrict__ tile_mask, int mask_words,
                                                        double* __restrict__ Lout, double* __restrict__ Z,
                                                        int* __restrict__ fail) {
   const int o = blockIdx.x;
+  const double radius = *radius_p;   // device-resident: the step is replayed as a CUDA graph, only this value changes
   const unsigned* mk = tile_mask ? tile_mask + (size_t)o * mask_words : nullptr;   // columns outside the observed blocks are zero in Wt and stay zero in Z
   const int n_f = Lo.n_f, ldz = Lo.ldz;
   double L[36], se[6];
@@ -796,9 +797,10 @@ __global__ void __launch_bounds__(256) k_gather_p2p(P2PGatherArgs a) {
 // K2e: reduced system. S = s_f F^T F s_f + D_f^2 - Z^T Z (full symmetric, n_f x n_f, ld n_f); rhs = s_f g_f - Z^T y.
 __global__ void k_build_reduced(const double* __restrict__ FF, const double* __restrict__ gf,
                                 const double* __restrict__ ZtZ, const double* __restrict__ scale_f,
-                                const double* __restrict__ diag_f, double radius, FLayout L,
+                                const double* __restrict__ diag_f, const double* __restrict__ radius_p, FLayout L,
                                 double* __restrict__ S, double* __restrict__ rhs) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const double radius = *radius_p;
   const int n_f = L.n_f, ldz = L.ldz;
   if (idx < n_f * n_f) {
     const int i = idx / n_f, j = idx % n_f;
@@ -1159,11 +1161,12 @@ __global__ void __launch_bounds__(CC_THREADS) k_chol_coop(double* __restrict__ S
 // model_cost_change and of the norms. part[o] = {p.y, |p|^2 - sum D^2 z^2 + 2 p.q, sum (x - x+)^2, sum x+^2}
 __global__ void __launch_bounds__(256) k_backsubst(const double* __restrict__ Z, const double* __restrict__ Lall,
                                                    const double* __restrict__ zf, const double* __restrict__ scale_e,
-                                                   const double* __restrict__ diag_e, double radius,
+                                                   const double* __restrict__ diag_e, const double* __restrict__ radius_p,
                                                    const double* __restrict__ pose, int n_pose, FLayout Lo,
                                                    const unsigned* __restrict__ tile_mask, int mask_words,
                                                    double* __restrict__ pose_cand, double* __restrict__ part) {
   const int n_f = Lo.n_f, ldz = Lo.ldz;
+  const double radius = *radius_p;
   // one warp per e-block: q = Z_o z_f by lanes striding the columns (coalesced), xor-shuffle tree (fixed order)
   const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (o >= n_pose) return;
