@@ -326,6 +326,15 @@ def main():
     schur_reduce = h.schur_reduce_mode()
     ms, ms_wall, clocks, launches, stats, summ = timed_iterations(h, init, opt, args.steps, args.warmup, sample_clocks=True)
     value = n_obs_global * args.steps / (ms * 1e-3) / 1e6
+    ms_direct = None
+    if world == 1:
+        # single-rank handles replay the iteration as CUDA graphs: no per-kernel events there. The per-kernel breakdown
+        # (and the roofline's per-launch time of the fused kernel) comes from a second handle that launches kernel by kernel.
+        os.environ["MCBA_GRAPH"] = "0"
+        hd = mcba.Handle(prob, device=local_rank)
+        ms_direct, _, _, _, stats, _ = timed_iterations(hd, init, opt, args.steps, args.warmup)
+        hd.close()
+        del os.environ["MCBA_GRAPH"]
     fused_n, fused_ms = stats["resid_jac_fused"]
     fused_avg_ms = fused_ms / max(1, fused_n)
     achieved_tf = FLOPS_PER_OBS[STAGE] * n_obs_local / (fused_avg_ms * 1e-3) / 1e12 if fused_n else None
@@ -333,14 +342,19 @@ def main():
     # ---- K1 materialising variant (the HBM-roofline kernel of the north star): a few iterations, same data -----
     optm = bench_options(mcba, materialize_jacobian=1)
     pm = init.copy()
-    h.solve_begin(pm, optm)
+    os.environ["MCBA_GRAPH"] = "0"                 # per-kernel events needed
+    hm = mcba.Handle(prob, device=local_rank) if world == 1 else h
+    del os.environ["MCBA_GRAPH"]
+    hm.solve_begin(pm, optm)
     for _ in range(2):
-        h.solve_step()
-    h.reset_kernel_stats()
+        hm.solve_step()
+    hm.reset_kernel_stats()
     for _ in range(3):
-        h.solve_step()
-    stm = h.kernel_stats()
-    h.solve_end(pm)
+        hm.solve_step()
+    stm = hm.kernel_stats()
+    hm.solve_end(pm)
+    if hm is not h:
+        hm.close()
     mat_n, mat_ms = stm["resid_jac_materialize"]
     mat_avg_ms = mat_ms / max(1, mat_n)
     hbm_peak, hbm_src = measured_peaks()
@@ -507,6 +521,22 @@ def main():
                 del p3, i3, o3
             except Exception as e:
                 extra["config3_full"] = {"error": repr(e)}
+            # configs 1 and 2 (launch / synchronisation bound): ms per LM iteration, stage 5
+            try:
+                small = {}
+                for cfg in ("c1", "c2"):
+                    ps, is_, _, ss_, _ = synth.config_problem(cfg, 5)
+                    hsm = mcba.Handle(ps, device=local_rank)
+                    qs = is_.copy(); qs.intrinsics[:] = ss_.intr_init
+                    best = None
+                    for _ in range(3):
+                        m_, w_, _, _, _, _ = timed_iterations(hsm, qs, opt, 50, 5)
+                        best = w_ / 50 if best is None else min(best, w_ / 50)
+                    hsm.close()
+                    small[cfg] = {"observations": int(ps.n_obs), "ms_per_lm_iteration": best}
+                extra["small_configs"] = small
+            except Exception as e:
+                extra["small_configs"] = {"error": repr(e)}
             # config 5: 4 096 independent per-camera intrinsic refinements x 300 frames, one batched launch sequence
             try:
                 t0 = time.perf_counter()
@@ -565,6 +595,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "Mobs/s", "lm_iter_per_s": args.steps / (ms * 1e-3), "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "ms_per_step_wall": ms_wall / args.steps, "higher_is_better": True,
+            "launch_mode": "CUDA graphs (two per iteration: step, assembly)" if world == 1 else "direct launches (ranks exchange per-launch epochs)",
+            "ms_per_step_direct_launches": (ms_direct / args.steps) if ms_direct else None,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world, n_obs_global, fpg * world),
             "schur_reduce": schur_reduce,
@@ -593,6 +625,7 @@ def main():
                 "materialize_mobs_per_s": (n_obs_global / (mat_avg_ms * 1e-3) / 1e6) if mat_n else None,
                 "note": "all ranks run the pass concurrently on their shards: global observations / rank-0 kernel time"},
             "kernel_ms_per_step": {k: v[1] / args.steps for k, v in stats.items() if v[0]},
+            "kernel_ms_note": "CUDA events around each kernel family, from the direct-launch handle at N = 1 (graphs carry no per-kernel events)",
             "timed_region_note": f"{args.steps} iterations = {ms:.1f} ms of device time: a short burst-clock region, as long as a real solve of this shard (8-10 iterations)",
             "cpu_baseline": cpu,
             "pose_init": pose_init,
