@@ -493,45 +493,44 @@ __global__ void __launch_bounds__(128) k_eblock_factor(const double* __restrict_
   const double radius = *radius_p;   // device-resident: the step is replayed as a CUDA graph, only this value changes
   const unsigned* mk = tile_mask ? tile_mask + (size_t)o * mask_words : nullptr;   // columns outside the observed blocks are zero in Wt and stay zero in Z
   const int n_f = Lo.n_f, ldz = Lo.ldz;
-  double L[36], se[6];
+  double L[36], se[6], inv[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) se[k] = scale_e[(size_t)o * 6 + k];
 #pragma unroll
   for (int p = 0; p < 6; ++p)
 #pragma unroll
-    for (int r = 0; r < 6; ++r) L[p * 6 + r] = se[p] * Hoo[(size_t)o * 36 + p * 6 + r] * se[r];
+    for (int r = 0; r <= p; ++r) L[p * 6 + r] = se[p] * Hoo[(size_t)o * 36 + p * 6 + r] * se[r];
 #pragma unroll
   for (int k = 0; k < 6; ++k) L[k * 7] += diag_e[(size_t)o * 6 + k] / radius;
-  const bool ok = chol6(L);
-  if (!ok) { if (threadIdx.x == 0) atomicExch(fail, 1); }
+  const bool ok = chol6_inv(L, inv);    // every thread its own copy, in registers (cheaper than a barrier)
   if (threadIdx.x == 0) {
+    if (!ok) atomicExch(fail, 1);
 #pragma unroll
-    for (int e = 0; e < 36; ++e) Lout[(size_t)o * 36 + e] = ok ? L[e] : 0.0;
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+      for (int r = 0; r < 6; ++r) Lout[(size_t)o * 36 + p * 6 + r] = (ok && r <= p) ? L[p * 6 + r] : 0.0;
   }
   const double* W = Wt + (size_t)o * 6 * ldz;
   double* Zo = Z + (size_t)o * 6 * ldz;
+  // the 15 strictly-lower entries as scalars: the column loop below must not read the factor back from local memory
+  const double l10 = L[6], l20 = L[12], l21 = L[13], l30 = L[18], l31 = L[19], l32 = L[20], l40 = L[24], l41 = L[25], l42 = L[26],
+               l43 = L[27], l50 = L[30], l51 = L[31], l52 = L[32], l53 = L[33], l54 = L[34];
+  const double i0 = inv[0], i1 = inv[1], i2 = inv[2], i3 = inv[3], i4 = inv[4], i5 = inv[5];
   // one real column (f index j, then the rhs as j = n_f) per thread and pass; the padding columns of Z stay zero
-  constexpr int EF_U = 1;   // columns per thread in flight (4 measured slower: 127 vs 105 us, register pressure)
-  for (int j0 = threadIdx.x; j0 <= n_f; j0 += EF_U * blockDim.x) {
-    double w[EF_U][6]; int pc[EF_U];
-#pragma unroll
-    for (int u = 0; u < EF_U; ++u) {
-      const int j = j0 + u * blockDim.x;
-      pc[u] = (j < n_f) ? Lo.pcol(j) : Lo.rhs_col;
-      if (mk && j <= n_f && !((mk[pc[u] >> 8] >> ((pc[u] >> 3) & 31)) & 1u)) pc[u] = -1;      // inactive tile: skip
-      const double sf = (j < n_f) ? scale_f[j] : 1.0;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) w[u][k] = (j <= n_f && pc[u] >= 0) ? se[k] * W[k * ldz + pc[u]] * sf : 0.0;
-    }
-#pragma unroll
-    for (int u = 0; u < EF_U; ++u) {
-      const int j = j0 + u * blockDim.x;
-      if (j <= n_f && pc[u] >= 0) {
-        if (ok) chol6_fwd(L, w[u]);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) Zo[k * ldz + pc[u]] = ok ? w[u][k] : 0.0;
-      }
-    }
+  for (int j = threadIdx.x; j <= n_f; j += blockDim.x) {
+    const int pc = (j < n_f) ? Lo.pcol(j) : Lo.rhs_col;
+    if (mk && !((mk[pc >> 8] >> ((pc >> 3) & 31)) & 1u)) continue;      // inactive tile (sparse layout only)
+    const double sf = (j < n_f) ? scale_f[j] : 1.0;
+    const double b0 = se[0] * W[pc] * sf, b1 = se[1] * W[ldz + pc] * sf, b2 = se[2] * W[2 * ldz + pc] * sf,
+                 b3 = se[3] * W[3 * ldz + pc] * sf, b4 = se[4] * W[4 * ldz + pc] * sf, b5 = se[5] * W[5 * ldz + pc] * sf;
+    const double w0 = b0 * i0;
+    const double w1 = (b1 - l10 * w0) * i1;
+    const double w2 = (b2 - l20 * w0 - l21 * w1) * i2;
+    const double w3 = (b3 - l30 * w0 - l31 * w1 - l32 * w2) * i3;
+    const double w4 = (b4 - l40 * w0 - l41 * w1 - l42 * w2 - l43 * w3) * i4;
+    const double w5 = (b5 - l50 * w0 - l51 * w1 - l52 * w2 - l53 * w3 - l54 * w4) * i5;
+    Zo[pc] = ok ? w0 : 0.0; Zo[ldz + pc] = ok ? w1 : 0.0; Zo[2 * ldz + pc] = ok ? w2 : 0.0;
+    Zo[3 * ldz + pc] = ok ? w3 : 0.0; Zo[4 * ldz + pc] = ok ? w4 : 0.0; Zo[5 * ldz + pc] = ok ? w5 : 0.0;
   }
 }
 

@@ -384,6 +384,39 @@ MCBA_HD bool chol6(double* A) {
   }
   return true;
 }
+// Same factorisation without the early return (the array then stays in registers on the device): on a non-positive
+// pivot the flag is cleared and the factorisation continues with 1 in its place; inv[j] = 1 / L[j][j].
+MCBA_HD bool chol6_inv(double (&A)[36], double (&inv)[6]) {
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double s = A[j * 6 + j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) s -= A[j * 6 + k] * A[j * 6 + k];
+    const bool bad = !(s > 0.0) || !(s < DBL_MAX);
+    ok = ok && !bad;
+    const double l = bad ? 1.0 : sqrt(s);
+    const double il = 1.0 / l;
+    A[j * 6 + j] = l; inv[j] = il;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double t = A[i * 6 + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) t -= A[i * 6 + k] * A[j * 6 + k];
+      A[i * 6 + j] = t * il;
+    }
+  }
+  return ok;
+}
+MCBA_HD void chol6_fwd_inv(const double (&L)[36], const double (&inv)[6], double (&b)[6]) {   // b <- L^-1 b, no division
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double s = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * b[k];
+    b[i] = s * inv[i];
+  }
+}
 MCBA_HD void chol6_fwd(const double* L, double* b) {   // b <- L^-1 b
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
