@@ -327,11 +327,13 @@ def main():
     ms, ms_wall, clocks, launches, stats, summ = timed_iterations(h, init, opt, args.steps, args.warmup, sample_clocks=True)
     value = n_obs_global * args.steps / (ms * 1e-3) / 1e6
     ms_direct = None
-    if world == 1:
-        # single-rank handles replay the iteration as CUDA graphs: no per-kernel events there. The per-kernel breakdown
-        # (and the roofline's per-launch time of the fused kernel) comes from a second handle that launches kernel by kernel.
+    graphed = world == 1 or schur_reduce == "p2p"
+    if graphed:
+        # the iteration is replayed as CUDA graphs: no per-kernel events there. The per-kernel breakdown (and the
+        # roofline's per-launch time of the fused kernel) comes from a second handle that launches kernel by kernel.
         os.environ["MCBA_GRAPH"] = "0"
         hd = mcba.Handle(prob, device=local_rank)
+        comm_init(hd)
         ms_direct, _, _, _, stats, _ = timed_iterations(hd, init, opt, args.steps, args.warmup)
         hd.close()
         del os.environ["MCBA_GRAPH"]
@@ -343,7 +345,8 @@ def main():
     optm = bench_options(mcba, materialize_jacobian=1)
     pm = init.copy()
     os.environ["MCBA_GRAPH"] = "0"                 # per-kernel events needed
-    hm = mcba.Handle(prob, device=local_rank) if world == 1 else h
+    hm = mcba.Handle(prob, device=local_rank)
+    comm_init(hm)
     del os.environ["MCBA_GRAPH"]
     hm.solve_begin(pm, optm)
     for _ in range(2):
@@ -595,7 +598,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "Mobs/s", "lm_iter_per_s": args.steps / (ms * 1e-3), "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "ms_per_step_wall": ms_wall / args.steps, "higher_is_better": True,
-            "launch_mode": "CUDA graphs (two per iteration: step, assembly)" if world == 1 else "direct launches (ranks exchange per-launch epochs)",
+            "launch_mode": "CUDA graphs (two per iteration: step, assembly)" if graphed else "direct launches (NCCL fallback)",
             "ms_per_step_direct_launches": (ms_direct / args.steps) if ms_direct else None,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world, n_obs_global, fpg * world),
@@ -625,7 +628,7 @@ def main():
                 "materialize_mobs_per_s": (n_obs_global / (mat_avg_ms * 1e-3) / 1e6) if mat_n else None,
                 "note": "all ranks run the pass concurrently on their shards: global observations / rank-0 kernel time"},
             "kernel_ms_per_step": {k: v[1] / args.steps for k, v in stats.items() if v[0]},
-            "kernel_ms_note": "CUDA events around each kernel family, from the direct-launch handle at N = 1 (graphs carry no per-kernel events)",
+            "kernel_ms_note": "CUDA events around each kernel family, from a second, direct-launch handle (graphs carry no per-kernel events)",
             "timed_region_note": f"{args.steps} iterations = {ms:.1f} ms of device time: a short burst-clock region, as long as a real solve of this shard (8-10 iterations)",
             "cpu_baseline": cpu,
             "pose_init": pose_init,

@@ -117,6 +117,7 @@ struct Handle {
   // pair records and phase scalars over the same mechanism: one more exported buffer per rank [pair in | pair out | scalar table x 2]
   double* d_p2p_x = nullptr; double* peer_x[P2P_MAX_RANKS] = {nullptr}; size_t x_pair = 0; unsigned long long pair_epoch = 0, gather_epoch = 0;
   unsigned int* d_p2p_counter2 = nullptr;
+  unsigned long long* d_epochs = nullptr;   // [3] launch counters of the three exchanges (device memory: the kernels sit in replayed graphs)
   std::vector<void*> ipc_opened;
   // LM state
   mcba_options opt;
@@ -128,7 +129,7 @@ struct Handle {
   std::vector<double> x0_cam, x0_pose, x0_board, x0_intr;   // start point of the solve in flight (returned on FAILURE)
   int64_t n_obs_global = 0;
   // CUDA graphs of the two per-iteration launch sequences (single-rank handles): key = 2 * cur + brec_par
-  bool use_graph = false, capturing = false; int brec_par = 0;
+  bool use_graph = false, graph_env = false, capturing = false; int brec_par = 0;
   cudaGraphExec_t g_step[4] = {nullptr, nullptr, nullptr, nullptr}, g_asm[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t g_step_launches[4] = {0, 0, 0, 0}, g_asm_launches[4] = {0, 0, 0, 0};
   mcba_options graph_opt; bool graph_opt_valid = false;
@@ -340,7 +341,7 @@ static int setup_stage(Handle* H, int stage) {
     CU(cudaFuncSetAttribute(k_observations<ST, MODE_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     CU(cudaFuncSetAttribute(k_observations<ST, MODE_FROM_J>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     CU(cudaFuncSetAttribute(k_observations_stream<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, OBS_WARPS * (2 * CTX_SIZE + Cols<ST>::NC * TS) * 8));
-    CU(cudaFuncSetAttribute(k_eblock_assemble<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * H->ldz * 8));
+    CU(cudaFuncSetAttribute(k_eblock_assemble<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * (H->ldz + EA_PAD) * 8));
   });
   return MCBA_OK;
 }
@@ -423,23 +424,41 @@ static int ensure_jmat(Handle* H) {
   return MCBA_OK;
 }
 
+// The scalar gather over peer memory in two halves: the launch part (capturable: bump the device-side launch counter,
+// k_gather_p2p, copy BOTH halves of the double-buffered table to pinned host memory) and the host part (synchronise,
+// pick the half by the parity of the mirrored launch count).
+constexpr int PIN_GATHER = 32;
+static int gather_p2p_launch(Handle* H, const double* d_local, int m) {
+  Timed t(H, KF_NCCL);
+  P2PGatherArgs ga;
+  const size_t tab = 2 * H->x_pair;
+  for (int r = 0; r < P2P_MAX_RANKS; ++r) { ga.table[r] = H->peer_x[r] ? H->peer_x[r] + tab : nullptr; ga.flags[r] = H->peer_flags[r]; }
+  ga.local = d_local; ga.m = m; ga.rank = H->rank; ga.n_ranks = H->n_ranks; ga.epoch_p = H->d_epochs + 2; ga.err = H->d_p2p_err;
+  H->n_launches += 2;
+  k_bump_epoch64<<<1, 1, 0, H->stream>>>(H->d_epochs + 2);
+  k_gather_p2p<<<1, 256, 0, H->stream>>>(ga);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(H->h_pin + PIN_GATHER, H->d_p2p_x + tab, (size_t)2 * P2P_MAX_RANKS * P2P_GATHER_W * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+  return MCBA_OK;
+}
+static int gather_p2p_read(Handle* H, int m, std::vector<double>& host) {
+  ++H->gather_epoch;                       // mirrors the device-side counter: one gather executed per call
+  CU(cudaStreamSynchronize(H->stream));
+  host.assign((size_t)m * H->n_ranks, 0.0);
+  const double* tabp = H->h_pin + PIN_GATHER + (H->gather_epoch & 1ull) * P2P_MAX_RANKS * P2P_GATHER_W;
+  for (int r = 0; r < H->n_ranks; ++r) for (int i = 0; i < m; ++i) host[(size_t)r * m + i] = tabp[(size_t)r * P2P_GATHER_W + i];
+  return MCBA_OK;
+}
+
 // gather [m] doubles from every rank (rank-major) to the host; world 1: plain D2H
 static int gather_scalars(Handle* H, const double* d_local, int m, std::vector<double>& host) {
   host.assign((size_t)m * H->n_ranks, 0.0);
   if (H->n_ranks == 1) {
     CU(cudaMemcpyAsync(host.data(), d_local, m * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
   } else if (H->p2p && m <= P2P_GATHER_W) {
-    { Timed t(H, KF_NCCL);
-      P2PGatherArgs ga;
-      const size_t tab = 2 * H->x_pair;
-      for (int r = 0; r < P2P_MAX_RANKS; ++r) { ga.table[r] = H->peer_x[r] ? H->peer_x[r] + tab : nullptr; ga.flags[r] = H->peer_flags[r]; }
-      ga.local = d_local; ga.m = m; ga.rank = H->rank; ga.n_ranks = H->n_ranks; ga.epoch = ++H->gather_epoch; ga.err = H->d_p2p_err;
-      ++H->n_launches;
-      k_gather_p2p<<<1, 256, 0, H->stream>>>(ga);
-      CU(cudaGetLastError()); }
-    const double* tabp = H->d_p2p_x + 2 * H->x_pair + (H->gather_epoch & 1ull) * P2P_MAX_RANKS * P2P_GATHER_W;
-    for (int r = 0; r < H->n_ranks; ++r)
-      CU(cudaMemcpyAsync(host.data() + (size_t)r * m, tabp + (size_t)r * P2P_GATHER_W, m * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+    int rc;
+    if ((rc = gather_p2p_launch(H, d_local, m))) return rc;
+    return gather_p2p_read(H, m, host);
   } else {
     { Timed t(H, KF_NCCL);
       const int rc = g_nccl.AllGather(d_local, H->d_gather, m, NCCL_DOUBLE, H->comm, H->stream);
@@ -543,7 +562,8 @@ static int eval_assemble_launch(Handle* H, bool first) {
     Timed t(H, KF_NCCL, sb);
     P2PVecArgs va;
     for (int r = 0; r < P2P_MAX_RANKS; ++r) { va.in[r] = H->peer_x[r]; va.out[r] = H->peer_x[r] ? H->peer_x[r] + H->x_pair : nullptr; va.flags[r] = H->peer_flags[r]; }
-    va.n = H->n_pair * H->NE; va.rank = H->rank; va.n_ranks = H->n_ranks; va.epoch = ++H->pair_epoch; va.counter = H->d_p2p_counter2; va.err = H->d_p2p_err;
+    k_bump_epoch64<<<1, 1, 0, sb>>>(H->d_epochs + 1);
+    va.n = H->n_pair * H->NE; va.rank = H->rank; va.n_ranks = H->n_ranks; va.epoch_p = H->d_epochs + 1; va.counter = H->d_p2p_counter2; va.err = H->d_p2p_err;
     ++H->n_launches;   // no grid-wide barrier inside (the CTAs only wait for other ranks' flags): an ordinary launch
     k_allreduce_p2p<<<std::min(H->n_sm, std::max(1, (va.n / H->n_ranks + 255) / 256)), 256, 0, sb>>>(va);
     CHECK_LAUNCH();
@@ -563,7 +583,7 @@ static int eval_assemble_launch(Handle* H, bool first) {
   if (H->n_pose > 0) {
     Timed t(H, KF_EASSEMBLE);
     ++H->n_launches;
-    DISPATCH_STAGE(H->stage, (k_eblock_assemble<ST><<<H->n_pose, 192, 6 * H->ldz * 8, H->stream>>>(
+    DISPATCH_STAGE(H->stage, (k_eblock_assemble<ST><<<H->n_pose, 192, 6 * (H->ldz + EA_PAD) * 8, H->stream>>>(
         H->d_bobs, H->d_pose_bobs_ptr, H->d_brec, H->fl, H->d_tile_mask, H->mask_words, H->d_Hoo, H->d_Wt)));
     CHECK_LAUNCH();
   }
@@ -588,6 +608,7 @@ static int eval_assemble_launch(Handle* H, bool first) {
     CHECK_LAUNCH();
   }
   if (H->n_ranks == 1) CU(cudaMemcpyAsync(H->h_pin + 8, H->d_scalars, SC_N * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+  else if (H->p2p && (rc = gather_p2p_launch(H, H->d_scalars, SC_N))) return rc;
   return MCBA_OK;
 }
 
@@ -607,7 +628,8 @@ static int eval_assemble(Handle* H, bool first) {
   if (H->n_ranks == 1) {
     CU(cudaStreamSynchronize(H->stream));
     hs.assign(H->h_pin + 8, H->h_pin + 8 + SC_N);
-  } else if ((rc = gather_scalars(H, H->d_scalars, SC_N, hs))) return rc;
+  } else if (H->p2p) { if ((rc = gather_p2p_read(H, SC_N, hs))) return rc; }
+  else if ((rc = gather_scalars(H, H->d_scalars, SC_N, hs))) return rc;
   double cost = 0, xe2 = 0, gmax = 0;
   for (int r = 0; r < H->n_ranks; ++r) {
     const double* s = &hs[(size_t)r * SC_N];
@@ -692,7 +714,8 @@ static int compute_step_launch(Handle* H) {
       P2PArgs pa;
       for (int r = 0; r < P2P_MAX_RANKS; ++r) { pa.stage[r] = H->peer_stage[r]; pa.ZtZ[r] = H->peer_ZtZ[r]; pa.flags[r] = H->peer_flags[r]; }
       pa.partial = H->d_syrk_partial; pa.nsplit = H->syrk_nsplit;
-      pa.rank = H->rank; pa.n_ranks = H->n_ranks; pa.epoch = ++H->p2p_epoch; pa.n_tiles = H->syrk_tiles; pa.nt = H->syrk_nt; pa.ldz = H->ldz;
+      k_bump_epoch64<<<1, 1, 0, H->stream>>>(H->d_epochs);
+      pa.rank = H->rank; pa.n_ranks = H->n_ranks; pa.epoch_p = H->d_epochs; pa.n_tiles = H->syrk_tiles; pa.nt = H->syrk_nt; pa.ldz = H->ldz;
       pa.counter = H->d_p2p_counter; pa.err = H->d_p2p_err;
       // the CTAs of this kernel wait for one another (and for the peers' kernels): a cooperative launch makes the
       // driver guarantee co-residency of the whole grid (it fails with an error instead of deadlocking)
@@ -732,6 +755,7 @@ static int compute_step_launch(Handle* H) {
   k_flag_to_scalar<<<1, 1, 0, H->stream>>>(H->d_fail, H->p2p ? H->d_p2p_err : nullptr, H->d_scalars + SC_FAIL);
   CHECK_LAUNCH();
   if (H->n_ranks == 1) CU(cudaMemcpyAsync(H->h_pin + 8, H->d_scalars, SC_N * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+  else if (H->p2p && (rc = gather_p2p_launch(H, H->d_scalars, SC_N))) return rc;
   return MCBA_OK;
 }
 
@@ -760,7 +784,8 @@ static int compute_step(Handle* H, LmStep* out) {
   if (H->n_ranks == 1) {
     CU(cudaStreamSynchronize(H->stream));
     hs.assign(H->h_pin + 8, H->h_pin + 8 + SC_N);
-  } else if ((rc = gather_scalars(H, H->d_scalars, SC_N, hs))) return rc;
+  } else if (H->p2p) { if ((rc = gather_p2p_read(H, SC_N, hs))) return rc; }
+  else if ((rc = gather_scalars(H, H->d_scalars, SC_N, hs))) return rc;
   double py = 0, he = 0, sn = 0, xn = 0, cost = 0, h_fail = 0;
   for (int r = 0; r < H->n_ranks; ++r) {
     const double* s = &hs[(size_t)r * SC_N];
@@ -853,7 +878,7 @@ static int setup_p2p(Handle* H) {
   static range_fn get_range = []() -> range_fn { void* l = dlopen("libcuda.so.1", RTLD_NOW); return l ? (range_fn)dlsym(l, "cuMemGetAddressRange_v2") : nullptr; }();
   const int N = H->n_ranks;
   if (!H->d_p2p_counter) {
-    if (dalloc(H, &H->d_p2p_counter, (size_t)2) || dalloc(H, &H->d_p2p_counter2, (size_t)2) || dalloc(H, &H->d_p2p_err, (size_t)1)) return MCBA_ERR_CUDA;
+    if (dalloc(H, &H->d_p2p_counter, (size_t)2) || dalloc(H, &H->d_p2p_counter2, (size_t)2) || dalloc(H, &H->d_p2p_err, (size_t)1) || dalloc(H, &H->d_epochs, (size_t)4)) return MCBA_ERR_CUDA;
     CU(cudaMemset(H->d_p2p_counter, 0, 2 * sizeof(unsigned int))); CU(cudaMemset(H->d_p2p_counter2, 0, 2 * sizeof(unsigned int))); CU(cudaMemset(H->d_p2p_err, 0, sizeof(int)));
   }
   // exported buffers come from the pool and are cleared BEFORE their handles are published (a peer may start writing
@@ -875,6 +900,7 @@ static int setup_p2p(Handle* H) {
   CU(cudaMemset(H->d_p2p_x, 0, x_doubles * sizeof(double)));
   CU(cudaDeviceSynchronize());
   H->p2p_epoch = 0; H->pair_epoch = 0; H->gather_epoch = 0;
+  CU(cudaMemset(H->d_epochs, 0, 4 * sizeof(unsigned long long)));
   IpcRecord mine; std::memset(&mine, 0, sizeof(mine));
   void* ptrs[4] = {H->d_p2p_stage, H->d_ZtZ, H->d_p2p_flags, H->d_p2p_x};
   mine.ok = get_range ? 1 : 0;
@@ -1043,7 +1069,7 @@ void mcba_destroy(void* h) {
   close_p2p(H);
   release_exported(H);
   if (H->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(H->comm);
-  dfree(H, &H->d_p2p_counter); dfree(H, &H->d_p2p_counter2); dfree(H, &H->d_p2p_err);
+  dfree(H, &H->d_p2p_counter); dfree(H, &H->d_p2p_counter2); dfree(H, &H->d_p2p_err); dfree(H, &H->d_epochs);
   for (auto& p : H->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : H->free_events) cudaEventDestroy(e);
   if (H->tm_a) { cudaEventDestroy(H->tm_a); cudaEventDestroy(H->tm_b); }
@@ -1173,8 +1199,8 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   CU(cudaMemsetAsync(H->d_ct_flags, 0, ((size_t)2 * CT_MAXT + 64) * sizeof(unsigned), H->stream));
   if (dalloc(H, &H->d_ct_epoch, (size_t)1) || dalloc(H, &H->d_radius, (size_t)1)) return MCBA_ERR_CUDA;
   CU(cudaMemsetAsync(H->d_ct_epoch, 0, sizeof(unsigned), H->stream));
-  CU(cudaMallocHost((void**)&H->h_pin, (8 + SC_N) * sizeof(double)));
-  { const char* e = getenv("MCBA_GRAPH"); H->use_graph = !H->batched && !(e && atoi(e) == 0); }   // replay the per-iteration launch sequences as CUDA graphs
+  CU(cudaMallocHost((void**)&H->h_pin, (PIN_GATHER + 2 * P2P_MAX_RANKS * P2P_GATHER_W) * sizeof(double)));
+  { const char* e = getenv("MCBA_GRAPH"); H->graph_env = !H->batched && !(e && atoi(e) == 0); H->use_graph = H->graph_env; }   // replay the per-iteration launch sequences as CUDA graphs
   mcba_default_options(&H->opt);
   mark("small allocs");
   const int rc = setup_stage(H, P->stage);
@@ -1205,6 +1231,7 @@ int mcba_set_stage(void* h, int stage) {
   if (rc) return rc;
   CU(cudaDeviceSynchronize());
   if (H->n_ranks > 1 && (rc = setup_p2p(H))) return rc;   // collective: every rank changes stage
+  H->use_graph = H->graph_env && (H->n_ranks == 1 || H->p2p);
   return MCBA_OK;
 }
 
@@ -1221,7 +1248,7 @@ int mcba_comm_init(void* h, int rank, int n_ranks, const void* uid) {
   if (n_ranks < 1 || rank < 0 || rank >= n_ranks || n_ranks > 64) { H->err = "bad rank / n_ranks"; return MCBA_ERR_INVALID; }
   H->rank = rank; H->n_ranks = n_ranks;
   if (n_ranks == 1) return MCBA_OK;
-  H->use_graph = false; drop_graphs(H);   // with ranks the iteration stays host-launched (the peer-memory exchanges carry per-launch epochs)
+  H->use_graph = false; drop_graphs(H);   // decided again below: graphs with ranks need every exchange to go over peer memory
   if (!g_nccl.load()) { H->err = "libnccl.so.2 not found"; return MCBA_ERR_NCCL; }
   CU(cudaSetDevice(H->device));
   nccl_uid_t id; std::memcpy(&id, uid, sizeof(id));
@@ -1248,6 +1275,7 @@ int mcba_comm_init(void* h, int rank, int n_ranks, const void* uid) {
     flush_timers(H);
     for (int k = 0; k < KF_COUNT; ++k) { H->kf_launches[k] = 0; H->kf_ms[k] = 0; }
     if ((rc = setup_p2p(H))) return rc;
+    H->use_graph = H->graph_env && H->p2p;
   }
   return MCBA_OK;
 }

@@ -298,14 +298,15 @@ struct FLayout {
 // ---------------------------------------------------------------------------------------------
 // K2a: per e-block sums over its board observations (fixed order): Hoo (6x6 full), and the dense row block
 // Wt[o] = [E^T F (6 x n_f) | E^T r] with leading dimension ldz.
+constexpr int EA_PAD = 6;   // row pitch of the e-block assembly's shared tile: with ldz a multiple of 16 doubles the six rows of a column would share a bank
 template <int STAGE>
 __global__ void __launch_bounds__(192) k_eblock_assemble(const int4* __restrict__ bobs, const int* __restrict__ pose_bobs_ptr,
                                                          const double* __restrict__ brec, FLayout L,
                                                          const unsigned* __restrict__ tile_mask, int mask_words,
                                                          double* __restrict__ Hoo, double* __restrict__ Wt) {
   typedef Cols<STAGE> C;
-  extern __shared__ double W[];   // [6][ldz]
-  const int ldz = L.ldz;
+  extern __shared__ double W[];   // [6][lds], lds = ldz + EA_PAD: the six e-rows of one column land in different banks
+  const int ldz = L.ldz, lds = L.ldz + EA_PAD;
   const int o = blockIdx.x, tid = threadIdx.x;
   // only the 8-column tiles of the blocks this e-block observes are ever non-zero (tile_mask, static per stage): the
   // others are neither cleared here nor written to Wt, which was zeroed once when it was allocated
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(192) k_eblock_assemble(const int4* __restrict_
     const int t = c >> 3;
     if (!mk || ((mk[t >> 5] >> (t & 31)) & 1u)) {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) W[k * ldz + c] = 0.0;
+      for (int k = 0; k < 6; ++k) W[k * lds + c] = 0.0;
     }
   }
   __syncthreads();
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(192) k_eblock_assemble(const int4* __restrict_
         }
 #pragma unroll
       for (int u = 0; u < EA_U; ++u)
-        if (b + u < b1) W[k * ldz + gc[u]] += v[u];
+        if (b + u < b1) W[k * lds + gc[u]] += v[u];
     }
   } else if (tid < 6 * C::WF + 42) {
     const int e = tid - 6 * C::WF;
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(192) k_eblock_assemble(const int4* __restrict_
       for (int u = 0; u < EA_U; ++u) if (b + u < b1) s += v[u];
     }
     if (e < 36) Hoo[(size_t)o * 36 + e] = s;
-    else W[(e - 36) * ldz + L.rhs_col] = s;
+    else W[(e - 36) * lds + L.rhs_col] = s;
   }
   __syncthreads();
   double* dst = Wt + (size_t)o * 6 * ldz;
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(192) k_eblock_assemble(const int4* __restrict_
     const int t = c >> 3;
     if (!mk || ((mk[t >> 5] >> (t & 31)) & 1u)) {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) dst[k * ldz + c] = W[k * ldz + c];
+      for (int k = 0; k < 6; ++k) dst[k * ldz + c] = W[k * lds + c];
     }
   }
 }
@@ -655,7 +656,7 @@ struct P2PArgs {
   unsigned long long* flags[P2P_MAX_RANKS];    // each [2][P2P_MAX_RANKS]: "staged" and "written" epochs per source rank
   const double* partial;                       // this rank's split-K partials
   int nsplit, rank, n_ranks;
-  unsigned long long epoch;
+  const unsigned long long* epoch_p;   // launch counter in device memory (bumped before every launch: graph replay)
   int n_tiles, nt, ldz;
   unsigned int* counter;                       // [2], zero between launches
   int* err;
@@ -670,9 +671,11 @@ __device__ __forceinline__ bool p2p_wait(const volatile unsigned long long* flag
   __threadfence_system();
   return true;
 }
+__global__ void k_bump_epoch64(unsigned long long* e) { *e += 1ull; }
 __device__ __forceinline__ void p2p_publish(const P2PArgs& a, int slot) {
   __threadfence_system();
-  for (int p = 0; p < a.n_ranks; ++p) ((volatile unsigned long long*)a.flags[p])[slot * P2P_MAX_RANKS + a.rank] = a.epoch;
+  const unsigned long long epoch = *a.epoch_p;
+  for (int p = 0; p < a.n_ranks; ++p) ((volatile unsigned long long*)a.flags[p])[slot * P2P_MAX_RANKS + a.rank] = epoch;
 }
 // (row, column) in ZtZ of element idx of the staging layout; false for entries nobody consumes
 __device__ __forceinline__ bool p2p_locate(int64_t idx, int nt, int ldz, int* i, int* j) {
@@ -684,6 +687,7 @@ __device__ __forceinline__ bool p2p_locate(int64_t idx, int nt, int ldz, int* i,
 }
 __global__ void __launch_bounds__(256) k_syrk_sum_p2p(P2PArgs a) {
   __shared__ int ok_s;
+  const unsigned long long epoch = *a.epoch_p;
   const int64_t total = (int64_t)a.n_tiles * SY_T * SY_T;
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gstride = (int64_t)gridDim.x * blockDim.x;
   // phase 1
@@ -700,7 +704,7 @@ __global__ void __launch_bounds__(256) k_syrk_sum_p2p(P2PArgs a) {
   volatile unsigned long long* my_flags = a.flags[a.rank];
   if (threadIdx.x == 0) {
     if (atomicAdd(a.counter, 1u) == gridDim.x - 1) { a.counter[0] = 0; p2p_publish(a, 0); }
-    ok_s = p2p_wait(my_flags, a.n_ranks, a.epoch, a.err) ? 1 : 0;
+    ok_s = p2p_wait(my_flags, a.n_ranks, epoch, a.err) ? 1 : 0;
   }
   __syncthreads();
   // phase 2
@@ -727,7 +731,7 @@ __global__ void __launch_bounds__(256) k_syrk_sum_p2p(P2PArgs a) {
   if (threadIdx.x == 0 && atomicAdd(a.counter + 1, 1u) == gridDim.x - 1) {
     a.counter[1] = 0;
     p2p_publish(a, 1);
-    p2p_wait(my_flags + P2P_MAX_RANKS, a.n_ranks, a.epoch, a.err);
+    p2p_wait(my_flags + P2P_MAX_RANKS, a.n_ranks, epoch, a.err);
   }
 }
 
@@ -740,18 +744,19 @@ __global__ void __launch_bounds__(256) k_syrk_sum_p2p(P2PArgs a) {
 constexpr int P2P_CH_PAIR = 2, P2P_CH_GATHER = 4, P2P_FLAG_SLOTS = 6, P2P_GATHER_W = 16;
 struct P2PVecArgs {
   double* in[P2P_MAX_RANKS]; double* out[P2P_MAX_RANKS]; unsigned long long* flags[P2P_MAX_RANKS];
-  int n, rank, n_ranks; unsigned long long epoch; unsigned int* counter; int* err;
+  int n, rank, n_ranks; const unsigned long long* epoch_p; unsigned int* counter; int* err;
 };
 __global__ void __launch_bounds__(256) k_allreduce_p2p(P2PVecArgs a) {
   __shared__ int ok_s;
+  const unsigned long long epoch = *a.epoch_p;
   volatile unsigned long long* my_flags = a.flags[a.rank];
   // the input was written by the previous kernel of this stream: publish it, then wait for everybody's
   if (threadIdx.x == 0) {
     if (blockIdx.x == 0) {
       __threadfence_system();
-      for (int p = 0; p < a.n_ranks; ++p) ((volatile unsigned long long*)a.flags[p])[P2P_CH_PAIR * P2P_MAX_RANKS + a.rank] = a.epoch;
+      for (int p = 0; p < a.n_ranks; ++p) ((volatile unsigned long long*)a.flags[p])[P2P_CH_PAIR * P2P_MAX_RANKS + a.rank] = epoch;
     }
-    ok_s = p2p_wait(my_flags + P2P_CH_PAIR * P2P_MAX_RANKS, a.n_ranks, a.epoch, a.err) ? 1 : 0;
+    ok_s = p2p_wait(my_flags + P2P_CH_PAIR * P2P_MAX_RANKS, a.n_ranks, epoch, a.err) ? 1 : 0;
   }
   __syncthreads();
   if (ok_s) {
@@ -773,24 +778,25 @@ __global__ void __launch_bounds__(256) k_allreduce_p2p(P2PVecArgs a) {
   if (threadIdx.x == 0 && atomicAdd(a.counter, 1u) == gridDim.x - 1) {
     a.counter[0] = 0;
     __threadfence_system();
-    for (int p = 0; p < a.n_ranks; ++p) ((volatile unsigned long long*)a.flags[p])[(P2P_CH_PAIR + 1) * P2P_MAX_RANKS + a.rank] = a.epoch;
-    p2p_wait(my_flags + (P2P_CH_PAIR + 1) * P2P_MAX_RANKS, a.n_ranks, a.epoch, a.err);
+    for (int p = 0; p < a.n_ranks; ++p) ((volatile unsigned long long*)a.flags[p])[(P2P_CH_PAIR + 1) * P2P_MAX_RANKS + a.rank] = epoch;
+    p2p_wait(my_flags + (P2P_CH_PAIR + 1) * P2P_MAX_RANKS, a.n_ranks, epoch, a.err);
   }
 }
 struct P2PGatherArgs {
   double* table[P2P_MAX_RANKS]; unsigned long long* flags[P2P_MAX_RANKS];
-  const double* local; int m, rank, n_ranks; unsigned long long epoch; int* err;
+  const double* local; int m, rank, n_ranks; const unsigned long long* epoch_p; int* err;
 };
 __global__ void __launch_bounds__(256) k_gather_p2p(P2PGatherArgs a) {
-  const int region = (int)(a.epoch & 1ull) * P2P_MAX_RANKS * P2P_GATHER_W;
+  const unsigned long long epoch = *a.epoch_p;
+  const int region = (int)(epoch & 1ull) * P2P_MAX_RANKS * P2P_GATHER_W;
   for (int t = threadIdx.x; t < a.m * a.n_ranks; t += blockDim.x) {
     const int p = t / a.m, i = t % a.m;
     a.table[p][region + a.rank * P2P_GATHER_W + i] = a.local[i];
   }
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x < a.n_ranks) ((volatile unsigned long long*)a.flags[threadIdx.x])[P2P_CH_GATHER * P2P_MAX_RANKS + a.rank] = a.epoch;
-  if (threadIdx.x == 0) p2p_wait((volatile unsigned long long*)a.flags[a.rank] + P2P_CH_GATHER * P2P_MAX_RANKS, a.n_ranks, a.epoch, a.err);
+  if (threadIdx.x < a.n_ranks) ((volatile unsigned long long*)a.flags[threadIdx.x])[P2P_CH_GATHER * P2P_MAX_RANKS + a.rank] = epoch;
+  if (threadIdx.x == 0) p2p_wait((volatile unsigned long long*)a.flags[a.rank] + P2P_CH_GATHER * P2P_MAX_RANKS, a.n_ranks, epoch, a.err);
 }
 
 // K2e: reduced system. S = s_f F^T F s_f + D_f^2 - Z^T Z (full symmetric, n_f x n_f, ld n_f); rhs = s_f g_f - Z^T y.
