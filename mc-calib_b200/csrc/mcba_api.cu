@@ -13,6 +13,7 @@
 #include "mcba_chol_tiles.cuh"
 #include "mcba_syrk.cuh"
 #include "mcba_obs_stream.cuh"
+#include "mcba_obs_fused.cuh"
 
 #include <dlfcn.h>
 #include <algorithm>
@@ -130,6 +131,7 @@ struct Handle {
   int64_t n_obs_global = 0;
   // CUDA graphs of the two per-iteration launch sequences (single-rank handles): key = 2 * cur + brec_par
   bool use_graph = false, graph_env = false, capturing = false; int brec_par = 0;
+  int k1_variant = 0;                // fused observation kernel of this handle (launch_obs)
   cudaGraphExec_t g_step[4] = {nullptr, nullptr, nullptr, nullptr}, g_asm[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t g_step_launches[4] = {0, 0, 0, 0}, g_asm_launches[4] = {0, 0, 0, 0};
   mcba_options graph_opt; bool graph_opt_valid = false;
@@ -341,6 +343,7 @@ static int setup_stage(Handle* H, int stage) {
     CU(cudaFuncSetAttribute(k_observations<ST, MODE_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     CU(cudaFuncSetAttribute(k_observations<ST, MODE_FROM_J>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     CU(cudaFuncSetAttribute(k_observations_stream<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, OBS_WARPS * (2 * CTX_SIZE + Cols<ST>::NC * TS) * 8));
+    CU(cudaFuncSetAttribute(k_observations_fused<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem<ST>::BYTES));
     CU(cudaFuncSetAttribute(k_eblock_assemble<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * (H->ldz + EA_PAD) * 8));
   });
   return MCBA_OK;
@@ -385,6 +388,7 @@ static int launch_prep(Handle* H, int which) {
   return MCBA_OK;
 }
 
+static int g_k1_variant = -1;   // mcba_debug_set_k1: overrides MCBA_K1 for handles created afterwards
 static int grid_for(const Handle* H, int nb, int ctas_per_sm) { return std::max(1, std::min((nb + OBS_WARPS - 1) / OBS_WARPS, H->n_sm * ctas_per_sm)); }
 
 template <int MODE> static int launch_obs(Handle* H, int which, double huber_a) {
@@ -392,17 +396,27 @@ template <int MODE> static int launch_obs(Handle* H, int which, double huber_a) 
   const int fam = MODE == MODE_FUSED ? KF_FUSED : MODE == MODE_MATERIALIZE ? KF_MATERIALIZE : MODE == MODE_FROM_J ? KF_FROM_J : KF_COST;
   Timed t(H, fam);
   ObsArgs a = obs_args(H, which, huber_a);
-  // MCBA_K1_STREAM=1: the streaming kernel packs the tail of one board observation and the head of the next into one
-  // warp pass (25 % fewer Jacobian passes on 48-corner boards). Measured SLOWER than one observation per pass sequence
-  // (0.96 vs 0.88 ms): kept as an opt-in experiment, parity-tested
-  static const bool stream_env = []() { const char* e = getenv("MCBA_K1_STREAM"); return e && atoi(e) != 0; }();
-  if (MODE == MODE_FUSED && stream_env && !a.gate) {
+  // Variant of the fused kernel, fixed per handle at mcba_create (MCBA_K1 / mcba_debug_set_k1): 0 = k_observations_fused
+  // (prefetched copy-free context, group-pair cover of the triangle; the default), 1 = the first version
+  // k_observations<S, MODE_FUSED> (also what gated / batched handles run), 2 = the streaming experiment (tails of
+  // consecutive board observations share a warp pass; measured slower than version 1, 0.96 vs 0.88 ms).
+  if (MODE == MODE_FUSED && H->k1_variant == 2 && !a.gate) {
     DISPATCH_STAGE(H->stage, {
       const int sm = OBS_WARPS * (2 * CTX_SIZE + Cols<ST>::NC * TS) * 8;
       const int per_sm = std::min(3, std::max(1, (227 * 1024) / (sm + 1024)));
       const int grid = std::max(1, std::min((H->nb + 2 * OBS_WARPS - 1) / (2 * OBS_WARPS), H->n_sm * per_sm));
       ++H->n_launches;
       k_observations_stream<ST><<<grid, OBS_WARPS * 32, sm, H->stream>>>(a);
+    });
+    CHECK_LAUNCH();
+    return MCBA_OK;
+  }
+  if (MODE == MODE_FUSED && H->k1_variant == 0 && !a.gate) {
+    DISPATCH_STAGE(H->stage, {
+      const int sm = FusedSmem<ST>::BYTES;
+      const int grid = grid_for(H, H->nb, std::min(3, std::max(1, (227 * 1024) / (sm + 1024))));
+      ++H->n_launches;
+      k_observations_fused<ST><<<grid, OBS_WARPS * 32, sm, H->stream>>>(a);
     });
     CHECK_LAUNCH();
     return MCBA_OK;
@@ -1200,6 +1214,7 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   if (dalloc(H, &H->d_ct_epoch, (size_t)1) || dalloc(H, &H->d_radius, (size_t)1)) return MCBA_ERR_CUDA;
   CU(cudaMemsetAsync(H->d_ct_epoch, 0, sizeof(unsigned), H->stream));
   CU(cudaMallocHost((void**)&H->h_pin, (PIN_GATHER + 2 * P2P_MAX_RANKS * P2P_GATHER_W) * sizeof(double)));
+  H->k1_variant = g_k1_variant >= 0 ? g_k1_variant : []() { const char* e = getenv("MCBA_K1"); return e ? atoi(e) : 0; }();
   { const char* e = getenv("MCBA_GRAPH"); H->graph_env = !H->batched && !(e && atoi(e) == 0); H->use_graph = H->graph_env; }   // replay the per-iteration launch sequences as CUDA graphs
   mcba_default_options(&H->opt);
   mark("small allocs");
@@ -1582,6 +1597,8 @@ int mcba_debug_cholesky(void* h, int n, const double* S_host, double* z_out, dou
 }
 
 // Debug/test hook: copy an internal device buffer to the host. Names: "FF","gf","S","rhs","zf","ZtZ","Hoo","Wt","Z","brec","scale_e","scale_f","diag_e","diag_f"
+int mcba_debug_set_k1(int variant) { g_k1_variant = variant; return MCBA_OK; }
+
 int mcba_debug_fetch(void* h, const char* name, double* out, int64_t cap, int64_t* n_out) {
   Handle* H = (Handle*)h; if (!H) return MCBA_ERR_INVALID;
   CU(cudaSetDevice(H->device));

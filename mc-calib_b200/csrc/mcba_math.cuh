@@ -138,6 +138,20 @@ constexpr int CTX_NO = 81;    // 27: Mc  dRo_k
 constexpr int CTX_NB = 108;   // 27: Mco dRb_k
 constexpr int CTX_IN = 135;   // 9 : intrinsics
 constexpr int CTX_SIZE = 144;
+// The same context as a layout type (obs_jacobian is written against one):
+struct CtxBuilt {   // entries computed / copied one by one (ctx_entry_a / ctx_entry_b)
+  static constexpr int RB = CTX_RB, TB = CTX_TB, RO = CTX_RO, TO = CTX_TO, RC = CTX_RC, TC = CTX_TC, DRC = CTX_DRC,
+                       MC = CTX_MC, MCO = CTX_MCO, NO = CTX_NO, NB = CTX_NB, IN = CTX_IN;
+};
+// Copy-free layout: the three prep records (camera, e-block pose, board) and the intrinsics land in shared memory as
+// they are (asynchronous copies, issued one board observation ahead), only Mco / No / Nb are computed. A block that is
+// not refined at this stage, or is the reference camera / board, points at the identity record (R = I, dR = 0, t = 0).
+struct CtxRaw {
+  static constexpr int PC = 0, PO = PREP, PB = 2 * PREP, IN = 3 * PREP;      // raw part: 3 x 39 + 9 = 126 doubles
+  static constexpr int RAW = 3 * PREP + 9;
+  static constexpr int MCO = RAW, NO = RAW + 9, NB = RAW + 36, SIZE = 192;  // 189 used
+  static constexpr int RB = PB, TB = PB + 36, RO = PO, TO = PO + 36, RC = PC, TC = PC + 36, DRC = PC + 9, MC = PC;
+};
 
 // Phase A entries [0,81) + [135,144): copies, Mc, Mco. Each entry depends only on the prep records.
 MCBA_HD double ctx_entry_a(int e, const double* pc, bool act_c, const double* po, const double* pb, bool act_b,
@@ -294,20 +308,20 @@ MCBA_HD float obs_error_ref(const double* ctx, int model, const double* X0, floa
 
 // Residual + Jacobian of one corner. Emits loss-corrected columns through sink.put(local_col, ju, jv)
 // in the local order of Cols<STAGE>, the corrected residual as column R0, and returns 1/2 rho.
-template <int STAGE, class Sink>
+template <int STAGE, class Sink, class L = CtxBuilt>
 MCBA_HD double obs_jacobian(const double* ctx, bool act_c, bool act_b, int model, const double* X0, double u,
                             double v, double huber_a, Sink& sink) {
   typedef StageTraits<STAGE> T;
   typedef Cols<STAGE> C;
   double X1[3], X2[3], X3[3];
-  mat3_vec_add(ctx + CTX_RB, X0, ctx + CTX_TB, X1);
-  mat3_vec_add(ctx + CTX_RO, X1, ctx + CTX_TO, X2);
-  mat3_vec_add(ctx + CTX_RC, X2, ctx + CTX_TC, X3);
+  mat3_vec_add(ctx + L::RB, X0, ctx + L::TB, X1);
+  mat3_vec_add(ctx + L::RO, X1, ctx + L::TO, X2);
+  mat3_vec_add(ctx + L::RC, X2, ctx + L::TC, X3);
   const double iz = rcp(X3[2]);
   const double a = X3[0] * iz, b = X3[1] * iz;
   Distort d;
-  distort<true>(model, ctx + CTX_IN, a, b, d);
-  const double* in = ctx + CTX_IN;
+  distort<true>(model, ctx + L::IN, a, b, d);
+  const double* in = ctx + L::IN;
   const double fx = in[0], fy = in[1];
   const double ru = fx * d.xd + in[2] - u;
   const double rv = fy * d.yd + in[3] - v;
@@ -321,7 +335,7 @@ MCBA_HD double obs_jacobian(const double* ctx, bool act_c, bool act_b, int model
   if (T::CAM) {
     if (act_c) {
       for (int k = 0; k < 3; ++k) {
-        mat3_vec(ctx + CTX_DRC + 9 * k, X2, g);
+        mat3_vec(ctx + L::DRC + 9 * k, X2, g);
         sink.put(C::C0 + k, Pu[0] * g[0] + Pu[1] * g[1] + Pu[2] * g[2], Pv[0] * g[0] + Pv[1] * g[1] + Pv[2] * g[2]);
       }
       for (int k = 0; k < 3; ++k) sink.put(C::C0 + 3 + k, Pu[k], Pv[k]);
@@ -338,9 +352,9 @@ MCBA_HD double obs_jacobian(const double* ctx, bool act_c, bool act_b, int model
   }
   if (T::BOARD) {
     if (act_b) {
-      const double* M = ctx + CTX_MCO;
+      const double* M = ctx + L::MCO;
       for (int k = 0; k < 3; ++k) {
-        mat3_vec(ctx + CTX_NB + 9 * k, X0, g);
+        mat3_vec(ctx + L::NB + 9 * k, X0, g);
         sink.put(C::B0 + k, Pu[0] * g[0] + Pu[1] * g[1] + Pu[2] * g[2], Pv[0] * g[0] + Pv[1] * g[1] + Pv[2] * g[2]);
       }
       for (int k = 0; k < 3; ++k)
@@ -351,9 +365,9 @@ MCBA_HD double obs_jacobian(const double* ctx, bool act_c, bool act_b, int model
     }
   }
   {
-    const double* M = ctx + CTX_MC;
+    const double* M = ctx + L::MC;
     for (int k = 0; k < 3; ++k) {
-      mat3_vec(ctx + CTX_NO + 9 * k, X1, g);
+      mat3_vec(ctx + L::NO + 9 * k, X1, g);
       sink.put(C::E0 + k, Pu[0] * g[0] + Pu[1] * g[1] + Pu[2] * g[2], Pv[0] * g[0] + Pv[1] * g[1] + Pv[2] * g[2]);
     }
     for (int k = 0; k < 3; ++k)

@@ -1,0 +1,234 @@
+// mcba_obs_fused.cuh — K1, fused residual + Jacobian + J~^T J~ (the dominant kernel of an LM iteration), second version.
+//
+// Same arithmetic per corner as k_observations<S, MODE_FUSED> (obs_jacobian, mcba_math.cuh) and the same per-board-
+// observation record; what changes is everything around it. Source-level ncu samples of the first version
+// (profiles/r02_ncu_k1_source_hotspots.txt) put 24 % of the warp time into building the per-board-observation context
+// (three dependent global round trips: record -> prep records -> products, behind a long if-chain per entry), 30 %
+// into the DMMA loop (10 tiles for 28 columns: 37 % of the products are padding or the mirrored half of a diagonal
+// tile) and 40 % into the per-corner Jacobian. Here:
+//
+//  * The context is copy-free and one board observation ahead. The prep records of the camera, the e-block pose and
+//    the board and the intrinsics are copied as they are into a double-buffered shared-memory slot with cp.async while
+//    the previous board observation is being processed (CtxRaw); a block that is not refined points at an identity
+//    record. Only Mco = Rc Ro, No_k = Rc dRo_k and Nb_k = Mco dRb_k (63 three-term products, two rounds) are computed.
+//    The board-observation record, the camera model and the first pass's pixels / corner coordinates are prefetched
+//    the same way, so no global load sits on the critical path of a warp.
+//  * The upper triangle of J~^T J~ is covered by 8x8 DMMA products of *two 4-column groups by two 4-column groups*
+//    (rows {a,b} x columns {c,d}) instead of aligned 8x8 tiles. With the 28 columns of stage 5 as 7 groups, the 7 lines
+//    {i, i+1, i+3} (mod 7) of the Fano plane cover every pair of groups exactly once; product i = rows {i, i+1} x
+//    columns {i, i+3} yields the blocks (i,i), (i,i+3), (i+1,i), (i+1,i+3): 7 DMMAs per k-step instead of 10, 448
+//    products for the 406 entries of the triangle (no padding column, one mirrored 4x4 half per product). The lower
+//    half-warp holds rows/columns of the first group of a product, the upper half-warp those of the second: every lane
+//    loads its column of all groups once per k-step (one shared-memory wavefront per group) and selects.
+//  * Tail passes only clear the one tile row pair a DMMA k-step can still read, not every idle lane's.
+#pragma once
+#include "mcba_kernels.cuh"
+
+namespace mcba {
+
+// Identity prep record (R = I, dR/dw_k = 0, t = 0) for blocks that are not refined.
+__device__ const double g_prep_identity[PREP + 1] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+
+// Cover of the upper triangle (in 4-column groups) by products rows {r0, r1} x columns {c0, c1}; own = which of the four
+// blocks (bit 2 * row_half + col_half) this product stores (a block may be computed twice in the small covers).
+template <int NG> struct RectCover;
+template <> struct RectCover<7> {   // Fano plane
+  static constexpr int NR = 7;
+  __host__ __device__ static constexpr int r0(int i) { return i; }
+  __host__ __device__ static constexpr int r1(int i) { return (i + 1) % 7; }
+  __host__ __device__ static constexpr int c0(int i) { return i; }
+  __host__ __device__ static constexpr int c1(int i) { return (i + 3) % 7; }
+  __host__ __device__ static constexpr int own(int) { return 15; }
+};
+template <> struct RectCover<5> {   // (0,0)(0,2)(1,0)(1,2) | (3,3)(3,0)(4,3)(4,0) | (1,3)(1,4)(2,3)(2,4) | (1,1)(2,2) | (4,4)
+  static constexpr int NR = 5;
+  __host__ __device__ static constexpr int r0(int i) { return i == 0 ? 0 : i == 1 ? 3 : i == 2 ? 1 : i == 3 ? 1 : 4; }
+  __host__ __device__ static constexpr int r1(int i) { return i == 0 ? 1 : i == 1 ? 4 : i == 2 ? 2 : i == 3 ? 2 : 4; }
+  __host__ __device__ static constexpr int c0(int i) { return i == 0 ? 0 : i == 1 ? 3 : i == 2 ? 3 : i == 3 ? 1 : 4; }
+  __host__ __device__ static constexpr int c1(int i) { return i == 0 ? 2 : i == 1 ? 0 : i == 2 ? 4 : i == 3 ? 2 : 4; }
+  __host__ __device__ static constexpr int own(int i) { return i < 3 ? 15 : i == 3 ? 9 : 1; }
+};
+template <> struct RectCover<4> {   // aligned 8x8 tiles: (0,0)(0,1)(1,1) | (0,2)(0,3)(1,2)(1,3) | (2,2)(2,3)(3,3)
+  static constexpr int NR = 3;
+  __host__ __device__ static constexpr int r0(int i) { return i == 2 ? 2 : 0; }
+  __host__ __device__ static constexpr int r1(int i) { return i == 2 ? 3 : 1; }
+  __host__ __device__ static constexpr int c0(int i) { return i == 0 ? 0 : 2; }
+  __host__ __device__ static constexpr int c1(int i) { return i == 0 ? 1 : 3; }
+  __host__ __device__ static constexpr int own(int i) { return i == 1 ? 15 : 11; }   // not the mirrored (1,0) / (3,2)
+};
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+template <int STAGE> struct FusedSmem {
+  typedef Cols<STAGE> C;
+  static constexpr int NG = (C::NC + 3) / 4;
+  static constexpr int TILE = 4 * NG * TS;                      // pad columns stay zero
+  static constexpr int WARP_DOUBLES = 2 * CtxRaw::SIZE + TILE;
+  static constexpr int NR = RectCover<NG>::NR;
+  static constexpr int IDX_BYTES = NR * 32 * 4;                 // per CTA: record index of every accumulator entry (short2 per product and lane)
+  static constexpr int BYTES = OBS_WARPS * WARP_DOUBLES * 8 + IDX_BYTES;
+};
+
+template <int STAGE>
+__global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_fused(ObsArgs a) {
+  typedef Cols<STAGE> C;
+  typedef StageTraits<STAGE> ST;
+  typedef FusedSmem<STAGE> SM;
+  typedef RectCover<SM::NG> RCV;
+  constexpr int NG = SM::NG, NR = RCV::NR;
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* cbuf = smem + warp * SM::WARP_DOUBLES;
+  double* T = cbuf + 2 * CtxRaw::SIZE;
+  const int total_warps = gridDim.x * OBS_WARPS;
+  const int g = lane >> 2, q = lane & 3, hi = lane >> 4, c4 = g & 3;
+  // Where each accumulator entry goes in the compact record (-1: not stored): lane constants, kept in shared memory -
+  // left to the compiler they are hoisted out of the board-observation loop and spilled (14 dependent local-memory
+  // round trips per board observation in the epilogue, 30 % of the kernel: profiles/r02_ncu_k1_source_hotspots.txt)
+  short2* sidx = reinterpret_cast<short2*>(smem + OBS_WARPS * SM::WARP_DOUBLES);
+  for (int r = warp; r < NR; r += OBS_WARPS) {
+    int gr = 0, gc = 0, own = 0;
+#pragma unroll
+    for (int rr = 0; rr < NR; ++rr)
+      if (rr == r) { gr = hi ? RCV::r1(rr) : RCV::r0(rr); gc = (q >> 1) ? RCV::c1(rr) : RCV::c0(rr); own = RCV::own(rr); }
+    short v[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int ea = 4 * gr + c4, eb = 4 * gc + ((2 * q + h) & 3);
+      const bool mine = (own >> (2 * hi + (q >> 1))) & 1;
+      int ci = -1;
+      if (mine && ea < C::NC && eb < C::NC && (gr != gc || ea <= eb)) ci = C::cidx(min(ea, eb), max(ea, eb));
+      v[h] = (short)ci;
+    }
+    sidx[r * 32 + lane] = make_short2(v[0], v[1]);
+  }
+  __syncthreads();
+  int b = blockIdx.x * OBS_WARPS + warp;
+  if (b >= a.nb) return;
+  for (int e = lane; e < SM::TILE; e += 32) T[e] = 0.0;
+  // lane-constant operands of the two rounds of context products: out = M[3 i + .] . D[. + j]
+  int m1, d1, o1, m2, d2, o2;
+  {
+    if (lane < 9) { m1 = CtxRaw::RC + 3 * (lane / 3); d1 = CtxRaw::RO + lane % 3; o1 = CtxRaw::MCO + lane; }
+    else { const int e = lane - 9, k = e / 9, i = (e % 9) / 3, j = e % 3; m1 = CtxRaw::MC + 3 * i; d1 = CtxRaw::PO + 9 + 9 * k + j; o1 = CtxRaw::NO + e; }
+    if (lane < 4) { const int e = 23 + lane, k = e / 9, i = (e % 9) / 3, j = e % 3; m2 = CtxRaw::MC + 3 * i; d2 = CtxRaw::PO + 9 + 9 * k + j; o2 = CtxRaw::NO + e; }
+    else { const int e = min(lane - 4, 26), k = e / 9, i = (e % 9) / 3, j = e % 3; m2 = CtxRaw::MCO + 3 * i; d2 = CtxRaw::PB + 9 + 9 * k + j; o2 = CtxRaw::NB + e; }
+  }
+  // flags of a board observation: raw loads (combined where they are used, so that nothing waits on them early)
+  struct Flags { unsigned char cref, bref; int model; };
+  auto load_flags = [&](const int4& r) {
+    Flags f;
+    f.cref = (ST::CAM && a.cam_is_ref) ? a.cam_is_ref[r.y] : 0;
+    f.bref = (ST::BOARD && a.board_is_ref) ? a.board_is_ref[r.w] : 0;
+    f.model = a.cam_model[r.y];
+    return f;
+  };
+  auto issue_ctx = [&](const int4& r, const Flags& f, double* dst) {   // raw context of one board observation -> dst (asynchronous)
+    const bool act_c = ST::CAM && !f.cref, act_b = ST::BOARD && !f.bref;
+    const double* pc = act_c ? a.prep_cam + (size_t)PREP * r.y : g_prep_identity;
+    const double* po = a.prep_pose + (size_t)PREP * r.z;
+    const double* pb = act_b ? a.prep_board + (size_t)PREP * r.w : g_prep_identity;
+    const double* in = a.intr + 9 * (size_t)r.y;
+#pragma unroll
+    for (int e = lane; e < CtxRaw::RAW; e += 32) {
+      const double* src = e < CtxRaw::PO ? pc + e : e < CtxRaw::PB ? po + (e - CtxRaw::PO) : e < CtxRaw::IN ? pb + (e - CtxRaw::PB) : in + (e - CtxRaw::IN);
+      cp_async8(dst + e, src);
+    }
+  };
+  // prologue: this warp's first board observation; the record of the second one
+  int4 rec = a.bobs[b];
+  int obs_end = a.bobs[b + 1].x;
+  Flags fl = load_flags(rec);
+  issue_ctx(rec, fl, cbuf);
+  int4 rec_n = rec; int end_n = obs_end;
+  if (b + total_warps < a.nb) { rec_n = a.bobs[b + total_warps]; end_n = a.bobs[b + total_warps + 1].x; }
+  float pf_u = 0.f, pf_v = 0.f; int pf_pt = 0;
+  if (rec.x + lane < obs_end) { pf_u = a.u[rec.x + lane]; pf_v = a.v[rec.x + lane]; pf_pt = a.pt[rec.x + lane]; }
+  double nX[3];
+  { const double* p3 = a.pts + 3 * (size_t)pf_pt; nX[0] = p3[0]; nX[1] = p3[1]; nX[2] = p3[2]; }
+  int par = 0;
+  while (true) {
+    double* ctx = cbuf + par * CtxRaw::SIZE;
+    const int bn = b + total_warps, bnn = bn + total_warps;
+    const bool has_n = bn < a.nb;
+    int4 rec_nn = rec_n; int end_nn = end_n;              // records run two board observations ahead, flags one
+    if (bnn < a.nb) { rec_nn = a.bobs[bnn]; end_nn = a.bobs[bnn + 1].x; }
+    Flags fl_n = fl;
+    if (has_n) fl_n = load_flags(rec_n);
+    cp_async_wait_all();
+    __syncwarp();
+    ctx[o1] = ctx[m1] * ctx[d1] + ctx[m1 + 1] * ctx[d1 + 3] + ctx[m1 + 2] * ctx[d1 + 6];
+    __syncwarp();
+    if (lane < 31) ctx[o2] = ctx[m2] * ctx[d2] + ctx[m2 + 1] * ctx[d2 + 3] + ctx[m2 + 2] * ctx[d2 + 6];
+    __syncwarp();
+    const bool act_c = ST::CAM && !fl.cref, act_b = ST::BOARD && !fl.bref;
+    const int model = fl.model;
+    double acc[NR][2];
+#pragma unroll
+    for (int t = 0; t < NR; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    double cost = 0.0;
+    const int obs_begin = rec.x;
+    for (int base = obs_begin; base < obs_end; base += OBS_PASS) {
+      const int nact = min(OBS_PASS, obs_end - base);
+      const bool active = lane < nact;
+      const float cur_u = pf_u, cur_v = pf_v;
+      const double X0[3] = {nX[0], nX[1], nX[2]};
+      // pixels / corner index of the following pass: of this board observation, or the first one of the next
+      const bool last_pass = base + OBS_PASS >= obs_end;
+      const int nxt = last_pass ? rec_n.x + lane : base + OBS_PASS + lane;
+      const int nxt_end = last_pass ? end_n : obs_end;
+      const bool nxt_ok = (has_n || !last_pass) && nxt < nxt_end;
+      if (nxt_ok) { pf_u = a.u[nxt]; pf_v = a.v[nxt]; pf_pt = a.pt[nxt]; }
+      if (active) {
+        TileSink sink{T, lane};
+        cost += obs_jacobian<STAGE, TileSink, CtxRaw>(ctx, act_c, act_b, model, X0, (double)cur_u, (double)cur_v, a.huber_a, sink);
+      } else if (lane == nact && (nact & 1)) {           // the odd corner's partner rows of the last k-step
+#pragma unroll
+        for (int col = 0; col < C::NC; ++col)
+          *reinterpret_cast<double2*>(T + col * TS + 2 * lane) = make_double2(0.0, 0.0);
+      }
+      if (nxt_ok) { const double* p3 = a.pts + 3 * (size_t)pf_pt; nX[0] = p3[0]; nX[1] = p3[1]; nX[2] = p3[2]; }
+      if (base == obs_begin && has_n) issue_ctx(rec_n, fl_n, cbuf + (par ^ 1) * CtxRaw::SIZE);
+      __syncwarp();
+      const int ksteps = (2 * nact + 3) >> 2;
+      const double* Tl = T + c4 * TS + q;
+      double G[NG], Gn[NG];
+#pragma unroll
+      for (int j = 0; j < NG; ++j) G[j] = Tl[4 * j * TS];
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int kn = min(ks + 1, ksteps - 1);
+#pragma unroll
+        for (int j = 0; j < NG; ++j) Gn[j] = Tl[4 * j * TS + 4 * kn];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const double fa = hi ? G[RCV::r1(r)] : G[RCV::r0(r)];
+          const double fb = hi ? G[RCV::c1(r)] : G[RCV::c0(r)];
+          dmma884(acc[r][0], acc[r][1], fa, fb);
+        }
+#pragma unroll
+        for (int j = 0; j < NG; ++j) G[j] = Gn[j];
+      }
+      __syncwarp();
+    }
+    {
+      double* out = a.brec + (size_t)b * C::NCOMP;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const short2 ci = sidx[r * 32 + lane];
+        if (ci.x >= 0) out[ci.x] = acc[r][0];
+        if (ci.y >= 0) out[ci.y] = acc[r][1];
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, off);
+      if (lane == 0) a.cost_bobs[b] = cost;
+    }
+    if (!has_n) break;
+    b = bn; rec = rec_n; obs_end = end_n; fl = fl_n; rec_n = rec_nn; end_n = end_nn; par ^= 1;
+  }
+}
+
+}  // namespace mcba

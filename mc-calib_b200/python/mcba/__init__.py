@@ -194,6 +194,7 @@ def load_lib():
     L.mcba_timer_start.argtypes = [vp]
     L.mcba_timer_stop.argtypes = [vp, c_f64p]
     L.mcba_debug_fetch.argtypes = [vp, C.c_char_p, c_f64p, C.c_int64, C.POINTER(C.c_int64)]
+    L.mcba_debug_set_k1.argtypes = [C.c_int]
     L.mcba_debug_cholesky.argtypes = [vp, C.c_int, c_f64p, c_f64p, c_f64p, C.c_int, C.c_int, c_f64p, C.POINTER(C.c_int)]
     _lib = L
     return L
