@@ -183,9 +183,10 @@ int mcba_timer_stop(void *handle, double *ms);       /* second event + elapsed d
 /* Test hook: copy an internal device buffer (normal-equation blocks, reduced system, scaling) to the host.
  * Names: "FF" "gf" "S" "rhs" "zf" "ZtZ" "Hoo" "Wt" "Z" "brec" "scale_e" "scale_f" "diag_e" "diag_f". */
 int mcba_debug_fetch(void *handle, const char *name, double *out, int64_t cap, int64_t *n_out);
-/* Test hook: fused observation kernel of the handles created afterwards. 0 = k_observations_fused (default),
- * 1 = first version (k_observations<S, MODE_FUSED>), 2 = streaming experiment; -1 = back to the MCBA_K1 environment
- * variable. Same per-board-observation records up to the summation order of the DMMA products. */
+/* Test hook: fused observation kernel of the handles created afterwards. 0 = k_observations_fused, 3 =
+ * k_observations_pair (two board observations per warp), 1 = first version (k_observations<S, MODE_FUSED>),
+ * 2 = streaming experiment; -1 = back to the MCBA_K1 environment variable (unset: 0 at stage 5, 3 otherwise).
+ * All variants write bit-identical per-board-observation records. */
 int mcba_debug_set_k1(int variant);
 /* Test / benchmark hook: factor and solve one dense symmetric positive definite system with the reduced-system
  * kernels alone. S_host is (n+1) x n row-major (matrix rows, then the right-hand side as row n); z_out [n] = solution,

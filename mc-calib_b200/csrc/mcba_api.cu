@@ -131,7 +131,7 @@ struct Handle {
   int64_t n_obs_global = 0;
   // CUDA graphs of the two per-iteration launch sequences (single-rank handles): key = 2 * cur + brec_par
   bool use_graph = false, graph_env = false, capturing = false; int brec_par = 0;
-  int k1_variant = 0;                // fused observation kernel of this handle (launch_obs)
+  int k1_variant = -1;               // fused observation kernel of this handle (launch_obs)
   cudaGraphExec_t g_step[4] = {nullptr, nullptr, nullptr, nullptr}, g_asm[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t g_step_launches[4] = {0, 0, 0, 0}, g_asm_launches[4] = {0, 0, 0, 0};
   mcba_options graph_opt; bool graph_opt_valid = false;
@@ -344,6 +344,7 @@ static int setup_stage(Handle* H, int stage) {
     CU(cudaFuncSetAttribute(k_observations<ST, MODE_FROM_J>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     CU(cudaFuncSetAttribute(k_observations_stream<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, OBS_WARPS * (2 * CTX_SIZE + Cols<ST>::NC * TS) * 8));
     CU(cudaFuncSetAttribute(k_observations_fused<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem<ST>::BYTES));
+    CU(cudaFuncSetAttribute(k_observations_pair<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem<ST>::BYTES));
     CU(cudaFuncSetAttribute(k_eblock_assemble<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * (H->ldz + EA_PAD) * 8));
   });
   return MCBA_OK;
@@ -396,11 +397,17 @@ template <int MODE> static int launch_obs(Handle* H, int which, double huber_a) 
   const int fam = MODE == MODE_FUSED ? KF_FUSED : MODE == MODE_MATERIALIZE ? KF_MATERIALIZE : MODE == MODE_FROM_J ? KF_FROM_J : KF_COST;
   Timed t(H, fam);
   ObsArgs a = obs_args(H, which, huber_a);
-  // Variant of the fused kernel, fixed per handle at mcba_create (MCBA_K1 / mcba_debug_set_k1): 0 = k_observations_fused
-  // (prefetched copy-free context, group-pair cover of the triangle; the default), 1 = the first version
-  // k_observations<S, MODE_FUSED> (also what gated / batched handles run), 2 = the streaming experiment (tails of
-  // consecutive board observations share a warp pass; measured slower than version 1, 0.96 vs 0.88 ms).
-  if (MODE == MODE_FUSED && H->k1_variant == 2 && !a.gate) {
+  // Variant of the fused kernel, fixed per handle at mcba_create (MCBA_K1 / mcba_debug_set_k1):
+  //   0 = k_observations_fused: one board observation per warp, prefetched copy-free context, group-pair cover of the
+  //       triangle (7 DMMAs per k-step instead of 10 at stage 5);
+  //   3 = k_observations_pair: the same with two board observations per warp (one per half-warp, 16 corners per pass);
+  //   1 = the first version k_observations<S, MODE_FUSED> (also what gated / batched handles run);
+  //   2 = the streaming experiment (tails of consecutive board observations share a warp pass; slower than version 1);
+  //  -1 = automatic (default): 0 at stage 5, where two sets of accumulators do not fit the register budget of 3 CTAs
+  //       per SM next to the 27-column Jacobian (measured 0.80 vs 0.75 ms), 3 at the other stages (0.54 vs 0.60 ms at
+  //       stage 4). All variants write bit-identical records.
+  const int k1v = H->k1_variant >= 0 ? H->k1_variant : (H->stage == 5 ? 0 : 3);
+  if (MODE == MODE_FUSED && k1v == 2 && !a.gate) {
     DISPATCH_STAGE(H->stage, {
       const int sm = OBS_WARPS * (2 * CTX_SIZE + Cols<ST>::NC * TS) * 8;
       const int per_sm = std::min(3, std::max(1, (227 * 1024) / (sm + 1024)));
@@ -411,7 +418,17 @@ template <int MODE> static int launch_obs(Handle* H, int which, double huber_a) 
     CHECK_LAUNCH();
     return MCBA_OK;
   }
-  if (MODE == MODE_FUSED && H->k1_variant == 0 && !a.gate) {
+  if (MODE == MODE_FUSED && k1v == 3 && !a.gate) {
+    DISPATCH_STAGE(H->stage, {
+      const int sm = PairSmem<ST>::BYTES;
+      const int grid = grid_for(H, (H->nb + 1) / 2, std::min(3, std::max(1, (227 * 1024) / (sm + 1024))));
+      ++H->n_launches;
+      k_observations_pair<ST><<<grid, OBS_WARPS * 32, sm, H->stream>>>(a);
+    });
+    CHECK_LAUNCH();
+    return MCBA_OK;
+  }
+  if (MODE == MODE_FUSED && k1v == 0 && !a.gate) {
     DISPATCH_STAGE(H->stage, {
       const int sm = FusedSmem<ST>::BYTES;
       const int grid = grid_for(H, H->nb, std::min(3, std::max(1, (227 * 1024) / (sm + 1024))));
@@ -1214,7 +1231,7 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   if (dalloc(H, &H->d_ct_epoch, (size_t)1) || dalloc(H, &H->d_radius, (size_t)1)) return MCBA_ERR_CUDA;
   CU(cudaMemsetAsync(H->d_ct_epoch, 0, sizeof(unsigned), H->stream));
   CU(cudaMallocHost((void**)&H->h_pin, (PIN_GATHER + 2 * P2P_MAX_RANKS * P2P_GATHER_W) * sizeof(double)));
-  H->k1_variant = g_k1_variant >= 0 ? g_k1_variant : []() { const char* e = getenv("MCBA_K1"); return e ? atoi(e) : 0; }();
+  H->k1_variant = g_k1_variant >= 0 ? g_k1_variant : []() { const char* e = getenv("MCBA_K1"); return e ? atoi(e) : -1; }();
   { const char* e = getenv("MCBA_GRAPH"); H->graph_env = !H->batched && !(e && atoi(e) == 0); H->use_graph = H->graph_env; }   // replay the per-iteration launch sequences as CUDA graphs
   mcba_default_options(&H->opt);
   mark("small allocs");

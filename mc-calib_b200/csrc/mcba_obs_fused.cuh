@@ -231,4 +231,199 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_fused(ObsArg
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Third version: TWO board observations per warp, one per half-warp, 16 corners of each per pass. A 48-corner board
+// takes 3 full passes per pair instead of 2 x (one full + one half-empty) = 4 - the per-corner Jacobian phase costs the
+// same whatever the number of active lanes - and a 16-corner board one pass per pair instead of two. Every lane keeps
+// the scalars of "its" board observation (record, range, flags, prefetched pixels), so nothing is held twice; the two
+// contexts sit 16 banks apart; tile rows 0..31 are the first observation's, 32..63 the second's; the DMMA loop runs
+// the two observations' k-steps side by side (two independent sets of accumulators: twice the products in flight per
+// shared-memory round trip). The context is single-buffered: the asynchronous copy for the next pair is issued after
+// the last Jacobian phase of the current one and lands during its last DMMA phase. Same per-observation arithmetic and
+// row order: the records are bit-identical to the other versions'.
+constexpr int HP = 16;                          // corners per half-warp pass
+constexpr int CTXP = CtxRaw::SIZE + 8;          // context pitch: 400 words = 16 banks apart
+
+template <int STAGE> struct PairSmem {
+  typedef Cols<STAGE> C;
+  static constexpr int NG = (C::NC + 3) / 4;
+  static constexpr int TILE = 4 * NG * TS;
+  static constexpr int WARP_DOUBLES = 2 * CTXP + TILE;
+  static constexpr int NR = RectCover<NG>::NR;
+  static constexpr int IDX_BYTES = NR * 32 * 4;
+  static constexpr int CTAB_BYTES = 64 * 4;     // operand offsets of the 63 context products, 4 rounds of 16
+  static constexpr int BYTES = OBS_WARPS * WARP_DOUBLES * 8 + IDX_BYTES + CTAB_BYTES;
+};
+
+template <int STAGE>
+__global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_pair(ObsArgs a) {
+  typedef Cols<STAGE> C;
+  typedef StageTraits<STAGE> ST;
+  typedef PairSmem<STAGE> SM;
+  typedef RectCover<SM::NG> RCV;
+  constexpr int NG = SM::NG, NR = RCV::NR;
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3, hi = lane >> 4, c4 = g & 3, l16 = lane & 15;
+  double* cbuf = smem + warp * SM::WARP_DOUBLES;
+  double* ctx = cbuf + hi * CTXP;                // this half-warp's context
+  double* T = cbuf + 2 * CTXP;
+  short2* sidx = reinterpret_cast<short2*>(smem + OBS_WARPS * SM::WARP_DOUBLES);
+  int* ctab = reinterpret_cast<int*>(sidx + NR * 32);
+  for (int r = warp; r < NR; r += OBS_WARPS) {
+    int gr = 0, gc = 0, own = 0;
+#pragma unroll
+    for (int rr = 0; rr < NR; ++rr)
+      if (rr == r) { gr = hi ? RCV::r1(rr) : RCV::r0(rr); gc = (q >> 1) ? RCV::c1(rr) : RCV::c0(rr); own = RCV::own(rr); }
+    short v[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int ea = 4 * gr + c4, eb = 4 * gc + ((2 * q + h) & 3);
+      const bool mine = (own >> (2 * hi + (q >> 1))) & 1;
+      int ci = -1;
+      if (mine && ea < C::NC && eb < C::NC && (gr != gc || ea <= eb)) ci = C::cidx(min(ea, eb), max(ea, eb));
+      v[h] = (short)ci;
+    }
+    sidx[r * 32 + lane] = make_short2(v[0], v[1]);
+  }
+  if (threadIdx.x < 64) {   // context products out = M[3 i + .] . D[. + j]: Mco (9), No (27), Nb (27, needs Mco: rounds 2, 3)
+    const int e = min((int)threadIdx.x, 62);
+    int m, d, o;
+    if (e < 9) { m = CtxRaw::RC + 3 * (e / 3); d = CtxRaw::RO + e % 3; o = CtxRaw::MCO + e; }
+    else if (e < 36) { const int f = e - 9, k = f / 9, i = (f % 9) / 3, j = f % 3; m = CtxRaw::MC + 3 * i; d = CtxRaw::PO + 9 + 9 * k + j; o = CtxRaw::NO + f; }
+    else { const int f = e - 36, k = f / 9, i = (f % 9) / 3, j = f % 3; m = CtxRaw::MCO + 3 * i; d = CtxRaw::PB + 9 + 9 * k + j; o = CtxRaw::NB + f; }
+    ctab[threadIdx.x] = m | (d << 8) | (o << 16);
+  }
+  __syncthreads();
+  const int total_warps = gridDim.x * OBS_WARPS;
+  const int n_pairs = (a.nb + 1) >> 1;
+  int p = blockIdx.x * OBS_WARPS + warp;
+  if (p >= n_pairs) return;
+  for (int e = lane; e < SM::TILE; e += 32) T[e] = 0.0;
+  struct Flags { unsigned char cref, bref; int model; };
+  auto load_rec = [&](int pp, int4& r, int& end) {          // this lane's board observation of pair pp (empty past the end)
+    const int bb = 2 * pp + hi;
+    if (bb < a.nb) { r = a.bobs[bb]; end = a.bobs[bb + 1].x; } else { r = make_int4(0, 0, 0, 0); end = 0; }
+  };
+  auto load_flags = [&](const int4& r) {
+    Flags f;
+    f.cref = (ST::CAM && a.cam_is_ref) ? a.cam_is_ref[r.y] : 0;
+    f.bref = (ST::BOARD && a.board_is_ref) ? a.board_is_ref[r.w] : 0;
+    f.model = a.cam_model[r.y];
+    return f;
+  };
+  auto issue_ctx = [&](const int4& r, const Flags& f) {
+    const bool act_c = ST::CAM && !f.cref, act_b = ST::BOARD && !f.bref;
+    const double* pc = act_c ? a.prep_cam + (size_t)PREP * r.y : g_prep_identity;
+    const double* po = a.prep_pose + (size_t)PREP * r.z;
+    const double* pb = act_b ? a.prep_board + (size_t)PREP * r.w : g_prep_identity;
+    const double* in = a.intr + 9 * (size_t)r.y;
+#pragma unroll
+    for (int e = l16; e < CtxRaw::RAW; e += 16) {
+      const double* src = e < CtxRaw::PO ? pc + e : e < CtxRaw::PB ? po + (e - CtxRaw::PO) : e < CtxRaw::IN ? pb + (e - CtxRaw::PB) : in + (e - CtxRaw::IN);
+      cp_async8(ctx + e, src);
+    }
+  };
+  int4 rec, rec_n; int obs_end, end_n;
+  load_rec(p, rec, obs_end);
+  Flags fl = load_flags(rec);
+  issue_ctx(rec, fl);
+  load_rec(p + total_warps < n_pairs ? p + total_warps : p, rec_n, end_n);
+  float pf_u = 0.f, pf_v = 0.f; int pf_pt = 0;
+  if (rec.x + l16 < obs_end) { pf_u = a.u[rec.x + l16]; pf_v = a.v[rec.x + l16]; pf_pt = a.pt[rec.x + l16]; }
+  double nX[3];
+  { const double* p3 = a.pts + 3 * (size_t)pf_pt; nX[0] = p3[0]; nX[1] = p3[1]; nX[2] = p3[2]; }
+  while (true) {
+    const int pn = p + total_warps, pnn = pn + total_warps;
+    const bool has_n = pn < n_pairs;
+    int4 rec_nn = rec_n; int end_nn = end_n;
+    if (pnn < n_pairs) load_rec(pnn, rec_nn, end_nn);
+    Flags fl_n = fl;
+    if (has_n) fl_n = load_flags(rec_n);
+    cp_async_wait_all();
+    __syncwarp();
+#pragma unroll
+    for (int rd = 0; rd < 4; ++rd) {
+      const int pk = ctab[rd * 16 + l16];
+      const int m = pk & 255, d = (pk >> 8) & 255, o = pk >> 16;
+      ctx[o] = ctx[m] * ctx[d] + ctx[m + 1] * ctx[d + 3] + ctx[m + 2] * ctx[d + 6];
+      __syncwarp();
+    }
+    const bool act_c = ST::CAM && !fl.cref, act_b = ST::BOARD && !fl.bref;
+    const int model = fl.model;
+    double accA[NR][2], accB[NR][2];
+#pragma unroll
+    for (int t = 0; t < NR; ++t) { accA[t][0] = 0.0; accA[t][1] = 0.0; accB[t][0] = 0.0; accB[t][1] = 0.0; }
+    double cost = 0.0;
+    const int my_begin = rec.x, n_mine = obs_end - rec.x;
+    const int nA = __shfl_sync(0xffffffffu, n_mine, 0), nB = __shfl_sync(0xffffffffu, n_mine, 16);
+    const int npass = (max(nA, nB) + HP - 1) / HP;
+    for (int pass = 0; pass < npass; ++pass) {
+      const int off = pass * HP;
+      const int nact = min(HP, max(0, n_mine - off));
+      const bool active = l16 < nact;
+      const float cur_u = pf_u, cur_v = pf_v;
+      const double X0[3] = {nX[0], nX[1], nX[2]};
+      const bool last = pass + 1 == npass;
+      const int nxt = last ? rec_n.x + l16 : my_begin + off + HP + l16;
+      const int nxt_end = last ? end_n : obs_end;
+      const bool nxt_ok = (has_n || !last) && nxt < nxt_end;
+      if (nxt_ok) { pf_u = a.u[nxt]; pf_v = a.v[nxt]; pf_pt = a.pt[nxt]; }
+      if (active) {
+        TileSink sink{T, lane};
+        cost += obs_jacobian<STAGE, TileSink, CtxRaw>(ctx, act_c, act_b, model, X0, (double)cur_u, (double)cur_v, a.huber_a, sink);
+      } else if (l16 == nact && (nact & 1)) {
+#pragma unroll
+        for (int col = 0; col < C::NC; ++col)
+          *reinterpret_cast<double2*>(T + col * TS + 2 * lane) = make_double2(0.0, 0.0);
+      }
+      if (nxt_ok) { const double* p3 = a.pts + 3 * (size_t)pf_pt; nX[0] = p3[0]; nX[1] = p3[1]; nX[2] = p3[2]; }
+      __syncwarp();
+      if (last && has_n) issue_ctx(rec_n, fl_n);          // the context is not read any more in this iteration
+      const int kA = (2 * min(HP, max(0, nA - off)) + 3) >> 2, kB = (2 * min(HP, max(0, nB - off)) + 3) >> 2;
+      const int kmax = max(kA, kB);
+      const double* TlA = T + c4 * TS + q;
+      const double* TlB = TlA + 2 * HP;
+      double GA[NG], GB[NG], GAn[NG], GBn[NG];
+#pragma unroll
+      for (int j = 0; j < NG; ++j) { GA[j] = TlA[4 * j * TS]; GB[j] = TlB[4 * j * TS]; }
+      for (int ks = 0; ks < kmax; ++ks) {
+        const int kn = min(ks + 1, kmax - 1);
+#pragma unroll
+        for (int j = 0; j < NG; ++j) { GAn[j] = TlA[4 * j * TS + 4 * kn]; GBn[j] = TlB[4 * j * TS + 4 * kn]; }
+        if (ks < kA) {
+#pragma unroll
+          for (int r = 0; r < NR; ++r)
+            dmma884(accA[r][0], accA[r][1], hi ? GA[RCV::r1(r)] : GA[RCV::r0(r)], hi ? GA[RCV::c1(r)] : GA[RCV::c0(r)]);
+        }
+        if (ks < kB) {
+#pragma unroll
+          for (int r = 0; r < NR; ++r)
+            dmma884(accB[r][0], accB[r][1], hi ? GB[RCV::r1(r)] : GB[RCV::r0(r)], hi ? GB[RCV::c1(r)] : GB[RCV::c0(r)]);
+        }
+#pragma unroll
+        for (int j = 0; j < NG; ++j) { GA[j] = GAn[j]; GB[j] = GBn[j]; }
+      }
+      __syncwarp();
+    }
+    {
+      const int bA = 2 * p, bB = 2 * p + 1;
+      double* outA = a.brec + (size_t)bA * C::NCOMP;
+      double* outB = a.brec + (size_t)bB * C::NCOMP;
+      const bool hasB = bB < a.nb;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const short2 ci = sidx[r * 32 + lane];
+        if (ci.x >= 0) { outA[ci.x] = accA[r][0]; if (hasB) outB[ci.x] = accB[r][0]; }
+        if (ci.y >= 0) { outA[ci.y] = accA[r][1]; if (hasB) outB[ci.y] = accB[r][1]; }
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, off);
+      if (l16 == 0 && 2 * p + hi < a.nb) a.cost_bobs[2 * p + hi] = cost;
+    }
+    if (!has_n) break;
+    p = pn; rec = rec_n; obs_end = end_n; fl = fl_n; rec_n = rec_nn; end_n = end_nn;
+  }
+}
+
 }  // namespace mcba

@@ -415,3 +415,59 @@ def test_registered_observations_are_shared_between_pose_init_and_bundle_adjustm
     mcba.obs_release(prob)
     assert np.array_equal(r0.pose, r1.pose) and np.array_equal(r0.inlier_mask, r1.inlier_mask)
     assert trace_tuple(ta) == trace_tuple(tb) and np.array_equal(pa.intrinsics, pb.intrinsics)
+
+
+def _ragged_problem(stage, seed=3):
+    """c2 scene with random corner counts per board observation (1 .. all 16, odd and even) and an odd number of
+    board observations: the tail handling of the fused observation kernels (half-empty passes, the zeroed partner row
+    of an odd corner count, the unpaired last board observation of k_observations_pair)."""
+    s = synth.make_scene("c2", n_frames=41)
+    o = synth.generate_observations(s)
+    prob, init, gt = synth.make_problem(s, o, stage)
+    rng = np.random.default_rng(seed)
+    counts = np.diff(prob.bobs_ptr)
+    keep_bobs = np.ones(prob.n_bobs, bool)
+    if prob.n_bobs % 2 == 0:
+        keep_bobs[-1] = False
+    new_counts = np.minimum(counts, rng.integers(1, counts.max() + 1, prob.n_bobs))
+    obs_keep = np.zeros(prob.n_obs, bool)
+    for b in range(prob.n_bobs):
+        if keep_bobs[b]:
+            obs_keep[prob.bobs_ptr[b]:prob.bobs_ptr[b] + new_counts[b]] = True
+    p2 = mcba.Problem(stage, prob.u[obs_keep], prob.v[obs_keep], prob.pt_idx[obs_keep],
+                      np.concatenate([[0], np.cumsum(new_counts[keep_bobs])]), prob.bobs_cam[keep_bobs],
+                      prob.bobs_pose[keep_bobs], prob.bobs_board[keep_bobs], prob.pts_xyz, prob.cam_model, prob.n_pose,
+                      prob.n_board, prob.cam_is_ref, prob.board_is_ref)
+    return p2, init
+
+
+@pytest.mark.parametrize("stage", [1, 2, 3, 4, 5])
+def test_fused_observation_kernel_variants_write_identical_records(stage, oracle):
+    """k_observations_fused (0), k_observations_pair (3) and the streaming experiment (2) against the first version
+    (1): same per-corner arithmetic and the same row order of the DMMA sums, so the per-board-observation records and
+    costs are identical bit for bit - on ragged corner counts too - and the first version is the one the oracle
+    comparison of the normal equations was made with (test_normal_equations_and_schur runs the default variant)."""
+    lib = mcba.load_lib()
+    prob, init = _ragged_problem(stage)
+    assert prob.n_bobs % 2 == 1 and len(set(np.diff(prob.bobs_ptr) % 2)) == 2
+    ref = None
+    try:
+        for variant in (1, 0, 3, 2):
+            lib.mcba_debug_set_k1(variant)
+            h = mcba.Handle(prob)
+            h.solve_begin(init.copy(), mcba.default_options())
+            rec = h.debug_fetch("brec").copy()
+            cost = h.eval(init.copy(), want_jac=False)[0]
+            h.solve_end(init.copy())
+            h.close()
+            assert np.isfinite(rec).all()
+            if ref is None:
+                ref = (rec, cost)
+                rc, co, _, _, _ = oracle.eval(prob, init.copy())
+                assert rc == 0 and abs(cost - co) <= 1e-11 * abs(co)
+            else:
+                scale = np.abs(ref[0]).max()
+                assert np.abs(rec - ref[0]).max() <= 1e-15 * scale, f"variant {variant}"
+                assert abs(cost - ref[1]) <= 1e-14 * abs(ref[1])
+    finally:
+        lib.mcba_debug_set_k1(-1)
