@@ -180,6 +180,17 @@ int64_t mcba_kernel_launches(void *handle);          /* kernels launched by this
 int mcba_timer_start(void *handle);                  /* CUDA event on the library's stream (after a stream sync) */
 int mcba_timer_stop(void *handle, double *ms);       /* second event + elapsed device time between the two */
 
+/* Binary dump / load of a packed problem with (optionally) its parameter blocks: the flat arrays above, as they are
+ * ("MCBAPRB1", layout in csrc/mcba_io.cpp). Replay of a bundle adjustment, resume from the parameters of an earlier
+ * solve, parity fixtures. The reference's own checkpoint is one step earlier and textual (detected_keypoints_data.yml +
+ * the camera-parameter file, McCalib/src/McCalib.cpp:493-548, :172-226, :662-688; host/McCalibInit.cpp reads those).
+ * mcba_problem_load allocates the arrays; *storage owns them until mcba_problem_free. params may be NULL on save (no
+ * parameter section) and on load (sections skipped); absent sections load as NULL pointers. Host only. */
+int mcba_problem_save(const char *path, const mcba_problem *prob, const mcba_params *params);
+int mcba_problem_load(const char *path, mcba_problem *prob, mcba_params *params, void **storage);
+void mcba_problem_free(void *storage);
+const char *mcba_io_last_error(void);
+
 /* Test hook: copy an internal device buffer (normal-equation blocks, reduced system, scaling) to the host.
  * Names: "FF" "gf" "S" "rhs" "zf" "ZtZ" "Hoo" "Wt" "Z" "brec" "scale_e" "scale_f" "diag_e" "diag_f". */
 int mcba_debug_fetch(void *handle, const char *name, double *out, int64_t cap, int64_t *n_out);

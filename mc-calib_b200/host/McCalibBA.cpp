@@ -19,6 +19,7 @@ namespace McCalib {
 int g_cuda_device = 0;
 int g_verbose = 1;
 std::string g_last_error;
+std::string g_problem_dump_dir;    // non-empty: every packed problem is written there before it is solved (mcba_problem_save)
 
 // ---------------------------------------------------------------------------------------------- pose helpers
 void rotVecToMat(const double* rv, double* R) {
@@ -161,6 +162,12 @@ bool solveStages(Packed& pk, const std::vector<int>& stages, int nb_iterations) 
     opt.max_num_iterations = nb_iterations; opt.verbose = g_verbose;   // minimizer_progress_to_stdout = true in the reference
     mcba_params X = pk.params();
     mcba_summary summary;
+    if (!g_problem_dump_dir.empty()) {   // checkpoint: the packed problem and the parameters this solve starts from
+      static int n_dumped = 0;
+      mcba_problem Pk = P; Pk.stage = stages[k];
+      const std::string path = g_problem_dump_dir + "/problem_" + std::to_string(n_dumped++) + "_stage" + std::to_string(stages[k]) + ".mcba";
+      if (mcba_problem_save(path.c_str(), &Pk, &X) != MCBA_OK) std::fprintf(stderr, "[McCalibBA] %s: %s\n", path.c_str(), mcba_io_last_error());
+    }
     rc = mcba_solve(h, &X, &opt, &summary, nullptr, 0);
     if (rc == MCBA_OK) pk.scatter(stages[k]);
   }

@@ -186,6 +186,7 @@ std::array<double, 3> getAverageRotation(std::vector<double>& r1, std::vector<do
                                          const bool use_quaternion_averaging = true);
 
 extern int g_verbose;              // 1: per-iteration table on stdout like minimizer_progress_to_stdout (default)
+extern std::string g_problem_dump_dir;   // non-empty: solveStages writes every packed problem + start parameters there (MCBAPRB1, include/mcba.h)
 extern int g_cuda_device;          // device used by the refine* methods (set from Calibration::cuda_device_)
 extern std::string g_last_error;   // text of the last libmcba failure (the reference ignores solver failures)
 

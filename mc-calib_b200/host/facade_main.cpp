@@ -24,6 +24,7 @@ int main(int argc, char** argv) {
   const std::string flow = argv[2];
   Calibration calib;
   g_verbose = 0;
+  if (const char* d = std::getenv("MCBA_DUMP_PROBLEM_DIR")) g_problem_dump_dir = d;   // checkpoint every packed problem (mcba_problem_save)
   int n_cam, n_board, n_frames, n_bobs;
   in >> n_cam >> n_board >> n_frames >> n_bobs >> calib.nb_iterations_ >> calib.fix_intrinsic_;
   const bool do_init = flow == "init" || flow == "init_final";

@@ -195,6 +195,11 @@ def load_lib():
     L.mcba_timer_stop.argtypes = [vp, c_f64p]
     L.mcba_debug_fetch.argtypes = [vp, C.c_char_p, c_f64p, C.c_int64, C.POINTER(C.c_int64)]
     L.mcba_debug_set_k1.argtypes = [C.c_int]
+    L.mcba_problem_save.argtypes = [C.c_char_p, C.POINTER(mcba_problem), C.POINTER(mcba_params)]
+    L.mcba_problem_load.argtypes = [C.c_char_p, C.POINTER(mcba_problem), C.POINTER(mcba_params), vpp]
+    L.mcba_problem_free.argtypes = [vp]
+    L.mcba_problem_free.restype = None
+    L.mcba_io_last_error.restype = C.c_char_p
     L.mcba_debug_cholesky.argtypes = [vp, C.c_int, c_f64p, c_f64p, c_f64p, C.c_int, C.c_int, c_f64p, C.POINTER(C.c_int)]
     _lib = L
     return L
@@ -202,6 +207,46 @@ def load_lib():
 
 class McbaError(RuntimeError):
     pass
+
+
+def save_problem(path, problem, params=None):
+    """Binary dump of a packed problem (+ parameter blocks): mcba_problem_save, the "MCBAPRB1" format."""
+    L = load_lib()
+    cp = problem.c()
+    cq = params.c() if params is not None else None
+    rc = L.mcba_problem_save(os.fsencode(path), C.byref(cp), C.byref(cq) if cq is not None else None)
+    if rc != 0:
+        raise McbaError(f"mcba_problem_save rc={rc}: {L.mcba_io_last_error().decode()}")
+
+
+def load_problem(path):
+    """-> (Problem, Params or None) from a file written by mcba_problem_save (copies out of the library's storage)."""
+    L = load_lib()
+    cp, cq, st = mcba_problem(), mcba_params(), C.c_void_p()
+    rc = L.mcba_problem_load(os.fsencode(path), C.byref(cp), C.byref(cq), C.byref(st))
+    if rc != 0:
+        raise McbaError(f"mcba_problem_load rc={rc}: {L.mcba_io_last_error().decode()}")
+    try:
+        def arr(ptr, n, dt):
+            if not ptr:
+                return None
+            return np.ctypeslib.as_array(ptr, shape=(int(n),)).astype(dt, copy=True) if n else np.zeros(0, dt)
+        nb, no, nc = cp.n_bobs, cp.n_obs, cp.n_cam
+        prob = Problem(cp.stage, arr(cp.u, no, np.float32), arr(cp.v, no, np.float32), arr(cp.pt_idx, no, np.int32),
+                       arr(cp.bobs_ptr, nb + 1, np.int64), arr(cp.bobs_cam, nb, np.int32), arr(cp.bobs_pose, nb, np.int32),
+                       arr(cp.bobs_board, nb, np.int32), arr(cp.pts_xyz, 3 * cp.n_pts, np.float32),
+                       arr(cp.cam_model, nc, np.int32), cp.n_pose, cp.n_board, arr(cp.cam_is_ref, nc, np.uint8),
+                       arr(cp.board_is_ref, cp.n_board, np.uint8), arr(cp.cam_problem, nc, np.int32), cp.n_problems)
+        params = None
+        if cq.pose or cq.intrinsics or cq.cam_pose or cq.board_pose:
+            z = lambda n, w: np.zeros((n, w))
+            params = Params(arr(cq.cam_pose, 6 * nc, np.float64) if cq.cam_pose else z(nc, 6),
+                            arr(cq.pose, 6 * cp.n_pose, np.float64) if cq.pose else z(cp.n_pose, 6),
+                            arr(cq.board_pose, 6 * cp.n_board, np.float64) if cq.board_pose else z(cp.n_board, 6),
+                            arr(cq.intrinsics, 9 * nc, np.float64) if cq.intrinsics else z(nc, 9))
+    finally:
+        L.mcba_problem_free(st)
+    return prob, params
 
 
 def obs_register(problem, device=0):

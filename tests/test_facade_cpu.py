@@ -156,3 +156,49 @@ def test_workflow_head_from_files(bins, tmp_path, oracle):
     fs.release()
     line = [l for l in r.stdout.splitlines() if l.startswith("valid board observations")][0].split()
     assert int(line[3]) == len(o.bobs_cam) and 0.2 < float(line[-2]) < 0.6
+
+
+def test_facade_dumps_the_packed_problems(bins, tmp_path, scene, monkeypatch):
+    """MCBA_DUMP_PROBLEM_DIR: solveStages checkpoints every packed problem with the parameters the solve starts from
+    (mcba_problem_save). The stage-4 dump of the final flow holds, board observation for board observation, the problem
+    packed in Python - the packer's slot assignment and corner tables checked without going through a solve - and the
+    stage-5 dump the same arrays with the parameters stage 4 ended at."""
+    s, o = scene
+    d = tmp_path / "dumps"
+    d.mkdir()
+    monkeypatch.setenv("MCBA_DUMP_PROBLEM_DIR", str(d))
+    got = run(bins[0], tmp_path, s, o, "final")
+    files = sorted(os.listdir(d))
+    assert files == ["problem_0_stage4.mcba", "problem_1_stage5.mcba"]
+    p4, x4 = mcba.load_problem(str(d / files[0]))
+    p5, x5 = mcba.load_problem(str(d / files[1]))
+    prob, init, gt = synth.make_problem(s, o, 4)
+    assert (p4.stage, p5.stage) == (4, 5) and p4.n_board == prob.n_board and p4.n_cam == prob.n_cam
+    # the facade numbers cameras / boards in the order its walk first meets them (Packed::camSlot / boardSlot): recover
+    # the relabelling from the parameter blocks (initial intrinsics and board poses are distinct per camera / board)
+    cam_of = [int(np.argmin(np.abs(s.intr_init - x4.intrinsics[f]).max(axis=1))) for f in range(p4.n_cam)]
+    board_of = [int(np.argmin(np.abs(init.board_pose - x4.board_pose[f]).max(axis=1))) for f in range(p4.n_board)]
+    assert sorted(cam_of) == list(range(s.n_cam)) and sorted(board_of) == list(range(s.n_board))
+    assert np.abs(x4.intrinsics - s.intr_init[cam_of]).max() == 0.0 and np.abs(x4.board_pose - init.board_pose[board_of]).max() <= 1e-12
+
+    def canon(p, cam_of=None, board_of=None):   # board observations keyed by (e-block, camera, board)
+        out = {}
+        rank = np.unique(p.bobs_pose, return_inverse=True)[1]   # e-block slots: only observed (frame, object) pairs get one
+        for b in range(p.n_bobs):
+            sl = slice(p.bobs_ptr[b], p.bobs_ptr[b + 1])
+            c, bd = int(p.bobs_cam[b]), int(p.bobs_board[b])
+            key = (int(rank[b]), cam_of[c] if cam_of else c, board_of[bd] if board_of else bd)
+            assert key not in out
+            out[key] = (p.u[sl].tobytes(), p.v[sl].tobytes(), p.pts_xyz[p.pt_idx[sl]].tobytes())
+        return out
+    ref = canon(prob)
+    assert canon(p4, cam_of, board_of) == ref and canon(p5, cam_of, board_of) == ref and p4.n_obs == prob.n_obs
+    assert np.all(np.diff(p4.bobs_pose) >= 0) and np.array_equal(p4.cam_model, prob.cam_model[cam_of])
+    for k in ("u", "v", "pt_idx", "bobs_ptr", "bobs_cam", "bobs_pose", "bobs_board", "cam_model"):
+        assert np.array_equal(getattr(p4, k), getattr(p5, k)), k
+    assert np.array_equal(p4.cam_is_ref, prob.cam_is_ref[cam_of]) and np.array_equal(p4.board_is_ref, prob.board_is_ref[board_of])
+    seen = np.unique(prob.bobs_pose)
+    assert p4.n_pose == len(seen)
+    assert np.abs(x4.pose - init.pose[seen]).max() <= 1e-12 and np.abs(x4.cam_pose - init.cam_pose[cam_of]).max() <= 1e-12
+    assert np.abs(x5.pose - x4.pose).max() > 0.0                                     # stage 4 moved the e-blocks
+    assert np.abs(x5.intrinsics - x4.intrinsics).max() == 0.0                        # ... and not the intrinsics

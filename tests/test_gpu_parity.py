@@ -471,3 +471,33 @@ def test_fused_observation_kernel_variants_write_identical_records(stage, oracle
                 assert abs(cost - ref[1]) <= 1e-14 * abs(ref[1])
     finally:
         lib.mcba_debug_set_k1(-1)
+
+
+def test_problem_file_replay_and_resume(tmp_path, c2):
+    """mcba_problem_save / mcba_problem_load (checkpoint / resume): a solve replayed from the file is
+    bit-identical to the solve from the arrays in memory, and a solve resumed from the parameters saved after three
+    iterations ends at the same minimum."""
+    prob, init = stage_problem(c2, 5)[:2]
+    path = str(tmp_path / "c2.mcba")
+    mcba.save_problem(path, prob, init)
+    p2, x2 = mcba.load_problem(path)
+    ha, hb = mcba.Handle(prob), mcba.Handle(p2)
+    pa, pb = init.copy(), x2.copy()
+    sa, ta = ha.solve(pa)
+    sb, tb = hb.solve(pb)
+    assert trace_tuple(ta) == trace_tuple(tb) and sa.final_cost == sb.final_cost
+    for k in ("cam_pose", "pose", "board_pose", "intrinsics"):
+        assert np.array_equal(getattr(pa, k), getattr(pb, k)), k
+    # checkpoint after 3 iterations, resume from the file
+    pc = init.copy()
+    sc, _ = ha.solve(pc, mcba.default_options(max_num_iterations=3))
+    assert sc.termination == 1                                     # NO_CONVERGENCE: stopped by the iteration limit
+    ck = str(tmp_path / "c2_it3.mcba")
+    mcba.save_problem(ck, prob, pc)
+    p3, x3 = mcba.load_problem(ck)
+    hc = mcba.Handle(p3)
+    sd, _ = hc.solve(x3)
+    assert sd.termination == 0 and abs(sd.rms_px - sa.rms_px) <= 1e-6
+    assert rel(x3.intrinsics, pa.intrinsics) <= 1e-6
+    for h in (ha, hb, hc):
+        h.close()
