@@ -196,8 +196,9 @@ const char *mcba_io_last_error(void);
 int mcba_debug_fetch(void *handle, const char *name, double *out, int64_t cap, int64_t *n_out);
 /* Test hook: fused observation kernel of the handles created afterwards. 0 = k_observations_fused, 3 =
  * k_observations_pair (two board observations per warp), 1 = first version (k_observations<S, MODE_FUSED>),
- * 2 = streaming experiment; -1 = back to the MCBA_K1 environment variable (unset: 0 at stage 5, 3 otherwise).
- * All variants write bit-identical per-board-observation records. */
+ * 2 = streaming experiment, 4 = 24-corner passes with 16 warps per SM (experiment); -1 = back to the MCBA_K1
+ * environment variable (unset: 0 at stage 5, 3 otherwise). Variants 0-3 write bit-identical per-board-observation
+ * records; 4 differs at rounding level (other multiply-add contractions). */
 int mcba_debug_set_k1(int variant);
 /* Test / benchmark hook: factor and solve one dense symmetric positive definite system with the reduced-system
  * kernels alone. S_host is (n+1) x n row-major (matrix rows, then the right-hand side as row n); z_out [n] = solution,

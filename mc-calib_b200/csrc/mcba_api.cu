@@ -345,6 +345,7 @@ static int setup_stage(Handle* H, int stage) {
     CU(cudaFuncSetAttribute(k_observations_stream<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, OBS_WARPS * (2 * CTX_SIZE + Cols<ST>::NC * TS) * 8));
     CU(cudaFuncSetAttribute(k_observations_fused<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem<ST>::BYTES));
     CU(cudaFuncSetAttribute(k_observations_pair<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem<ST>::BYTES));
+    CU(cudaFuncSetAttribute(k_observations_fused<ST, 24, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem<ST, 24, false>::BYTES));
     CU(cudaFuncSetAttribute(k_eblock_assemble<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * (H->ldz + EA_PAD) * 8));
   });
   return MCBA_OK;
@@ -403,6 +404,9 @@ template <int MODE> static int launch_obs(Handle* H, int which, double huber_a) 
   //   3 = k_observations_pair: the same with two board observations per warp (one per half-warp, 16 corners per pass);
   //   1 = the first version k_observations<S, MODE_FUSED> (also what gated / batched handles run);
   //   2 = the streaming experiment (tails of consecutive board observations share a warp pass; slower than version 1);
+  //   4 = k_observations_fused with 24-corner passes, one context slot and 4 CTAs (16 warps) per SM at 128 registers:
+  //       0.91 ms at stage 5 (spills), 0.60 ms at stage 4 (= variant 0): the kernel is bound by the pipe the DMMA and DFMA
+  //       instructions share (63 % busy) and the shared-memory wavefronts (56 %), not by the number of resident warps;
   //  -1 = automatic (default): 0 at stage 5, where two sets of accumulators do not fit the register budget of 3 CTAs
   //       per SM next to the 27-column Jacobian (measured 0.80 vs 0.75 ms), 3 at the other stages (0.54 vs 0.60 ms at
   //       stage 4). All variants write bit-identical records.
@@ -424,6 +428,16 @@ template <int MODE> static int launch_obs(Handle* H, int which, double huber_a) 
       const int grid = grid_for(H, (H->nb + 1) / 2, std::min(3, std::max(1, (227 * 1024) / (sm + 1024))));
       ++H->n_launches;
       k_observations_pair<ST><<<grid, OBS_WARPS * 32, sm, H->stream>>>(a);
+    });
+    CHECK_LAUNCH();
+    return MCBA_OK;
+  }
+  if (MODE == MODE_FUSED && k1v == 4 && !a.gate) {   // experiment: 24-corner passes, one context slot, 4 CTAs (16 warps) per SM
+    DISPATCH_STAGE(H->stage, {
+      const int sm = FusedSmem<ST, 24, false>::BYTES;
+      const int grid = grid_for(H, H->nb, std::min(4, std::max(1, (227 * 1024) / (sm + 1024))));
+      ++H->n_launches;
+      k_observations_fused<ST, 24, 4, false><<<grid, OBS_WARPS * 32, sm, H->stream>>>(a);
     });
     CHECK_LAUNCH();
     return MCBA_OK;

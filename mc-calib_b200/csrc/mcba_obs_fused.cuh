@@ -63,27 +63,39 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-template <int STAGE> struct FusedSmem {
+// PASS corners per warp pass (tile rows = 2 PASS, row pitch 2 PASS + 4: pitch mod 16 == 4 for 32 and 24), DBUF: two
+// context slots (copy for the next board observation issued during the first pass) or one (issued after the last
+// Jacobian phase, lands during the last DMMA phase).
+template <int PASS> struct TileSinkP {
+  static constexpr int PITCH = 2 * PASS + 4;
+  double* T; int lane;
+  __device__ __forceinline__ void put(int col, double ju, double jv) {
+    *reinterpret_cast<double2*>(T + col * PITCH + 2 * lane) = make_double2(ju, jv);
+  }
+};
+template <int STAGE, int PASS = OBS_PASS, bool DBUF = true> struct FusedSmem {
   typedef Cols<STAGE> C;
   static constexpr int NG = (C::NC + 3) / 4;
-  static constexpr int TILE = 4 * NG * TS;                      // pad columns stay zero
-  static constexpr int WARP_DOUBLES = 2 * CtxRaw::SIZE + TILE;
+  static constexpr int PITCH = 2 * PASS + 4;
+  static constexpr int TILE = 4 * NG * PITCH;                   // pad columns stay zero
+  static constexpr int WARP_DOUBLES = (DBUF ? 2 : 1) * CtxRaw::SIZE + TILE;
   static constexpr int NR = RectCover<NG>::NR;
   static constexpr int IDX_BYTES = NR * 32 * 4;                 // per CTA: record index of every accumulator entry (short2 per product and lane)
   static constexpr int BYTES = OBS_WARPS * WARP_DOUBLES * 8 + IDX_BYTES;
 };
 
-template <int STAGE>
-__global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_fused(ObsArgs a) {
+template <int STAGE, int PASS = OBS_PASS, int MINB = 3, bool DBUF = true>
+__global__ void __launch_bounds__(OBS_WARPS * 32, MINB) k_observations_fused(ObsArgs a) {
   typedef Cols<STAGE> C;
   typedef StageTraits<STAGE> ST;
-  typedef FusedSmem<STAGE> SM;
+  typedef FusedSmem<STAGE, PASS, DBUF> SM;
+  constexpr int TSP = SM::PITCH;
   typedef RectCover<SM::NG> RCV;
   constexpr int NG = SM::NG, NR = RCV::NR;
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* cbuf = smem + warp * SM::WARP_DOUBLES;
-  double* T = cbuf + 2 * CtxRaw::SIZE;
+  double* T = cbuf + (DBUF ? 2 : 1) * CtxRaw::SIZE;
   const int total_warps = gridDim.x * OBS_WARPS;
   const int g = lane >> 2, q = lane & 3, hi = lane >> 4, c4 = g & 3;
   // Where each accumulator entry goes in the compact record (-1: not stored): lane constants, kept in shared memory -
@@ -147,12 +159,12 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_fused(ObsArg
   int4 rec_n = rec; int end_n = obs_end;
   if (b + total_warps < a.nb) { rec_n = a.bobs[b + total_warps]; end_n = a.bobs[b + total_warps + 1].x; }
   float pf_u = 0.f, pf_v = 0.f; int pf_pt = 0;
-  if (rec.x + lane < obs_end) { pf_u = a.u[rec.x + lane]; pf_v = a.v[rec.x + lane]; pf_pt = a.pt[rec.x + lane]; }
+  if (lane < PASS && rec.x + lane < obs_end) { pf_u = a.u[rec.x + lane]; pf_v = a.v[rec.x + lane]; pf_pt = a.pt[rec.x + lane]; }
   double nX[3];
   { const double* p3 = a.pts + 3 * (size_t)pf_pt; nX[0] = p3[0]; nX[1] = p3[1]; nX[2] = p3[2]; }
   int par = 0;
   while (true) {
-    double* ctx = cbuf + par * CtxRaw::SIZE;
+    double* ctx = cbuf + (DBUF ? par : 0) * CtxRaw::SIZE;
     const int bn = b + total_warps, bnn = bn + total_warps;
     const bool has_n = bn < a.nb;
     int4 rec_nn = rec_n; int end_nn = end_n;              // records run two board observations ahead, flags one
@@ -172,37 +184,38 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_fused(ObsArg
     for (int t = 0; t < NR; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
     double cost = 0.0;
     const int obs_begin = rec.x;
-    for (int base = obs_begin; base < obs_end; base += OBS_PASS) {
-      const int nact = min(OBS_PASS, obs_end - base);
+    for (int base = obs_begin; base < obs_end; base += PASS) {
+      const int nact = min(PASS, obs_end - base);
       const bool active = lane < nact;
       const float cur_u = pf_u, cur_v = pf_v;
       const double X0[3] = {nX[0], nX[1], nX[2]};
       // pixels / corner index of the following pass: of this board observation, or the first one of the next
-      const bool last_pass = base + OBS_PASS >= obs_end;
-      const int nxt = last_pass ? rec_n.x + lane : base + OBS_PASS + lane;
+      const bool last_pass = base + PASS >= obs_end;
+      const int nxt = last_pass ? rec_n.x + lane : base + PASS + lane;
       const int nxt_end = last_pass ? end_n : obs_end;
-      const bool nxt_ok = (has_n || !last_pass) && nxt < nxt_end;
+      const bool nxt_ok = lane < PASS && (has_n || !last_pass) && nxt < nxt_end;
       if (nxt_ok) { pf_u = a.u[nxt]; pf_v = a.v[nxt]; pf_pt = a.pt[nxt]; }
       if (active) {
-        TileSink sink{T, lane};
-        cost += obs_jacobian<STAGE, TileSink, CtxRaw>(ctx, act_c, act_b, model, X0, (double)cur_u, (double)cur_v, a.huber_a, sink);
+        TileSinkP<PASS> sink{T, lane};
+        cost += obs_jacobian<STAGE, TileSinkP<PASS>, CtxRaw>(ctx, act_c, act_b, model, X0, (double)cur_u, (double)cur_v, a.huber_a, sink);
       } else if (lane == nact && (nact & 1)) {           // the odd corner's partner rows of the last k-step
 #pragma unroll
         for (int col = 0; col < C::NC; ++col)
-          *reinterpret_cast<double2*>(T + col * TS + 2 * lane) = make_double2(0.0, 0.0);
+          *reinterpret_cast<double2*>(T + col * TSP + 2 * lane) = make_double2(0.0, 0.0);
       }
       if (nxt_ok) { const double* p3 = a.pts + 3 * (size_t)pf_pt; nX[0] = p3[0]; nX[1] = p3[1]; nX[2] = p3[2]; }
-      if (base == obs_begin && has_n) issue_ctx(rec_n, fl_n, cbuf + (par ^ 1) * CtxRaw::SIZE);
+      if (DBUF && base == obs_begin && has_n) issue_ctx(rec_n, fl_n, cbuf + (par ^ 1) * CtxRaw::SIZE);
       __syncwarp();
+      if (!DBUF && last_pass && has_n) issue_ctx(rec_n, fl_n, cbuf);   // nobody reads the context any more in this iteration
       const int ksteps = (2 * nact + 3) >> 2;
-      const double* Tl = T + c4 * TS + q;
+      const double* Tl = T + c4 * TSP + q;
       double G[NG], Gn[NG];
 #pragma unroll
-      for (int j = 0; j < NG; ++j) G[j] = Tl[4 * j * TS];
+      for (int j = 0; j < NG; ++j) G[j] = Tl[4 * j * TSP];
       for (int ks = 0; ks < ksteps; ++ks) {
         const int kn = min(ks + 1, ksteps - 1);
 #pragma unroll
-        for (int j = 0; j < NG; ++j) Gn[j] = Tl[4 * j * TS + 4 * kn];
+        for (int j = 0; j < NG; ++j) Gn[j] = Tl[4 * j * TSP + 4 * kn];
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
           const double fa = hi ? G[RCV::r1(r)] : G[RCV::r0(r)];
@@ -213,6 +226,13 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_fused(ObsArg
         for (int j = 0; j < NG; ++j) G[j] = Gn[j];
       }
       __syncwarp();
+    }
+    if (obs_begin >= obs_end && has_n) {                  // empty board observation: no pass prefetched for the next one
+      issue_ctx(rec_n, fl_n, cbuf + (DBUF ? (par ^ 1) : 0) * CtxRaw::SIZE);
+      if (lane < PASS && rec_n.x + lane < end_n) {
+        pf_u = a.u[rec_n.x + lane]; pf_v = a.v[rec_n.x + lane]; pf_pt = a.pt[rec_n.x + lane];
+        const double* p3 = a.pts + 3 * (size_t)pf_pt; nX[0] = p3[0]; nX[1] = p3[1]; nX[2] = p3[2];
+      }
     }
     {
       double* out = a.brec + (size_t)b * C::NCOMP;
@@ -405,6 +425,13 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_pair(ObsArgs
         for (int j = 0; j < NG; ++j) { GA[j] = GAn[j]; GB[j] = GBn[j]; }
       }
       __syncwarp();
+    }
+    if (npass == 0 && has_n) {                             // both board observations empty: nothing prefetched for the next pair
+      issue_ctx(rec_n, fl_n);
+      if (rec_n.x + l16 < end_n) {
+        pf_u = a.u[rec_n.x + l16]; pf_v = a.v[rec_n.x + l16]; pf_pt = a.pt[rec_n.x + l16];
+        const double* p3 = a.pts + 3 * (size_t)pf_pt; nX[0] = p3[0]; nX[1] = p3[1]; nX[2] = p3[2];
+      }
     }
     {
       const int bA = 2 * p, bB = 2 * p + 1;

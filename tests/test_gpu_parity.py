@@ -418,7 +418,7 @@ def test_registered_observations_are_shared_between_pose_init_and_bundle_adjustm
 
 
 def _ragged_problem(stage, seed=3):
-    """c2 scene with random corner counts per board observation (1 .. all 16, odd and even) and an odd number of
+    """c2 scene with random corner counts per board observation (0 .. all 16, odd and even) and an odd number of
     board observations: the tail handling of the fused observation kernels (half-empty passes, the zeroed partner row
     of an odd corner count, the unpaired last board observation of k_observations_pair)."""
     s = synth.make_scene("c2", n_frames=41)
@@ -430,6 +430,7 @@ def _ragged_problem(stage, seed=3):
     if prob.n_bobs % 2 == 0:
         keep_bobs[-1] = False
     new_counts = np.minimum(counts, rng.integers(1, counts.max() + 1, prob.n_bobs))
+    new_counts[[5, 40, 41, 77, 78, 79]] = 0                      # empty board observations, also a whole empty pair / warp turn
     obs_keep = np.zeros(prob.n_obs, bool)
     for b in range(prob.n_bobs):
         if keep_bobs[b]:
@@ -443,8 +444,8 @@ def _ragged_problem(stage, seed=3):
 
 @pytest.mark.parametrize("stage", [1, 2, 3, 4, 5])
 def test_fused_observation_kernel_variants_write_identical_records(stage, oracle):
-    """k_observations_fused (0), k_observations_pair (3) and the streaming experiment (2) against the first version
-    (1): same per-corner arithmetic and the same row order of the DMMA sums, so the per-board-observation records and
+    """k_observations_fused (0), k_observations_pair (3), the streaming experiment (2) and the 16-warp experiment (4)
+    against the first version (1): same per-corner arithmetic and the same row order of the DMMA sums, so the per-board-observation records and
     costs are identical bit for bit - on ragged corner counts too - and the first version is the one the oracle
     comparison of the normal equations was made with (test_normal_equations_and_schur runs the default variant)."""
     lib = mcba.load_lib()
@@ -452,7 +453,7 @@ def test_fused_observation_kernel_variants_write_identical_records(stage, oracle
     assert prob.n_bobs % 2 == 1 and len(set(np.diff(prob.bobs_ptr) % 2)) == 2
     ref = None
     try:
-        for variant in (1, 0, 3, 2):
+        for variant in (1, 0, 3, 2, 4):
             lib.mcba_debug_set_k1(variant)
             h = mcba.Handle(prob)
             h.solve_begin(init.copy(), mcba.default_options())
@@ -467,7 +468,8 @@ def test_fused_observation_kernel_variants_write_identical_records(stage, oracle
                 assert rc == 0 and abs(cost - co) <= 1e-11 * abs(co)
             else:
                 scale = np.abs(ref[0]).max()
-                assert np.abs(rec - ref[0]).max() <= 1e-15 * scale, f"variant {variant}"
+                # variant 4 (24-corner passes) compiles obs_jacobian with other multiply-add contractions: rounding level
+                assert np.abs(rec - ref[0]).max() <= (1e-12 if variant == 4 else 1e-15) * scale, f"variant {variant}"
                 assert abs(cost - ref[1]) <= 1e-14 * abs(ref[1])
     finally:
         lib.mcba_debug_set_k1(-1)
