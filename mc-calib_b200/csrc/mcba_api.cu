@@ -77,7 +77,7 @@ struct Handle {
   std::vector<int64_t> h_bobs_ptr;
   // static device data
   float *d_u = nullptr, *d_v = nullptr; int32_t* d_pt = nullptr; double* d_pts = nullptr;
-  int4* d_bobs = nullptr; int* d_pose_bobs_ptr = nullptr;
+  int4* d_bobs = nullptr; int* d_pose_bobs_ptr = nullptr; int* d_bobs_flags = nullptr;
   int32_t* d_cam_model = nullptr; uint8_t *d_cam_is_ref = nullptr, *d_board_is_ref = nullptr;
   // stage-dependent
   FLayout fl{};   // padded column layout of Wt / Z / ZtZ
@@ -375,7 +375,7 @@ static ObsArgs obs_args(Handle* H, int which, double huber_a) {
   a.prep_cam = H->d_prep_cam; a.prep_pose = H->d_prep_pose; a.prep_board = H->d_prep_board; a.intr = H->d_intr[which];
   a.cam_model = H->d_cam_model; a.cam_is_ref = H->d_cam_is_ref; a.board_is_ref = H->d_board_is_ref;
   a.huber_a = huber_a; a.nb = H->nb; a.brec = H->brec_target ? H->brec_target : H->d_brec; a.cost_bobs = H->d_cost_bobs;
-  a.jmat = H->d_jmat; a.resmat = H->d_resmat; a.npad = H->npad; a.gate = H->obs_gate;
+  a.jmat = H->d_jmat; a.resmat = H->d_resmat; a.npad = H->npad; a.gate = H->obs_gate; a.bobs_flags = H->d_bobs_flags;
   return a;
 }
 
@@ -1119,7 +1119,7 @@ void mcba_destroy(void* h) {
   for (auto e : H->free_events) cudaEventDestroy(e);
   if (H->tm_a) { cudaEventDestroy(H->tm_a); cudaEventDestroy(H->tm_b); }
   if (H->obs_shared) { obs_cache_release(H->d_u); H->d_u = nullptr; H->d_v = nullptr; H->d_pt = nullptr; }
-  dfree(H, &H->d_u); dfree(H, &H->d_v); dfree(H, &H->d_pt); dfree(H, &H->d_pts); dfree(H, &H->d_bobs); dfree(H, &H->d_pose_bobs_ptr);
+  dfree(H, &H->d_u); dfree(H, &H->d_v); dfree(H, &H->d_pt); dfree(H, &H->d_pts); dfree(H, &H->d_bobs); dfree(H, &H->d_pose_bobs_ptr); dfree(H, &H->d_bobs_flags);
   dfree(H, &H->d_cam_model); dfree(H, &H->d_cam_is_ref); dfree(H, &H->d_board_is_ref);
   dfree(H, &H->d_pair_bobs); dfree(H, &H->d_chunks); dfree(H, &H->d_pair_chunk_ptr);
   dfree(H, &H->d_brec); dfree(H, &H->d_brec_alt); dfree(H, &H->d_cost_bobs); dfree(H, &H->d_Hoo); dfree(H, &H->d_Wt); dfree(H, &H->d_Z); dfree(H, &H->d_L);
@@ -1178,6 +1178,7 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   mark("device + stream");
   // validate + pack the board-observation table (host, small)
   std::vector<int4> bobs(H->nb + 1);
+  std::vector<int> bflags(H->nb + 1, 0);
   std::vector<int> ppt(H->n_pose + 1, 0);
   H->h_bobs_cam.resize(H->nb); H->h_bobs_pose.resize(H->nb); H->h_bobs_board.resize(H->nb);
   H->h_bobs_ptr.assign(P->bobs_ptr, P->bobs_ptr + H->nb + 1);
@@ -1187,6 +1188,7 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
         P->bobs_ptr[b] > P->bobs_ptr[b + 1] || P->bobs_ptr[b] < 0 || P->bobs_ptr[b + 1] > P->n_obs ||
         (H->n_board > 0 && (bd < 0 || bd >= H->n_board))) { H->err = "inconsistent board-observation table"; return MCBA_ERR_INVALID; }
     bobs[b] = make_int4((int)P->bobs_ptr[b], c, o, H->n_board > 0 ? bd : 0);
+    bflags[b] = ((P->cam_is_ref && P->cam_is_ref[c]) ? 1 : 0) | ((P->board_is_ref && H->n_board > 0 && P->board_is_ref[bd]) ? 2 : 0) | (P->cam_model[c] << 2);
     H->h_bobs_cam[b] = c; H->h_bobs_pose[b] = o; H->h_bobs_board[b] = H->n_board > 0 ? bd : 0;
     ppt[o + 1] = b + 1;
   }
@@ -1212,12 +1214,13 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   std::vector<double> pts((size_t)std::max(1, P->n_pts) * 3);
   for (int i = 0; i < P->n_pts * 3; ++i) pts[i] = (double)P->pts_xyz[i];
   mark("validate + pack (host)");
-  if (dalloc(H, &H->d_pts, pts.size()) || dalloc(H, &H->d_bobs, bobs.size()) || dalloc(H, &H->d_pose_bobs_ptr, ppt.size())) return MCBA_ERR_CUDA;
+  if (dalloc(H, &H->d_pts, pts.size()) || dalloc(H, &H->d_bobs, bobs.size()) || dalloc(H, &H->d_pose_bobs_ptr, ppt.size()) || dalloc(H, &H->d_bobs_flags, bflags.size())) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_cam_model, (size_t)H->n_cam) || dalloc(H, &H->d_cam_is_ref, (size_t)H->n_cam) || dalloc(H, &H->d_board_is_ref, (size_t)std::max(1, H->n_board))) return MCBA_ERR_CUDA;
   // small tables from vector storage of this call: pageable copies are staged before cudaMemcpyAsync returns
   CU(cudaMemcpyAsync(H->d_pts, pts.data(), pts.size() * sizeof(double), cudaMemcpyHostToDevice, H->stream));
   CU(cudaMemcpyAsync(H->d_bobs, bobs.data(), bobs.size() * sizeof(int4), cudaMemcpyHostToDevice, H->stream));
   CU(cudaMemcpyAsync(H->d_pose_bobs_ptr, ppt.data(), ppt.size() * sizeof(int), cudaMemcpyHostToDevice, H->stream));
+  CU(cudaMemcpyAsync(H->d_bobs_flags, bflags.data(), bflags.size() * sizeof(int), cudaMemcpyHostToDevice, H->stream));
   CU(cudaMemcpyAsync(H->d_cam_model, P->cam_model, H->n_cam * sizeof(int32_t), cudaMemcpyHostToDevice, H->stream));
   std::vector<uint8_t> zc((size_t)std::max(H->n_cam, std::max(1, H->n_board)), 0);
   CU(cudaMemcpyAsync(H->d_cam_is_ref, P->cam_is_ref ? P->cam_is_ref : zc.data(), H->n_cam, cudaMemcpyHostToDevice, H->stream));

@@ -41,6 +41,7 @@ struct ObsArgs {
   double* cost_bobs;                // [nb]
   double* jmat; double* resmat;     // materialised Jacobian blocks (see BlockSink); resmat unused
   int64_t npad;
+  const int* bobs_flags;            // [nb] bit 0: reference camera, bit 1: reference board, camera model << 2 (the fused kernels of round 2)
   const uint8_t* gate;              // batched problems: per-camera flag, board observations of gated-off cameras are skipped
 };
 

@@ -130,17 +130,10 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, MINB) k_observations_fused(Obs
     if (lane < 4) { const int e = 23 + lane, k = e / 9, i = (e % 9) / 3, j = e % 3; m2 = CtxRaw::MC + 3 * i; d2 = CtxRaw::PO + 9 + 9 * k + j; o2 = CtxRaw::NO + e; }
     else { const int e = min(lane - 4, 26), k = e / 9, i = (e % 9) / 3, j = e % 3; m2 = CtxRaw::MCO + 3 * i; d2 = CtxRaw::PB + 9 + 9 * k + j; o2 = CtxRaw::NB + e; }
   }
-  // flags of a board observation: raw loads (combined where they are used, so that nothing waits on them early)
-  struct Flags { unsigned char cref, bref; int model; };
-  auto load_flags = [&](const int4& r) {
-    Flags f;
-    f.cref = (ST::CAM && a.cam_is_ref) ? a.cam_is_ref[r.y] : 0;
-    f.bref = (ST::BOARD && a.board_is_ref) ? a.board_is_ref[r.w] : 0;
-    f.model = a.cam_model[r.y];
-    return f;
-  };
-  auto issue_ctx = [&](const int4& r, const Flags& f, double* dst) {   // raw context of one board observation -> dst (asynchronous)
-    const bool act_c = ST::CAM && !f.cref, act_b = ST::BOARD && !f.bref;
+  // flags of a board observation (ObsArgs::bobs_flags: bit 0 reference camera, bit 1 reference board, camera model
+  // << 2): one word per board observation, so that nothing has to be looked up through the record
+  auto issue_ctx = [&](const int4& r, int f, double* dst) {   // raw context of one board observation -> dst (asynchronous)
+    const bool act_c = ST::CAM && !(f & 1), act_b = ST::BOARD && !(f & 2);
     const double* pc = act_c ? a.prep_cam + (size_t)PREP * r.y : g_prep_identity;
     const double* po = a.prep_pose + (size_t)PREP * r.z;
     const double* pb = act_b ? a.prep_board + (size_t)PREP * r.w : g_prep_identity;
@@ -151,44 +144,40 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, MINB) k_observations_fused(Obs
       cp_async8(dst + e, src);
     }
   };
-  // prologue: this warp's first board observation; the record of the second one
-  int4 rec = a.bobs[b];
-  int obs_end = a.bobs[b + 1].x;
-  Flags fl = load_flags(rec);
-  issue_ctx(rec, fl, cbuf);
-  int4 rec_n = rec; int end_n = obs_end;
-  if (b + total_warps < a.nb) { rec_n = a.bobs[b + total_warps]; end_n = a.bobs[b + total_warps + 1].x; }
+  // prologue: this warp's first board observation
+  int obs_begin, obs_end, fl;
+  {
+    const int4 rec = a.bobs[b];
+    obs_begin = rec.x; obs_end = a.bobs[b + 1].x; fl = a.bobs_flags[b];
+    issue_ctx(rec, fl, cbuf);
+  }
   float pf_u = 0.f, pf_v = 0.f; int pf_pt = 0;
-  if (lane < PASS && rec.x + lane < obs_end) { pf_u = a.u[rec.x + lane]; pf_v = a.v[rec.x + lane]; pf_pt = a.pt[rec.x + lane]; }
-  double nX[3];
-  { const double* p3 = a.pts + 3 * (size_t)pf_pt; nX[0] = p3[0]; nX[1] = p3[1]; nX[2] = p3[2]; }
+  if (lane < PASS && obs_begin + lane < obs_end) { pf_u = a.u[obs_begin + lane]; pf_v = a.v[obs_begin + lane]; pf_pt = a.pt[obs_begin + lane]; }
   int par = 0;
   while (true) {
     double* ctx = cbuf + (DBUF ? par : 0) * CtxRaw::SIZE;
-    const int bn = b + total_warps, bnn = bn + total_warps;
+    const int bn = b + total_warps;
     const bool has_n = bn < a.nb;
-    int4 rec_nn = rec_n; int end_nn = end_n;              // records run two board observations ahead, flags one
-    if (bnn < a.nb) { rec_nn = a.bobs[bnn]; end_nn = a.bobs[bnn + 1].x; }
-    Flags fl_n = fl;
-    if (has_n) fl_n = load_flags(rec_n);
+    int4 rec_n = make_int4(0, 0, 0, 0); int end_n = 0, fl_n = 0;   // the next board observation: consumed after the first Jacobian phase at the earliest
+    if (has_n) { rec_n = a.bobs[bn]; end_n = a.bobs[bn + 1].x; fl_n = a.bobs_flags[bn]; }
     cp_async_wait_all();
     __syncwarp();
     ctx[o1] = ctx[m1] * ctx[d1] + ctx[m1 + 1] * ctx[d1 + 3] + ctx[m1 + 2] * ctx[d1 + 6];
     __syncwarp();
     if (lane < 31) ctx[o2] = ctx[m2] * ctx[d2] + ctx[m2 + 1] * ctx[d2 + 3] + ctx[m2 + 2] * ctx[d2 + 6];
     __syncwarp();
-    const bool act_c = ST::CAM && !fl.cref, act_b = ST::BOARD && !fl.bref;
-    const int model = fl.model;
+    const bool act_c = ST::CAM && !(fl & 1), act_b = ST::BOARD && !(fl & 2);
+    const int model = fl >> 2;
     double acc[NR][2];
 #pragma unroll
     for (int t = 0; t < NR; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
     double cost = 0.0;
-    const int obs_begin = rec.x;
     for (int base = obs_begin; base < obs_end; base += PASS) {
       const int nact = min(PASS, obs_end - base);
       const bool active = lane < nact;
       const float cur_u = pf_u, cur_v = pf_v;
-      const double X0[3] = {nX[0], nX[1], nX[2]};
+      const double* p3 = a.pts + 3 * (size_t)pf_pt;       // the point table is small: L1 hits
+      const double X0[3] = {p3[0], p3[1], p3[2]};
       // pixels / corner index of the following pass: of this board observation, or the first one of the next
       const bool last_pass = base + PASS >= obs_end;
       const int nxt = last_pass ? rec_n.x + lane : base + PASS + lane;
@@ -203,7 +192,6 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, MINB) k_observations_fused(Obs
         for (int col = 0; col < C::NC; ++col)
           *reinterpret_cast<double2*>(T + col * TSP + 2 * lane) = make_double2(0.0, 0.0);
       }
-      if (nxt_ok) { const double* p3 = a.pts + 3 * (size_t)pf_pt; nX[0] = p3[0]; nX[1] = p3[1]; nX[2] = p3[2]; }
       if (DBUF && base == obs_begin && has_n) issue_ctx(rec_n, fl_n, cbuf + (par ^ 1) * CtxRaw::SIZE);
       __syncwarp();
       if (!DBUF && last_pass && has_n) issue_ctx(rec_n, fl_n, cbuf);   // nobody reads the context any more in this iteration
@@ -229,10 +217,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, MINB) k_observations_fused(Obs
     }
     if (obs_begin >= obs_end && has_n) {                  // empty board observation: no pass prefetched for the next one
       issue_ctx(rec_n, fl_n, cbuf + (DBUF ? (par ^ 1) : 0) * CtxRaw::SIZE);
-      if (lane < PASS && rec_n.x + lane < end_n) {
-        pf_u = a.u[rec_n.x + lane]; pf_v = a.v[rec_n.x + lane]; pf_pt = a.pt[rec_n.x + lane];
-        const double* p3 = a.pts + 3 * (size_t)pf_pt; nX[0] = p3[0]; nX[1] = p3[1]; nX[2] = p3[2];
-      }
+      if (lane < PASS && rec_n.x + lane < end_n) { pf_u = a.u[rec_n.x + lane]; pf_v = a.v[rec_n.x + lane]; pf_pt = a.pt[rec_n.x + lane]; }
     }
     {
       double* out = a.brec + (size_t)b * C::NCOMP;
@@ -247,7 +232,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, MINB) k_observations_fused(Obs
       if (lane == 0) a.cost_bobs[b] = cost;
     }
     if (!has_n) break;
-    b = bn; rec = rec_n; obs_end = end_n; fl = fl_n; rec_n = rec_nn; end_n = end_nn; par ^= 1;
+    b = bn; obs_begin = rec_n.x; obs_end = end_n; fl = fl_n; par ^= 1;
   }
 }
 
@@ -320,20 +305,12 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_pair(ObsArgs
   int p = blockIdx.x * OBS_WARPS + warp;
   if (p >= n_pairs) return;
   for (int e = lane; e < SM::TILE; e += 32) T[e] = 0.0;
-  struct Flags { unsigned char cref, bref; int model; };
-  auto load_rec = [&](int pp, int4& r, int& end) {          // this lane's board observation of pair pp (empty past the end)
+  auto load_rec = [&](int pp, int4& r, int& end, int& f) {   // this lane's board observation of pair pp (empty past the end)
     const int bb = 2 * pp + hi;
-    if (bb < a.nb) { r = a.bobs[bb]; end = a.bobs[bb + 1].x; } else { r = make_int4(0, 0, 0, 0); end = 0; }
+    if (bb < a.nb) { r = a.bobs[bb]; end = a.bobs[bb + 1].x; f = a.bobs_flags[bb]; } else { r = make_int4(0, 0, 0, 0); end = 0; f = 0; }
   };
-  auto load_flags = [&](const int4& r) {
-    Flags f;
-    f.cref = (ST::CAM && a.cam_is_ref) ? a.cam_is_ref[r.y] : 0;
-    f.bref = (ST::BOARD && a.board_is_ref) ? a.board_is_ref[r.w] : 0;
-    f.model = a.cam_model[r.y];
-    return f;
-  };
-  auto issue_ctx = [&](const int4& r, const Flags& f) {
-    const bool act_c = ST::CAM && !f.cref, act_b = ST::BOARD && !f.bref;
+  auto issue_ctx = [&](const int4& r, int f) {
+    const bool act_c = ST::CAM && !(f & 1), act_b = ST::BOARD && !(f & 2);
     const double* pc = act_c ? a.prep_cam + (size_t)PREP * r.y : g_prep_identity;
     const double* po = a.prep_pose + (size_t)PREP * r.z;
     const double* pb = act_b ? a.prep_board + (size_t)PREP * r.w : g_prep_identity;
@@ -344,22 +321,20 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_pair(ObsArgs
       cp_async8(ctx + e, src);
     }
   };
-  int4 rec, rec_n; int obs_end, end_n;
-  load_rec(p, rec, obs_end);
-  Flags fl = load_flags(rec);
-  issue_ctx(rec, fl);
-  load_rec(p + total_warps < n_pairs ? p + total_warps : p, rec_n, end_n);
+  int my_begin, obs_end, fl;
+  {
+    int4 rec;
+    load_rec(p, rec, obs_end, fl);
+    my_begin = rec.x;
+    issue_ctx(rec, fl);
+  }
   float pf_u = 0.f, pf_v = 0.f; int pf_pt = 0;
-  if (rec.x + l16 < obs_end) { pf_u = a.u[rec.x + l16]; pf_v = a.v[rec.x + l16]; pf_pt = a.pt[rec.x + l16]; }
-  double nX[3];
-  { const double* p3 = a.pts + 3 * (size_t)pf_pt; nX[0] = p3[0]; nX[1] = p3[1]; nX[2] = p3[2]; }
+  if (my_begin + l16 < obs_end) { pf_u = a.u[my_begin + l16]; pf_v = a.v[my_begin + l16]; pf_pt = a.pt[my_begin + l16]; }
   while (true) {
-    const int pn = p + total_warps, pnn = pn + total_warps;
+    const int pn = p + total_warps;
     const bool has_n = pn < n_pairs;
-    int4 rec_nn = rec_n; int end_nn = end_n;
-    if (pnn < n_pairs) load_rec(pnn, rec_nn, end_nn);
-    Flags fl_n = fl;
-    if (has_n) fl_n = load_flags(rec_n);
+    int4 rec_n = make_int4(0, 0, 0, 0); int end_n = 0, fl_n = 0;   // consumed in the last pass
+    if (has_n) load_rec(pn, rec_n, end_n, fl_n);
     cp_async_wait_all();
     __syncwarp();
 #pragma unroll
@@ -369,13 +344,13 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_pair(ObsArgs
       ctx[o] = ctx[m] * ctx[d] + ctx[m + 1] * ctx[d + 3] + ctx[m + 2] * ctx[d + 6];
       __syncwarp();
     }
-    const bool act_c = ST::CAM && !fl.cref, act_b = ST::BOARD && !fl.bref;
-    const int model = fl.model;
+    const bool act_c = ST::CAM && !(fl & 1), act_b = ST::BOARD && !(fl & 2);
+    const int model = fl >> 2;
     double accA[NR][2], accB[NR][2];
 #pragma unroll
     for (int t = 0; t < NR; ++t) { accA[t][0] = 0.0; accA[t][1] = 0.0; accB[t][0] = 0.0; accB[t][1] = 0.0; }
     double cost = 0.0;
-    const int my_begin = rec.x, n_mine = obs_end - rec.x;
+    const int n_mine = obs_end - my_begin;
     const int nA = __shfl_sync(0xffffffffu, n_mine, 0), nB = __shfl_sync(0xffffffffu, n_mine, 16);
     const int npass = (max(nA, nB) + HP - 1) / HP;
     for (int pass = 0; pass < npass; ++pass) {
@@ -383,7 +358,8 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_pair(ObsArgs
       const int nact = min(HP, max(0, n_mine - off));
       const bool active = l16 < nact;
       const float cur_u = pf_u, cur_v = pf_v;
-      const double X0[3] = {nX[0], nX[1], nX[2]};
+      const double* p3 = a.pts + 3 * (size_t)pf_pt;       // the point table is small: L1 hits
+      const double X0[3] = {p3[0], p3[1], p3[2]};
       const bool last = pass + 1 == npass;
       const int nxt = last ? rec_n.x + l16 : my_begin + off + HP + l16;
       const int nxt_end = last ? end_n : obs_end;
@@ -397,41 +373,37 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_pair(ObsArgs
         for (int col = 0; col < C::NC; ++col)
           *reinterpret_cast<double2*>(T + col * TS + 2 * lane) = make_double2(0.0, 0.0);
       }
-      if (nxt_ok) { const double* p3 = a.pts + 3 * (size_t)pf_pt; nX[0] = p3[0]; nX[1] = p3[1]; nX[2] = p3[2]; }
       __syncwarp();
       if (last && has_n) issue_ctx(rec_n, fl_n);          // the context is not read any more in this iteration
       const int kA = (2 * min(HP, max(0, nA - off)) + 3) >> 2, kB = (2 * min(HP, max(0, nB - off)) + 3) >> 2;
-      const int kmax = max(kA, kB);
-      const double* TlA = T + c4 * TS + q;
-      const double* TlB = TlA + 2 * HP;
-      double GA[NG], GB[NG], GAn[NG], GBn[NG];
+      // the two observations' k-steps one after the other (side by side, with both sets of fragments live, the loop
+      // runs out of registers at stage 5 and the DMMAs serialise on two temporaries: 41 % of the kernel's samples)
 #pragma unroll
-      for (int j = 0; j < NG; ++j) { GA[j] = TlA[4 * j * TS]; GB[j] = TlB[4 * j * TS]; }
-      for (int ks = 0; ks < kmax; ++ks) {
-        const int kn = min(ks + 1, kmax - 1);
+      for (int half = 0; half < 2; ++half) {
+        const int kh = half ? kB : kA;
+        const double* Tl = T + c4 * TS + q + half * 2 * HP;
+        double G[NG], Gn[NG];
 #pragma unroll
-        for (int j = 0; j < NG; ++j) { GAn[j] = TlA[4 * j * TS + 4 * kn]; GBn[j] = TlB[4 * j * TS + 4 * kn]; }
-        if (ks < kA) {
+        for (int j = 0; j < NG; ++j) G[j] = Tl[4 * j * TS];
+        for (int ks = 0; ks < kh; ++ks) {
+          const int kn = min(ks + 1, kh - 1);
 #pragma unroll
-          for (int r = 0; r < NR; ++r)
-            dmma884(accA[r][0], accA[r][1], hi ? GA[RCV::r1(r)] : GA[RCV::r0(r)], hi ? GA[RCV::c1(r)] : GA[RCV::c0(r)]);
+          for (int j = 0; j < NG; ++j) Gn[j] = Tl[4 * j * TS + 4 * kn];
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            const double fa = hi ? G[RCV::r1(r)] : G[RCV::r0(r)];
+            const double fb = hi ? G[RCV::c1(r)] : G[RCV::c0(r)];
+            if (half) dmma884(accB[r][0], accB[r][1], fa, fb); else dmma884(accA[r][0], accA[r][1], fa, fb);
+          }
+#pragma unroll
+          for (int j = 0; j < NG; ++j) G[j] = Gn[j];
         }
-        if (ks < kB) {
-#pragma unroll
-          for (int r = 0; r < NR; ++r)
-            dmma884(accB[r][0], accB[r][1], hi ? GB[RCV::r1(r)] : GB[RCV::r0(r)], hi ? GB[RCV::c1(r)] : GB[RCV::c0(r)]);
-        }
-#pragma unroll
-        for (int j = 0; j < NG; ++j) { GA[j] = GAn[j]; GB[j] = GBn[j]; }
       }
       __syncwarp();
     }
     if (npass == 0 && has_n) {                             // both board observations empty: nothing prefetched for the next pair
       issue_ctx(rec_n, fl_n);
-      if (rec_n.x + l16 < end_n) {
-        pf_u = a.u[rec_n.x + l16]; pf_v = a.v[rec_n.x + l16]; pf_pt = a.pt[rec_n.x + l16];
-        const double* p3 = a.pts + 3 * (size_t)pf_pt; nX[0] = p3[0]; nX[1] = p3[1]; nX[2] = p3[2];
-      }
+      if (rec_n.x + l16 < end_n) { pf_u = a.u[rec_n.x + l16]; pf_v = a.v[rec_n.x + l16]; pf_pt = a.pt[rec_n.x + l16]; }
     }
     {
       const int bA = 2 * p, bB = 2 * p + 1;
@@ -449,7 +421,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_pair(ObsArgs
       if (l16 == 0 && 2 * p + hi < a.nb) a.cost_bobs[2 * p + hi] = cost;
     }
     if (!has_n) break;
-    p = pn; rec = rec_n; obs_end = end_n; fl = fl_n; rec_n = rec_nn; end_n = end_nn;
+    p = pn; my_begin = rec_n.x; obs_end = end_n; fl = fl_n;
   }
 }
 
