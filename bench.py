@@ -44,7 +44,7 @@ FLOPS_PER_OBS = {4: 500 + 756, 5: 500 + 1620}                  # SURVEY.md §8(d
 FP64_PEAK_TFLOPS = 36.9    # measured on this pool's B200 with tools/peak_fp64.cu (DMMA m8n8k4), profiles/r01_peak_fp64.json
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the two K1 variants on the 6.18 M-observation
 # shard, from ncu --set full captures of this same command; NOT measured inside the run (ncu cannot run under the timer)
-NCU_TRAFFIC = {"fused": (77.2e6 + 361.6e6, "profiles/r01c_ncu_full_step_kernels.txt"),
+NCU_TRAFFIC = {"fused": (77.5e6 + 367.3e6, "profiles/r02b_ncu_full_step_kernels.txt"),
                "materialize": (77.6e6 + 2712.9e6, "profiles/r01c_ncu_full_materialize.txt")}
 METRIC = "LM bundle-adjustment throughput (full LM iteration: resid+Jac, normal equations, Schur, Cholesky, candidate cost)"
 
@@ -140,8 +140,8 @@ def workload_config(n_gpus, n_obs_global, frames_global, schur_reduce=None):
     return {"workload": f"BASELINE configs[3]: 64-camera dome, 10 boards x 48 corners, stage 5 (intrinsics+extrinsics+object), "
                         f"{FRAMES_PER_GPU} frames/GPU weak-scaled (N=8 = the full 20,000-frame ~50M-observation case)",
             "n_cameras": 64, "n_boards": 10, "frames": int(frames_global), "observations": int(n_obs_global), "reduced_system_n": 1020,
-            "parallelism": f"frame-sharded x{n_gpus}; reduced system summed across ranks in the Schur kernel's epilogue over NVLink "
-                           "peer memory (NCCL allreduce as fallback), pair records by NCCL allreduce" if n_gpus > 1 else "single GPU",
+            "parallelism": f"frame-sharded x{n_gpus}; reduced system summed across ranks in the Schur kernel's epilogue, pair records and "
+                           "per-phase scalars exchanged by their own kernels, all over NVLink peer memory (NCCL as rendezvous and fallback)" if n_gpus > 1 else "single GPU",
             "lm_options": "radius pinned (initial=max=1e-2), tolerances off: every timed iteration is an accepted step",
             "l2": "per-step working set (observations 75 MB + per-board-observation J^T J tiles 0.42 GB x 2 + E^T F rows 0.25 GB per GPU) exceeds the 126 MB L2; no explicit flush"}
 
@@ -603,12 +603,13 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world, n_obs_global, fpg * world),
             "schur_reduce": schur_reduce,
-            "comm": {"schur_reduce": schur_reduce, "nccl_ms_per_step": nccl_ms,
+            "comm": {"schur_reduce": schur_reduce, "exchange_ms_per_step": nccl_ms,
                      "nvlink_bytes_per_step_per_gpu": (int(2 * upper * (world - 1) / world) if schur_reduce == "p2p" else None),
                      "note": "p2p: each rank pulls its 1/N slice of the upper triangle of the reduced system from the N-1 peers and pushes "
-                             "the sum back (inside k_syrk_sum_p2p, timed under schur_syrk); nccl_ms = pair-record allreduce + scalar gathers"} if world > 1 else None,
+                             "the sum back (inside k_syrk_sum_p2p, timed under schur_syrk); exchange_ms = pair-record sum + the two scalar gathers "
+                             "(k_allreduce_p2p, k_gather_p2p over peer memory when schur_reduce is p2p, NCCL otherwise), from the direct-launch handle"} if world > 1 else None,
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "parity": parity,
-            "roofline": {"kernel": "k_observations<5,MODE_FUSED> (resid + Jacobian + J^T J/J^T r, DMMA)", "bound": "tensor",
+            "roofline": {"kernel": "k_observations_fused<5> (resid + Jacobian + J^T J/J^T r, DMMA; csrc/mcba_obs_fused.cuh)", "bound": "tensor",
                          "achieved": achieved_tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                          "frac": (achieved_tf / FP64_PEAK_TFLOPS) if achieved_tf else None,
                          "traffic": NCU_TRAFFIC["fused"][0] if fpg == FRAMES_PER_GPU else None,
