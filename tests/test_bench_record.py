@@ -16,7 +16,8 @@ def last_line(path):
     return json.loads(open(path).read().strip().splitlines()[-1])
 
 
-@pytest.mark.parametrize("name,n", [("r01e_bench_n1.json", 1), ("r01e_bench_n2.json", 2), ("r01d_bench_n4.json", 4), ("r01d_bench_n8.json", 8)])
+@pytest.mark.parametrize("name,n", [("r01e_bench_n1.json", 1), ("r01e_bench_n2.json", 2), ("r01d_bench_n4.json", 4), ("r01d_bench_n8.json", 8),
+                                    ("r02b_bench_n1.json", 1), ("r02b_bench_n2.json", 2), ("r02b_bench_n4.json", 4), ("r02b_bench_n8.json", 8)])
 def test_committed_gpu_records(name, n):
     d = last_line(os.path.join(REPO, "profiles", name))
     for k in BASE + ["clocks", "gpu_launches", "e2e", "roofline", "cpu_baseline"]:
@@ -41,6 +42,9 @@ def test_committed_gpu_records(name, n):
         assert c["kind"] in ("port", "reference") and c["cores"] >= 1
     else:
         assert d["cpu_baseline"] is None          # rank 0 at N = 1 only
+    if name.startswith("r02"):                    # round 2: every line carries a parity object and says which data plane ran
+        assert d["parity"]["pass"] is True and all(st["same_accept_reject_sequence_and_termination"] for st in d["parity"]["stages"])
+        assert d["schur_reduce"] == ("single" if n == 1 else "p2p") and d["launch_mode"].startswith("CUDA graphs")
 
 
 def test_reference_arm_runs_on_the_cpu():
