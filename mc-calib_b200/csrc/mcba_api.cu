@@ -402,7 +402,7 @@ template <int MODE> static int launch_obs(Handle* H, int which, double huber_a) 
   //   0 = k_observations_fused: one board observation per warp, prefetched copy-free context, group-pair cover of the
   //       triangle (7 DMMAs per k-step instead of 10 at stage 5);
   //   3 = k_observations_pair: the same with two board observations per warp (one per half-warp, 16 corners per pass);
-  //   1 = the first version k_observations<S, MODE_FUSED> (also what gated / batched handles run);
+  //   1 = the first version k_observations<S, MODE_FUSED> (what gated / batched handles run unless the variant is 3);
   //   2 = the streaming experiment (tails of consecutive board observations share a warp pass; slower than version 1);
   //   4 = k_observations_fused with 24-corner passes, one context slot and 4 CTAs (16 warps) per SM at 128 registers:
   //       0.91 ms at stage 5 (spills), 0.60 ms at stage 4 (= variant 0): the kernel is bound by the pipe the DMMA and DFMA
@@ -422,7 +422,7 @@ template <int MODE> static int launch_obs(Handle* H, int which, double huber_a) 
     CHECK_LAUNCH();
     return MCBA_OK;
   }
-  if (MODE == MODE_FUSED && k1v == 3 && !a.gate) {
+  if (MODE == MODE_FUSED && k1v == 3) {   // the pair kernel honours ObsArgs::gate (batched problems)
     DISPATCH_STAGE(H->stage, {
       const int sm = PairSmem<ST>::BYTES;
       const int grid = grid_for(H, (H->nb + 1) / 2, std::min(3, std::max(1, (227 * 1024) / (sm + 1024))));

@@ -321,12 +321,14 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_pair(ObsArgs
       cp_async8(ctx + e, src);
     }
   };
-  int my_begin, obs_end, fl;
+  // batched problems: board observations of cameras whose gate is off are skipped (nothing computed, nothing stored)
+  int my_begin, obs_end, fl, gate_on = 1;
   {
     int4 rec;
     load_rec(p, rec, obs_end, fl);
     my_begin = rec.x;
     issue_ctx(rec, fl);
+    if (a.gate) gate_on = a.gate[rec.y];
   }
   float pf_u = 0.f, pf_v = 0.f; int pf_pt = 0;
   if (my_begin + l16 < obs_end) { pf_u = a.u[my_begin + l16]; pf_v = a.v[my_begin + l16]; pf_pt = a.pt[my_begin + l16]; }
@@ -350,7 +352,8 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_pair(ObsArgs
 #pragma unroll
     for (int t = 0; t < NR; ++t) { accA[t][0] = 0.0; accA[t][1] = 0.0; accB[t][0] = 0.0; accB[t][1] = 0.0; }
     double cost = 0.0;
-    const int n_mine = obs_end - my_begin;
+    const int n_mine = gate_on ? obs_end - my_begin : 0;
+    int gate_n = 1;
     const int nA = __shfl_sync(0xffffffffu, n_mine, 0), nB = __shfl_sync(0xffffffffu, n_mine, 16);
     const int npass = (max(nA, nB) + HP - 1) / HP;
     for (int pass = 0; pass < npass; ++pass) {
@@ -374,6 +377,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_pair(ObsArgs
           *reinterpret_cast<double2*>(T + col * TS + 2 * lane) = make_double2(0.0, 0.0);
       }
       __syncwarp();
+      if (last && has_n && a.gate) gate_n = a.gate[rec_n.y];   // consumed at the top of the next iteration
       if (last && has_n) issue_ctx(rec_n, fl_n);          // the context is not read any more in this iteration
       const int kA = (2 * min(HP, max(0, nA - off)) + 3) >> 2, kB = (2 * min(HP, max(0, nB - off)) + 3) >> 2;
       // the two observations' k-steps one after the other (side by side, with both sets of fragments live, the loop
@@ -403,25 +407,27 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_pair(ObsArgs
     }
     if (npass == 0 && has_n) {                             // both board observations empty: nothing prefetched for the next pair
       issue_ctx(rec_n, fl_n);
+      if (a.gate) gate_n = a.gate[rec_n.y];
       if (rec_n.x + l16 < end_n) { pf_u = a.u[rec_n.x + l16]; pf_v = a.v[rec_n.x + l16]; pf_pt = a.pt[rec_n.x + l16]; }
     }
     {
       const int bA = 2 * p, bB = 2 * p + 1;
       double* outA = a.brec + (size_t)bA * C::NCOMP;
       double* outB = a.brec + (size_t)bB * C::NCOMP;
-      const bool hasB = bB < a.nb;
+      const bool okA = __shfl_sync(0xffffffffu, gate_on, 0) != 0;
+      const bool okB = bB < a.nb && __shfl_sync(0xffffffffu, gate_on, 16) != 0;
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
         const short2 ci = sidx[r * 32 + lane];
-        if (ci.x >= 0) { outA[ci.x] = accA[r][0]; if (hasB) outB[ci.x] = accB[r][0]; }
-        if (ci.y >= 0) { outA[ci.y] = accA[r][1]; if (hasB) outB[ci.y] = accB[r][1]; }
+        if (ci.x >= 0) { if (okA) outA[ci.x] = accA[r][0]; if (okB) outB[ci.x] = accB[r][0]; }
+        if (ci.y >= 0) { if (okA) outA[ci.y] = accA[r][1]; if (okB) outB[ci.y] = accB[r][1]; }
       }
 #pragma unroll
       for (int off = 8; off > 0; off >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, off);
-      if (l16 == 0 && 2 * p + hi < a.nb) a.cost_bobs[2 * p + hi] = cost;
+      if (l16 == 0 && 2 * p + hi < a.nb && gate_on) a.cost_bobs[2 * p + hi] = cost;
     }
     if (!has_n) break;
-    p = pn; my_begin = rec_n.x; obs_end = end_n; fl = fl_n;
+    p = pn; my_begin = rec_n.x; obs_end = end_n; fl = fl_n; gate_on = gate_n;
   }
 }
 
