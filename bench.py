@@ -655,7 +655,7 @@ def main():
                              "the sum back (inside k_syrk_sum_p2p, timed under schur_syrk); exchange_ms = pair-record sum + the two scalar gathers "
                              "(k_allreduce_p2p, k_gather_p2p over peer memory when schur_reduce is p2p, NCCL otherwise), from the direct-launch handle"} if world > 1 else None,
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "parity": parity,
-            "roofline": {"kernel": "k_observations_fused<5> (resid + Jacobian + J^T J/J^T r, DMMA; csrc/mcba_obs_fused.cuh)", "bound": "tensor",
+            "roofline": {"kernel": "k_observations_pair<5> (resid + Jacobian + J^T J/J^T r, DMMA; csrc/mcba_obs_fused.cuh)", "bound": "tensor",
                          "achieved": achieved_tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                          "frac": (achieved_tf / FP64_PEAK_TFLOPS) if achieved_tf else None,
                          "traffic": NCU_TRAFFIC["fused"][0] if fpg == FRAMES_PER_GPU else None,

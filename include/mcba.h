@@ -192,13 +192,16 @@ void mcba_problem_free(void *storage);
 const char *mcba_io_last_error(void);
 
 /* Test hook: copy an internal device buffer (normal-equation blocks, reduced system, scaling) to the host.
- * Names: "FF" "gf" "S" "rhs" "zf" "ZtZ" "Hoo" "Wt" "Z" "brec" "scale_e" "scale_f" "diag_e" "diag_f". */
+ * Names: "FF" "gf" "S" "rhs" "zf" "ZtZ" "Hoo" "Wt" "Z" "brec" "pair_rec" "scale_e" "scale_f" "diag_e" "diag_f". */
 int mcba_debug_fetch(void *handle, const char *name, double *out, int64_t cap, int64_t *n_out);
-/* Test hook: fused observation kernel of the handles created afterwards. 0 = k_observations_fused, 3 =
- * k_observations_pair (two board observations per warp), 1 = first version (k_observations<S, MODE_FUSED>),
- * 2 = streaming experiment, 4 = 24-corner passes with 16 warps per SM (experiment); -1 = back to the MCBA_K1
- * environment variable (unset: 0 at stage 5, 3 otherwise). Variants 0-3 write bit-identical per-board-observation
- * records; 4 differs at rounding level (other multiply-add contractions). */
+/* Test hook: fused observation kernel of the handles created afterwards. 3 = k_observations_pair (two board
+ * observations per warp; the default at every stage), 0 = k_observations_fused (one per warp), 1 = first version
+ * (k_observations<S, MODE_FUSED>), 2 = streaming experiment, 4 = 24-corner passes with 16 warps per SM (experiment);
+ * -1 = back to the MCBA_K1 environment variable. Variants 0-3 write bit-identical per-board-observation records; 4
+ * differs at rounding level (other multiply-add contractions). + 32: variants 0 and 3 keep the f x f / f x r part of
+ * J~^T J~ in registers over runs of one (camera, board) pair and write partial pair records ("pair_rec" after the
+ * assembly) instead of that part of every record (MCBA_K1_ACC=1 does the same; measured slower, off by default);
+ * + 16 forces it off. */
 int mcba_debug_set_k1(int variant);
 /* Test / benchmark hook: factor and solve one dense symmetric positive definite system with the reduced-system
  * kernels alone. S_host is (n+1) x n row-major (matrix rows, then the right-hand side as row n); z_out [n] = solution,

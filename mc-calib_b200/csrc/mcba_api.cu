@@ -73,7 +73,7 @@ struct Handle {
   // problem (host copies of the small things)
   int stage = 0, n_cam = 0, n_pose = 0, n_board = 0, n_pts = 0, nb = 0;
   int64_t n_obs = 0, npad = 0;
-  std::vector<int32_t> h_bobs_cam, h_bobs_pose, h_bobs_board;
+  std::vector<int32_t> h_bobs_cam, h_bobs_pose, h_bobs_board, h_bobs_flags;
   std::vector<int64_t> h_bobs_ptr;
   // static device data
   float *d_u = nullptr, *d_v = nullptr; int32_t* d_pt = nullptr; double* d_pts = nullptr;
@@ -132,6 +132,12 @@ struct Handle {
   // CUDA graphs of the two per-iteration launch sequences (single-rank handles): key = 2 * cur + brec_par
   bool use_graph = false, graph_env = false, capturing = false; int brec_par = 0;
   int k1_variant = -1;               // fused observation kernel of this handle (launch_obs)
+  // K1 with in-kernel accumulation of the f x f / f x r part over runs of one (camera, board) pair (k1_acc): the board
+  // observations in pair order with everything a warp needs per item, the runs ("chunks") cut at the streams' range
+  // boundaries, one partial pair record per chunk for each of the two tile sets
+  bool k1_acc = false; int k1_grid = 0, k1_streams = 0, n_k1_chunks = 0;
+  int4 *d_k1_rec = nullptr, *d_k1_aux = nullptr; int* d_k1_chunk_ptr = nullptr;
+  double *d_k1_partial = nullptr, *d_k1_partial_alt = nullptr;
   cudaGraphExec_t g_step[4] = {nullptr, nullptr, nullptr, nullptr}, g_asm[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t g_step_launches[4] = {0, 0, 0, 0}, g_asm_launches[4] = {0, 0, 0, 0};
   mcba_options graph_opt; bool graph_opt_valid = false;
@@ -239,6 +245,19 @@ static int setup_batched(Handle* H) {
 }
 
 static void drop_graphs(Handle* H);
+// Fused observation kernel of a stage (launch_obs): the handle's variant, or the default per stage.
+// (variant + 32 = that variant with the in-kernel pair accumulation, + 16 = without it, whatever MCBA_K1_ACC says: test hook)
+static int k1_variant_of(const Handle* H, int stage) { (void)stage; return H->k1_variant >= 0 ? (H->k1_variant & 15) : 3; }
+// Grid of the two kernels that can accumulate pair records (k_observations_fused / k_observations_pair): 3 CTAs per SM
+// unless the shared memory of the stage allows fewer; the streams (warps / half-warps) of this grid own fixed ranges.
+static int k1_grid_of(const Handle* H, int stage, int k1v, int nb) {
+  int sm = 0;
+  DISPATCH_STAGE(stage, { sm = k1v == 3 ? PairSmem<ST>::BYTES : FusedSmem<ST>::BYTES; });
+  const int per_sm = std::min(3, std::max(1, (227 * 1024) / (sm + 1024)));
+  const int units = k1v == 3 ? (nb + 1) / 2 : nb;
+  return std::max(1, std::min((units + OBS_WARPS - 1) / OBS_WARPS, H->n_sm * per_sm));
+}
+static bool k1_acc_on(const Handle* H) { return H->k1_acc && !H->opt.materialize_jacobian; }
 static int setup_stage(Handle* H, int stage) {
   if (H->batched) return setup_batched(H);
   drop_graphs(H);   // every buffer the captured launches point to is reallocated below
@@ -283,6 +302,44 @@ static int setup_stage(Handle* H, int stage) {
   CU(cudaMemcpy(H->d_pair_bobs, pair_bobs.data(), pair_bobs.size() * sizeof(int), cudaMemcpyHostToDevice));
   if (!chunks.empty()) CU(cudaMemcpy(H->d_chunks, chunks.data(), chunks.size() * sizeof(PairChunk), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(H->d_pair_chunk_ptr, pcp.data(), pcp.size() * sizeof(int), cudaMemcpyHostToDevice));
+  {
+    // K1 accumulating the f x f / f x r part itself (variants 0 and 3): items in pair order, streams own contiguous
+    // ranges of them, a chunk = a run of one pair inside one range; k_pair_final sums the chunks of a pair in order
+    const int k1v = k1_variant_of(H, stage);
+    // Off by default - measured slower: the runs of a pair are spread over all frames, so a warp's consecutive items
+    // share nothing but the camera and the board (pose records, pixels and records scattered over HBM instead of
+    // streaming), and K1 loses 0.05 ms where the assembly gains 0.04. MCBA_K1_ACC=1 turns it on.
+    static const bool acc_env = []() { const char* e = getenv("MCBA_K1_ACC"); return e && atoi(e) != 0; }();
+    const bool want = H->k1_variant >= 0 && (H->k1_variant & 32) ? true : (H->k1_variant >= 0 && (H->k1_variant & 16) ? false : acc_env);
+    H->k1_acc = want && (k1v == 0 || k1v == 3) && H->nb > 0;
+    if (H->k1_acc) {
+      H->k1_grid = k1_grid_of(H, stage, k1v, H->nb);
+      H->k1_streams = H->k1_grid * OBS_WARPS * (k1v == 3 ? 2 : 1);
+      std::vector<int4> rec(H->nb + 1), aux(H->nb + 1);
+      std::vector<int> k1pcp(H->n_pair + 1, 0);
+      int n_ch = 0, s_cur = 0;
+      long long s_hi = (long long)H->nb * 1 / H->k1_streams;   // end of stream 0's range
+      int prev_pair = -1;
+      for (int i = 0; i < H->nb; ++i) {
+        while (i >= s_hi && s_cur + 1 < H->k1_streams) { ++s_cur; s_hi = (long long)H->nb * (s_cur + 1) / H->k1_streams; prev_pair = -1; }
+        const int b = pair_bobs[i];
+        const int pr = H->h_bobs_cam[b] * nbp + (sd.board ? H->h_bobs_board[b] : 0);
+        if (pr != prev_pair) { ++n_ch; prev_pair = pr; }
+        const int bf = H->h_bobs_flags[b];
+        rec[i] = make_int4((int)H->h_bobs_ptr[b], H->h_bobs_cam[b], H->h_bobs_pose[b], H->h_bobs_board[b]);
+        aux[i] = make_int4((int)H->h_bobs_ptr[b + 1], bf, b, n_ch - 1);
+        k1pcp[pr + 1] = n_ch;
+      }
+      rec[H->nb] = make_int4(0, 0, 0, 0); aux[H->nb] = make_int4(0, 0, 0, -1);
+      for (int p = 0; p < H->n_pair; ++p) k1pcp[p + 1] = std::max(k1pcp[p + 1], k1pcp[p]);   // pairs without board observations
+      H->n_k1_chunks = n_ch;
+      if (dalloc(H, &H->d_k1_rec, rec.size()) || dalloc(H, &H->d_k1_aux, aux.size()) || dalloc(H, &H->d_k1_chunk_ptr, k1pcp.size())) return MCBA_ERR_CUDA;
+      if (dalloc(H, &H->d_k1_partial, (size_t)n_ch * H->NE) || dalloc(H, &H->d_k1_partial_alt, (size_t)n_ch * H->NE)) return MCBA_ERR_CUDA;
+      CU(cudaMemcpy(H->d_k1_rec, rec.data(), rec.size() * sizeof(int4), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(H->d_k1_aux, aux.data(), aux.size() * sizeof(int4), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(H->d_k1_chunk_ptr, k1pcp.data(), k1pcp.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+  }
   const size_t np = H->n_pose, nf = H->n_f, ldz = H->ldz;
   if (dalloc(H, &H->d_brec, (size_t)H->nb * sd.NCOMP) || dalloc(H, &H->d_brec_alt, (size_t)H->nb * sd.NCOMP)) return MCBA_ERR_CUDA;
   if (dalloc(H, &H->d_cost_bobs, (size_t)H->nb)) return MCBA_ERR_CUDA;
@@ -344,7 +401,9 @@ static int setup_stage(Handle* H, int stage) {
     CU(cudaFuncSetAttribute(k_observations<ST, MODE_FROM_J>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     CU(cudaFuncSetAttribute(k_observations_stream<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, OBS_WARPS * (2 * CTX_SIZE + Cols<ST>::NC * TS) * 8));
     CU(cudaFuncSetAttribute(k_observations_fused<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem<ST>::BYTES));
-    CU(cudaFuncSetAttribute(k_observations_pair<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem<ST>::BYTES));
+    CU(cudaFuncSetAttribute(k_observations_fused<ST, OBS_PASS, 3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem<ST>::BYTES));
+    CU(cudaFuncSetAttribute(k_observations_pair<ST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem<ST>::BYTES));
+    CU(cudaFuncSetAttribute(k_observations_pair<ST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem<ST>::BYTES));
     CU(cudaFuncSetAttribute(k_observations_fused<ST, 24, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem<ST, 24, false>::BYTES));
     CU(cudaFuncSetAttribute(k_eblock_assemble<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * (H->ldz + EA_PAD) * 8));
   });
@@ -376,6 +435,8 @@ static ObsArgs obs_args(Handle* H, int which, double huber_a) {
   a.cam_model = H->d_cam_model; a.cam_is_ref = H->d_cam_is_ref; a.board_is_ref = H->d_board_is_ref;
   a.huber_a = huber_a; a.nb = H->nb; a.brec = H->brec_target ? H->brec_target : H->d_brec; a.cost_bobs = H->d_cost_bobs;
   a.jmat = H->d_jmat; a.resmat = H->d_resmat; a.npad = H->npad; a.gate = H->obs_gate; a.bobs_flags = H->d_bobs_flags;
+  a.srec = H->d_k1_rec; a.saux = H->d_k1_aux; a.n_streams = H->k1_streams;
+  a.partial = (H->brec_target && H->brec_target == H->d_brec_alt) ? H->d_k1_partial_alt : H->d_k1_partial;
   return a;
 }
 
@@ -407,10 +468,10 @@ template <int MODE> static int launch_obs(Handle* H, int which, double huber_a) 
   //   4 = k_observations_fused with 24-corner passes, one context slot and 4 CTAs (16 warps) per SM at 128 registers:
   //       0.91 ms at stage 5 (spills), 0.60 ms at stage 4 (= variant 0): the kernel is bound by the pipe the DMMA and DFMA
   //       instructions share (63 % busy) and the shared-memory wavefronts (56 %), not by the number of resident warps;
-  //  -1 = automatic (default): 0 at stage 5, where two sets of accumulators do not fit the register budget of 3 CTAs
-  //       per SM next to the 27-column Jacobian (measured 0.80 vs 0.75 ms), 3 at the other stages (0.54 vs 0.60 ms at
-  //       stage 4). All variants write bit-identical records.
-  const int k1v = H->k1_variant >= 0 ? H->k1_variant : (H->stage == 5 ? 0 : 3);
+  //  -1 = default: 3 at every stage (at stage 5 the two kernels are within 1 % of each other: 0.726 vs 0.734 ms).
+  //  Variants 0-3 write bit-identical records. MCBA_K1_ACC=1 (or variant + 32): variants 0 and 3 accumulate the f x f /
+  //  f x r part over runs of one (camera, board) pair and write partial pair records instead (setup_stage).
+  const int k1v = k1_variant_of(H, H->stage);
   if (MODE == MODE_FUSED && k1v == 2 && !a.gate) {
     DISPATCH_STAGE(H->stage, {
       const int sm = OBS_WARPS * (2 * CTX_SIZE + Cols<ST>::NC * TS) * 8;
@@ -423,11 +484,12 @@ template <int MODE> static int launch_obs(Handle* H, int which, double huber_a) 
     return MCBA_OK;
   }
   if (MODE == MODE_FUSED && k1v == 3) {   // the pair kernel honours ObsArgs::gate (batched problems)
+    const bool acc = k1_acc_on(H) && !a.gate;
     DISPATCH_STAGE(H->stage, {
       const int sm = PairSmem<ST>::BYTES;
-      const int grid = grid_for(H, (H->nb + 1) / 2, std::min(3, std::max(1, (227 * 1024) / (sm + 1024))));
       ++H->n_launches;
-      k_observations_pair<ST><<<grid, OBS_WARPS * 32, sm, H->stream>>>(a);
+      if (acc) k_observations_pair<ST, true><<<H->k1_grid, OBS_WARPS * 32, sm, H->stream>>>(a);
+      else k_observations_pair<ST, false><<<k1_grid_of(H, H->stage, 3, H->nb), OBS_WARPS * 32, sm, H->stream>>>(a);
     });
     CHECK_LAUNCH();
     return MCBA_OK;
@@ -443,11 +505,12 @@ template <int MODE> static int launch_obs(Handle* H, int which, double huber_a) 
     return MCBA_OK;
   }
   if (MODE == MODE_FUSED && k1v == 0 && !a.gate) {
+    const bool acc = k1_acc_on(H);
     DISPATCH_STAGE(H->stage, {
       const int sm = FusedSmem<ST>::BYTES;
-      const int grid = grid_for(H, H->nb, std::min(3, std::max(1, (227 * 1024) / (sm + 1024))));
       ++H->n_launches;
-      k_observations_fused<ST><<<grid, OBS_WARPS * 32, sm, H->stream>>>(a);
+      if (acc) k_observations_fused<ST, OBS_PASS, 3, true, true><<<H->k1_grid, OBS_WARPS * 32, sm, H->stream>>>(a);
+      else k_observations_fused<ST><<<k1_grid_of(H, H->stage, 0, H->nb), OBS_WARPS * 32, sm, H->stream>>>(a);
     });
     CHECK_LAUNCH();
     return MCBA_OK;
@@ -593,14 +656,16 @@ static int eval_assemble_launch(Handle* H, bool first) {
   if (ov) { CU(cudaEventRecord(H->ev_fork, H->stream)); CU(cudaStreamWaitEvent(H->stream_b, H->ev_fork, 0)); }
   {
     Timed t(H, KF_PAIR, sb);
-    if (H->n_chunks > 0) {
+    const bool acc = k1_acc_on(H);   // the fused kernel already left one partial pair record per chunk of its streams
+    if (!acc && H->n_chunks > 0) {
       ++H->n_launches;
       DISPATCH_STAGE(H->stage, (k_pair_reduce<ST><<<H->n_chunks, 256, 0, sb>>>(H->d_chunks, H->d_pair_bobs, H->d_brec, H->d_pair_partial)));
       CHECK_LAUNCH();
     }
     const int n = H->n_pair * H->NE;
     ++H->n_launches;
-    DISPATCH_STAGE(H->stage, (k_pair_final<ST><<<(n + 255) / 256, 256, 0, sb>>>(H->d_pair_chunk_ptr, H->n_pair, H->d_pair_partial, H->pair_in)));
+    DISPATCH_STAGE(H->stage, (k_pair_final<ST><<<(n + 255) / 256, 256, 0, sb>>>(acc ? H->d_k1_chunk_ptr : H->d_pair_chunk_ptr, H->n_pair,
+                                                                              acc ? H->d_k1_partial : H->d_pair_partial, H->pair_in)));
     CHECK_LAUNCH();
   }
   if (H->n_ranks > 1 && H->p2p) {   // sum of the pair records across ranks over peer memory (k_allreduce_p2p)
@@ -1120,6 +1185,7 @@ void mcba_destroy(void* h) {
   if (H->tm_a) { cudaEventDestroy(H->tm_a); cudaEventDestroy(H->tm_b); }
   if (H->obs_shared) { obs_cache_release(H->d_u); H->d_u = nullptr; H->d_v = nullptr; H->d_pt = nullptr; }
   dfree(H, &H->d_u); dfree(H, &H->d_v); dfree(H, &H->d_pt); dfree(H, &H->d_pts); dfree(H, &H->d_bobs); dfree(H, &H->d_pose_bobs_ptr); dfree(H, &H->d_bobs_flags);
+  dfree(H, &H->d_k1_rec); dfree(H, &H->d_k1_aux); dfree(H, &H->d_k1_chunk_ptr); dfree(H, &H->d_k1_partial); dfree(H, &H->d_k1_partial_alt);
   dfree(H, &H->d_cam_model); dfree(H, &H->d_cam_is_ref); dfree(H, &H->d_board_is_ref);
   dfree(H, &H->d_pair_bobs); dfree(H, &H->d_chunks); dfree(H, &H->d_pair_chunk_ptr);
   dfree(H, &H->d_brec); dfree(H, &H->d_brec_alt); dfree(H, &H->d_cost_bobs); dfree(H, &H->d_Hoo); dfree(H, &H->d_Wt); dfree(H, &H->d_Z); dfree(H, &H->d_L);
@@ -1178,7 +1244,8 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   mark("device + stream");
   // validate + pack the board-observation table (host, small)
   std::vector<int4> bobs(H->nb + 1);
-  std::vector<int> bflags(H->nb + 1, 0);
+  std::vector<int32_t>& bflags = H->h_bobs_flags;
+  bflags.assign(H->nb + 1, 0);
   std::vector<int> ppt(H->n_pose + 1, 0);
   H->h_bobs_cam.resize(H->nb); H->h_bobs_pose.resize(H->nb); H->h_bobs_board.resize(H->nb);
   H->h_bobs_ptr.assign(P->bobs_ptr, P->bobs_ptr + H->nb + 1);
@@ -1378,7 +1445,7 @@ int mcba_solve_step(void* h) {
   if (d == LM_TERMINATED) return 0;
   if (d == LM_ACCEPT) {   // HandleSuccessfulStep
     H->cur = 1 - H->cur;
-    if (H->cand_has_jac) { std::swap(H->d_brec, H->d_brec_alt); H->brec_par ^= 1; rc = eval_assemble(H, false); }
+    if (H->cand_has_jac) { std::swap(H->d_brec, H->d_brec_alt); std::swap(H->d_k1_partial, H->d_k1_partial_alt); H->brec_par ^= 1; rc = eval_assemble(H, false); }
     else rc = eval_jacobian(H, false);
     if (rc == MCBA_ERR_NUMERIC) { H->lm.termination = MCBA_FAILURE; H->lm.done = 1; return 0; }
     if (rc) return rc;
@@ -1644,6 +1711,7 @@ int mcba_debug_fetch(void* h, const char* name, double* out, int64_t cap, int64_
   else if (s == "zf") { src = H->d_zf; n = nf; } else if (s == "ZtZ") { src = H->d_ZtZ; n = ldz * ldz; }
   else if (s == "Hoo") { src = H->d_Hoo; n = np * 36; } else if (s == "Wt") { src = H->d_Wt; n = np * 6 * ldz; }
   else if (s == "Z") { src = H->d_Z; n = np * 6 * ldz; } else if (s == "brec") { src = H->d_brec; n = (int64_t)H->nb * stage_dims(H->stage).NCOMP; }
+  else if (s == "pair_rec") { src = H->pair_out; n = (int64_t)H->n_pair * H->NE; }
   else if (s == "scale_e") { src = H->d_scale_e; n = np * 6; } else if (s == "scale_f") { src = H->d_scale_f; n = nf; }
   else if (s == "diag_e") { src = H->d_diag_e; n = np * 6; } else if (s == "diag_f") { src = H->d_diag_f; n = nf; }
   else if (s == "chol_prof") {   // %globaltimer stamps of the last k_chol_tiles launch, as doubles (ns)

@@ -42,6 +42,9 @@ struct ObsArgs {
   double* jmat; double* resmat;     // materialised Jacobian blocks (see BlockSink); resmat unused
   int64_t npad;
   const int* bobs_flags;            // [nb] bit 0: reference camera, bit 1: reference board, camera model << 2 (the fused kernels of round 2)
+  // accumulating variants of the fused kernels: items in (camera, board) pair order - srec {first obs, cam, pose, board},
+  // saux {end obs, flags, board-observation index, chunk} - n_streams contiguous ranges, one partial pair record per chunk
+  const int4* srec; const int4* saux; int n_streams; double* partial;
   const uint8_t* gate;              // batched problems: per-camera flag, board observations of gated-off cameras are skipped
 };
 

@@ -84,7 +84,13 @@ template <int STAGE, int PASS = OBS_PASS, bool DBUF = true> struct FusedSmem {
   static constexpr int BYTES = OBS_WARPS * WARP_DOUBLES * 8 + IDX_BYTES;
 };
 
-template <int STAGE, int PASS = OBS_PASS, int MINB = 3, bool DBUF = true>
+// ACC: the warp walks a contiguous range of the items in (camera, board) pair order (ObsArgs::srec / saux) and keeps the
+// f x f / f x r entries of J~^T J~ in its accumulators across the board observations of one pair: per board observation
+// only the e-block part of the record (f x e, e x e, e x r: 153 of 405 doubles at stage 5) goes to HBM, per run ("chunk")
+// one partial pair record. k_pair_reduce - a second pass over 62 % of every record - disappears; k_pair_final sums the
+// chunks of a pair in order. The sums are deterministic (fixed ranges, fixed order) but ordered differently from the
+// per-record path: pair records agree with it to rounding.
+template <int STAGE, int PASS = OBS_PASS, int MINB = 3, bool DBUF = true, bool ACC = false>
 __global__ void __launch_bounds__(OBS_WARPS * 32, MINB) k_observations_fused(ObsArgs a) {
   typedef Cols<STAGE> C;
   typedef StageTraits<STAGE> ST;
@@ -119,8 +125,17 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, MINB) k_observations_fused(Obs
     sidx[r * 32 + lane] = make_short2(v[0], v[1]);
   }
   __syncthreads();
-  int b = blockIdx.x * OBS_WARPS + warp;
-  if (b >= a.nb) return;
+  // work items: ACC: positions [it, it_end) of the pair-ordered list; otherwise board observations it, it + total_warps, ...
+  int it, it_end, it_step;
+  if (ACC) {
+    const long long s = blockIdx.x * OBS_WARPS + warp;
+    it = (int)((long long)a.nb * s / a.n_streams); it_end = (int)((long long)a.nb * (s + 1) / a.n_streams); it_step = 1;
+  } else { it = blockIdx.x * OBS_WARPS + warp; it_end = a.nb; it_step = total_warps; }
+  if (it >= it_end) return;
+  auto fetch = [&](int i, int4& r, int& end, int& f, int& ob, int& ch) {
+    if (ACC) { r = a.srec[i]; const int4 x = a.saux[i]; end = x.x; f = x.y; ob = x.z; ch = x.w; }
+    else { r = a.bobs[i]; end = a.bobs[i + 1].x; f = a.bobs_flags[i]; ob = i; ch = 0; }
+  };
   for (int e = lane; e < SM::TILE; e += 32) T[e] = 0.0;
   // lane-constant operands of the two rounds of context products: out = M[3 i + .] . D[. + j]
   int m1, d1, o1, m2, d2, o2;
@@ -145,21 +160,25 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, MINB) k_observations_fused(Obs
     }
   };
   // prologue: this warp's first board observation
-  int obs_begin, obs_end, fl;
+  int obs_begin, obs_end, fl, ob, ch;
   {
-    const int4 rec = a.bobs[b];
-    obs_begin = rec.x; obs_end = a.bobs[b + 1].x; fl = a.bobs_flags[b];
+    int4 rec;
+    fetch(it, rec, obs_end, fl, ob, ch);
+    obs_begin = rec.x;
     issue_ctx(rec, fl, cbuf);
   }
+  double acc[NR][2];
+#pragma unroll
+  for (int t = 0; t < NR; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
   float pf_u = 0.f, pf_v = 0.f; int pf_pt = 0;
   if (lane < PASS && obs_begin + lane < obs_end) { pf_u = a.u[obs_begin + lane]; pf_v = a.v[obs_begin + lane]; pf_pt = a.pt[obs_begin + lane]; }
   int par = 0;
   while (true) {
     double* ctx = cbuf + (DBUF ? par : 0) * CtxRaw::SIZE;
-    const int bn = b + total_warps;
-    const bool has_n = bn < a.nb;
-    int4 rec_n = make_int4(0, 0, 0, 0); int end_n = 0, fl_n = 0;   // the next board observation: consumed after the first Jacobian phase at the earliest
-    if (has_n) { rec_n = a.bobs[bn]; end_n = a.bobs[bn + 1].x; fl_n = a.bobs_flags[bn]; }
+    const int itn = it + it_step;
+    const bool has_n = itn < it_end;
+    int4 rec_n = make_int4(0, 0, 0, 0); int end_n = 0, fl_n = 0, ob_n = 0, ch_n = -1;   // the next item: consumed after the first Jacobian phase at the earliest
+    if (has_n) fetch(itn, rec_n, end_n, fl_n, ob_n, ch_n);
     cp_async_wait_all();
     __syncwarp();
     ctx[o1] = ctx[m1] * ctx[d1] + ctx[m1 + 1] * ctx[d1 + 3] + ctx[m1 + 2] * ctx[d1 + 6];
@@ -168,9 +187,10 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, MINB) k_observations_fused(Obs
     __syncwarp();
     const bool act_c = ST::CAM && !(fl & 1), act_b = ST::BOARD && !(fl & 2);
     const int model = fl >> 2;
-    double acc[NR][2];
+    if (!ACC) {
 #pragma unroll
-    for (int t = 0; t < NR; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+      for (int t = 0; t < NR; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    }
     double cost = 0.0;
     for (int base = obs_begin; base < obs_end; base += PASS) {
       const int nact = min(PASS, obs_end - base);
@@ -220,19 +240,39 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, MINB) k_observations_fused(Obs
       if (lane < PASS && rec_n.x + lane < end_n) { pf_u = a.u[rec_n.x + lane]; pf_v = a.v[rec_n.x + lane]; pf_pt = a.pt[rec_n.x + lane]; }
     }
     {
-      double* out = a.brec + (size_t)b * C::NCOMP;
+      double* out = a.brec + (size_t)ob * C::NCOMP;
+      if (!ACC) {
 #pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        const short2 ci = sidx[r * 32 + lane];
-        if (ci.x >= 0) out[ci.x] = acc[r][0];
-        if (ci.y >= 0) out[ci.y] = acc[r][1];
+        for (int r = 0; r < NR; ++r) {
+          const short2 ci = sidx[r * 32 + lane];
+          if (ci.x >= 0) out[ci.x] = acc[r][0];
+          if (ci.y >= 0) out[ci.y] = acc[r][1];
+        }
+      } else {
+        // e-block part: stored and cleared per board observation; f part: kept until the run of this pair ends
+        const bool run_ends = !has_n || ch_n != ch;
+        double* part = a.partial + (size_t)ch * (size_t)C::CI_FE;
+        // (one predicated store and one select per entry: the class of an entry varies from lane to lane, branches
+        // here serialise the warp - 15 % of the kernel in the first build)
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const short2 ci = sidx[r * 32 + lane];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = h ? ci.y : ci.x;
+            const bool is_e = c >= C::CI_FE;
+            double* dst = (is_e ? out : part) + max(c, 0);
+            if (is_e || (run_ends && c >= 0)) *dst = acc[r][h];
+            acc[r][h] = (is_e || run_ends) ? 0.0 : acc[r][h];
+          }
+        }
       }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, off);
-      if (lane == 0) a.cost_bobs[b] = cost;
+      if (lane == 0) a.cost_bobs[ob] = cost;
     }
     if (!has_n) break;
-    b = bn; obs_begin = rec_n.x; obs_end = end_n; fl = fl_n; par ^= 1;
+    it = itn; obs_begin = rec_n.x; obs_end = end_n; fl = fl_n; ob = ob_n; ch = ch_n; par ^= 1;
   }
 }
 
@@ -260,7 +300,9 @@ template <int STAGE> struct PairSmem {
   static constexpr int BYTES = OBS_WARPS * WARP_DOUBLES * 8 + IDX_BYTES + CTAB_BYTES;
 };
 
-template <int STAGE>
+// ACC (see k_observations_fused): every half-warp is a stream with its own contiguous range of the pair-ordered items
+// and its own accumulator set; otherwise half h of warp w takes board observations 2 (w + k total_warps) + h.
+template <int STAGE, bool ACC = false>
 __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_pair(ObsArgs a) {
   typedef Cols<STAGE> C;
   typedef StageTraits<STAGE> ST;
@@ -301,13 +343,19 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_pair(ObsArgs
   }
   __syncthreads();
   const int total_warps = gridDim.x * OBS_WARPS;
-  const int n_pairs = (a.nb + 1) >> 1;
-  int p = blockIdx.x * OBS_WARPS + warp;
-  if (p >= n_pairs) return;
+  // this half-warp's items
+  int it, it_end, it_step;
+  if (ACC) {
+    const long long s = 2 * (blockIdx.x * OBS_WARPS + warp) + hi;
+    it = (int)((long long)a.nb * s / a.n_streams); it_end = (int)((long long)a.nb * (s + 1) / a.n_streams); it_step = 1;
+  } else { it = 2 * (blockIdx.x * OBS_WARPS + warp) + hi; it_end = a.nb; it_step = 2 * total_warps; }
+  bool cur_ok = it < it_end;
+  if (!__any_sync(0xffffffffu, cur_ok)) return;
   for (int e = lane; e < SM::TILE; e += 32) T[e] = 0.0;
-  auto load_rec = [&](int pp, int4& r, int& end, int& f) {   // this lane's board observation of pair pp (empty past the end)
-    const int bb = 2 * pp + hi;
-    if (bb < a.nb) { r = a.bobs[bb]; end = a.bobs[bb + 1].x; f = a.bobs_flags[bb]; } else { r = make_int4(0, 0, 0, 0); end = 0; f = 0; }
+  auto fetch = [&](int i, bool ok, int4& r, int& end, int& f, int& ob, int& ch) {   // an exhausted half sees empty items
+    if (!ok) { r = make_int4(0, 0, 0, 0); end = 0; f = 0; ob = 0; ch = -1; }
+    else if (ACC) { r = a.srec[i]; const int4 x = a.saux[i]; end = x.x; f = x.y; ob = x.z; ch = x.w; }
+    else { r = a.bobs[i]; end = a.bobs[i + 1].x; f = a.bobs_flags[i]; ob = i; ch = 0; }
   };
   auto issue_ctx = [&](const int4& r, int f) {
     const bool act_c = ST::CAM && !(f & 1), act_b = ST::BOARD && !(f & 2);
@@ -322,21 +370,24 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_pair(ObsArgs
     }
   };
   // batched problems: board observations of cameras whose gate is off are skipped (nothing computed, nothing stored)
-  int my_begin, obs_end, fl, gate_on = 1;
+  int my_begin, obs_end, fl, ob, ch, gate_on = 1;
   {
     int4 rec;
-    load_rec(p, rec, obs_end, fl);
+    fetch(it, cur_ok, rec, obs_end, fl, ob, ch);
     my_begin = rec.x;
     issue_ctx(rec, fl);
-    if (a.gate) gate_on = a.gate[rec.y];
+    if (a.gate && cur_ok) gate_on = a.gate[rec.y];
   }
   float pf_u = 0.f, pf_v = 0.f; int pf_pt = 0;
   if (my_begin + l16 < obs_end) { pf_u = a.u[my_begin + l16]; pf_v = a.v[my_begin + l16]; pf_pt = a.pt[my_begin + l16]; }
+  double accA[NR][2], accB[NR][2];
+#pragma unroll
+  for (int t = 0; t < NR; ++t) { accA[t][0] = 0.0; accA[t][1] = 0.0; accB[t][0] = 0.0; accB[t][1] = 0.0; }
   while (true) {
-    const int pn = p + total_warps;
-    const bool has_n = pn < n_pairs;
-    int4 rec_n = make_int4(0, 0, 0, 0); int end_n = 0, fl_n = 0;   // consumed in the last pass
-    if (has_n) load_rec(pn, rec_n, end_n, fl_n);
+    const int itn = it + it_step;
+    const bool has_n = cur_ok && itn < it_end;
+    int4 rec_n; int end_n, fl_n, ob_n, ch_n;                   // consumed in the last pass
+    fetch(itn, has_n, rec_n, end_n, fl_n, ob_n, ch_n);
     cp_async_wait_all();
     __syncwarp();
 #pragma unroll
@@ -348,9 +399,10 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_pair(ObsArgs
     }
     const bool act_c = ST::CAM && !(fl & 1), act_b = ST::BOARD && !(fl & 2);
     const int model = fl >> 2;
-    double accA[NR][2], accB[NR][2];
+    if (!ACC) {
 #pragma unroll
-    for (int t = 0; t < NR; ++t) { accA[t][0] = 0.0; accA[t][1] = 0.0; accB[t][0] = 0.0; accB[t][1] = 0.0; }
+      for (int t = 0; t < NR; ++t) { accA[t][0] = 0.0; accA[t][1] = 0.0; accB[t][0] = 0.0; accB[t][1] = 0.0; }
+    }
     double cost = 0.0;
     const int n_mine = gate_on ? obs_end - my_begin : 0;
     int gate_n = 1;
@@ -411,23 +463,46 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_pair(ObsArgs
       if (rec_n.x + l16 < end_n) { pf_u = a.u[rec_n.x + l16]; pf_v = a.v[rec_n.x + l16]; pf_pt = a.pt[rec_n.x + l16]; }
     }
     {
-      const int bA = 2 * p, bB = 2 * p + 1;
-      double* outA = a.brec + (size_t)bA * C::NCOMP;
-      double* outB = a.brec + (size_t)bB * C::NCOMP;
-      const bool okA = __shfl_sync(0xffffffffu, gate_on, 0) != 0;
-      const bool okB = bB < a.nb && __shfl_sync(0xffffffffu, gate_on, 16) != 0;
+      const int obA = __shfl_sync(0xffffffffu, ob, 0), obB = __shfl_sync(0xffffffffu, ob, 16);
+      const bool ok = cur_ok && gate_on;
+      const bool okA = __shfl_sync(0xffffffffu, (int)ok, 0) != 0, okB = __shfl_sync(0xffffffffu, (int)ok, 16) != 0;
+      double* outA = a.brec + (size_t)obA * C::NCOMP;
+      double* outB = a.brec + (size_t)obB * C::NCOMP;
+      if (!ACC) {
 #pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        const short2 ci = sidx[r * 32 + lane];
-        if (ci.x >= 0) { if (okA) outA[ci.x] = accA[r][0]; if (okB) outB[ci.x] = accB[r][0]; }
-        if (ci.y >= 0) { if (okA) outA[ci.y] = accA[r][1]; if (okB) outB[ci.y] = accB[r][1]; }
+        for (int r = 0; r < NR; ++r) {
+          const short2 ci = sidx[r * 32 + lane];
+          if (ci.x >= 0) { if (okA) outA[ci.x] = accA[r][0]; if (okB) outB[ci.x] = accB[r][0]; }
+          if (ci.y >= 0) { if (okA) outA[ci.y] = accA[r][1]; if (okB) outB[ci.y] = accB[r][1]; }
+        }
+      } else {
+        const bool ends = cur_ok && (!has_n || ch_n != ch);
+        const bool endA = __shfl_sync(0xffffffffu, (int)ends, 0) != 0, endB = __shfl_sync(0xffffffffu, (int)ends, 16) != 0;
+        const int chA = __shfl_sync(0xffffffffu, ch, 0), chB = __shfl_sync(0xffffffffu, ch, 16);
+        double* partA = a.partial + (size_t)max(chA, 0) * (size_t)C::CI_FE;
+        double* partB = a.partial + (size_t)max(chB, 0) * (size_t)C::CI_FE;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const short2 ci = sidx[r * 32 + lane];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = h ? ci.y : ci.x;
+            const bool is_e = c >= C::CI_FE;
+            double* dA = (is_e ? outA : partA) + max(c, 0);
+            double* dB = (is_e ? outB : partB) + max(c, 0);
+            if (is_e ? okA : (endA && c >= 0)) *dA = accA[r][h];
+            if (is_e ? okB : (endB && c >= 0)) *dB = accB[r][h];
+            accA[r][h] = (is_e || endA) ? 0.0 : accA[r][h];
+            accB[r][h] = (is_e || endB) ? 0.0 : accB[r][h];
+          }
+        }
       }
 #pragma unroll
       for (int off = 8; off > 0; off >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, off);
-      if (l16 == 0 && 2 * p + hi < a.nb && gate_on) a.cost_bobs[2 * p + hi] = cost;
+      if (l16 == 0 && ok) a.cost_bobs[ob] = cost;
     }
-    if (!has_n) break;
-    p = pn; my_begin = rec_n.x; obs_end = end_n; fl = fl_n; gate_on = gate_n;
+    if (!__any_sync(0xffffffffu, has_n)) break;
+    it = itn; cur_ok = has_n; my_begin = rec_n.x; obs_end = end_n; fl = fl_n; ob = ob_n; ch = ch_n; gate_on = gate_n;
   }
 }
 

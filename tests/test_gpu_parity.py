@@ -442,35 +442,52 @@ def _ragged_problem(stage, seed=3):
     return p2, init
 
 
+def _record_layout(stage):
+    """(first index of the e-block part, length) of a compact per-board-observation record (Cols<STAGE>, mcba_math.cuh)."""
+    wf = {1: 9, 2: 6, 3: 6, 4: 12, 5: 21}[stage]
+    ci_fe = wf * (wf + 1) // 2 + wf
+    return ci_fe, ci_fe + 6 * wf + 27
+
+
 @pytest.mark.parametrize("stage", [1, 2, 3, 4, 5])
 def test_fused_observation_kernel_variants_write_identical_records(stage, oracle):
-    """k_observations_fused (0), k_observations_pair (3), the streaming experiment (2) and the 16-warp experiment (4)
-    against the first version (1): same per-corner arithmetic and the same row order of the DMMA sums, so the per-board-observation records and
-    costs are identical bit for bit - on ragged corner counts too - and the first version is the one the oracle
-    comparison of the normal equations was made with (test_normal_equations_and_schur runs the default variant)."""
+    """The fused observation kernels against the first version (variant 1): k_observations_fused (0), k_observations_pair
+    (3), the streaming experiment (2) and the 16-warp experiment (4). Same per-corner arithmetic and the same row order
+    of the DMMA sums: the per-board-observation records and costs are identical bit for bit - on ragged corner counts,
+    empty board observations and an odd count too. With the in-kernel pair accumulation on (32 + variant; an
+    experiment, off by default) the e-block part of every record is still identical and the pair records
+    (sums over the board observations of a (camera, board) pair, taken in another order) agree to rounding. Variant 1
+    is the one whose normal equations are compared with the oracle's (test_normal_equations_and_schur runs the default)."""
     lib = mcba.load_lib()
     prob, init = _ragged_problem(stage)
     assert prob.n_bobs % 2 == 1 and len(set(np.diff(prob.bobs_ptr) % 2)) == 2
+    ci_fe, ncomp = _record_layout(stage)
     ref = None
     try:
-        for variant in (1, 0, 3, 2, 4):
+        for variant in (1, 0, 3, 2, 4, 32 + 0, 32 + 3):
             lib.mcba_debug_set_k1(variant)
             h = mcba.Handle(prob)
             h.solve_begin(init.copy(), mcba.default_options())
-            rec = h.debug_fetch("brec").copy()
+            rec = h.debug_fetch("brec").reshape(prob.n_bobs, ncomp).copy()
+            pair = h.debug_fetch("pair_rec").copy()
             cost = h.eval(init.copy(), want_jac=False)[0]
             h.solve_end(init.copy())
             h.close()
-            assert np.isfinite(rec).all()
+            assert np.isfinite(pair).all() and np.isfinite(rec[:, ci_fe:]).all()
             if ref is None:
-                ref = (rec, cost)
+                assert np.isfinite(rec).all()
+                ref = (rec, cost, pair)
                 rc, co, _, _, _ = oracle.eval(prob, init.copy())
                 assert rc == 0 and abs(cost - co) <= 1e-11 * abs(co)
-            else:
-                scale = np.abs(ref[0]).max()
-                # variant 4 (24-corner passes) compiles obs_jacobian with other multiply-add contractions: rounding level
-                assert np.abs(rec - ref[0]).max() <= (1e-12 if variant == 4 else 1e-15) * scale, f"variant {variant}"
-                assert abs(cost - ref[1]) <= 1e-14 * abs(ref[1])
+                continue
+            scale = np.abs(ref[0]).max()
+            # variant 4 (24-corner passes) compiles obs_jacobian with other multiply-add contractions: rounding level
+            tol = 1e-12 if variant == 4 else 1e-15
+            accumulating = variant >= 32
+            part = slice(ci_fe, None) if accumulating else slice(None)
+            assert np.abs(rec[:, part] - ref[0][:, part]).max() <= tol * scale, f"variant {variant}"
+            assert np.abs(pair - ref[2]).max() <= (1e-13 if accumulating or variant == 4 else 1e-15) * np.abs(ref[2]).max(), f"variant {variant}"
+            assert abs(cost - ref[1]) <= 1e-14 * abs(ref[1])
     finally:
         lib.mcba_debug_set_k1(-1)
 

@@ -18,7 +18,7 @@ from bench import bench_options
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, default=2500)
-ap.add_argument("--variants", default="1,0")
+ap.add_argument("--variants", default="1,0,3")
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--stages", default="5,4")
 ap.add_argument("--small", action="store_true", help="also compare the records on configs c1 / c2, all five stages")
@@ -28,10 +28,17 @@ lib = mcba.load_lib()
 out = {"frames": args.frames, "runs": []}
 
 
+WF = {1: 9, 2: 6, 3: 6, 4: 12, 5: 21}
+
+
 def records(h, prob, p, opt):
+    """e-block part of every record (the f part is not written when the kernel accumulates pair records itself) and the
+    pair records after the assembly."""
     h.solve_begin(p.copy(), opt)
-    rec = h.debug_fetch("brec").copy()
-    return rec
+    wf = WF[prob.stage]
+    ci_fe = wf * (wf + 1) // 2 + wf
+    rec = h.debug_fetch("brec").reshape(prob_nb(prob), -1)[:, ci_fe:].copy()
+    return rec, h.debug_fetch("pair_rec").copy()
 
 
 def run(prob, init, label, steps):
@@ -41,7 +48,7 @@ def run(prob, init, label, steps):
         lib.mcba_debug_set_k1(v)
         h = mcba.Handle(prob)
         p = init.copy()
-        rec = records(h, prob, p, opt)
+        rec, pair = records(h, prob, p, opt)
         row = {"case": label, "variant": v, "observations": int(prob.n_obs)}
         if steps:
             for _ in range(3):
@@ -58,12 +65,13 @@ def run(prob, init, label, steps):
         summ = h.solve_end(p)
         h.close()
         if ref is None:
-            ref = rec
+            ref = (rec, pair)
         else:
-            a = ref.reshape(prob_nb(prob), -1); b = rec.reshape(prob_nb(prob), -1)
+            a = ref[0]; b = rec
             scale = np.abs(a).max(axis=1, keepdims=True) + 1e-300
             row["max_rel_diff_vs_first"] = float((np.abs(a - b) / scale).max())
-            row["n_nan"] = int(np.isnan(b).sum())
+            row["pair_rec_max_rel_diff_vs_first"] = float(np.abs(pair - ref[1]).max() / (np.abs(ref[1]).max() + 1e-300))
+            row["n_nan"] = int(np.isnan(b).sum() + np.isnan(pair).sum())
         out["runs"].append(row)
         print(json.dumps(row), file=sys.stderr, flush=True)
     lib.mcba_debug_set_k1(-1)
