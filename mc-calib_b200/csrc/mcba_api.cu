@@ -132,6 +132,7 @@ struct Handle {
   // CUDA graphs of the two per-iteration launch sequences (single-rank handles): key = 2 * cur + brec_par
   bool use_graph = false, graph_env = false, capturing = false; int brec_par = 0;
   int k1_variant = -1;               // fused observation kernel of this handle (launch_obs)
+  bool k1_pair_saves = true;         // 16-corner half-warp passes of two board observations < 0.9 x the 32-corner passes of one
   // K1 with in-kernel accumulation of the f x f / f x r part over runs of one (camera, board) pair (k1_acc): the board
   // observations in pair order with everything a warp needs per item, the runs ("chunks") cut at the streams' range
   // boundaries, one partial pair record per chunk for each of the two tile sets
@@ -247,7 +248,11 @@ static int setup_batched(Handle* H) {
 static void drop_graphs(Handle* H);
 // Fused observation kernel of a stage (launch_obs): the handle's variant, or the default per stage.
 // (variant + 32 = that variant with the in-kernel pair accumulation, + 16 = without it, whatever MCBA_K1_ACC says: test hook)
-static int k1_variant_of(const Handle* H, int stage) { (void)stage; return H->k1_variant >= 0 ? (H->k1_variant & 15) : 3; }
+// Default: the pair kernel (3) when pairing saves Jacobian passes - corner counts whose last 32-corner pass is at most
+// half full (48-corner boards: 3 passes of 16 + 16 per pair instead of 4; 16-corner boards: 1 instead of 2) - else the
+// one-observation kernel (0): with 63-corner boards both need 2 passes per board observation and the pair kernel only
+// adds its bookkeeping (config 3, stage 5: 1.81 vs 1.70 ms per iteration).
+static int k1_variant_of(const Handle* H, int stage) { (void)stage; return H->k1_variant >= 0 ? (H->k1_variant & 15) : (H->k1_pair_saves ? 3 : 0); }
 // Grid of the two kernels that can accumulate pair records (k_observations_fused / k_observations_pair): 3 CTAs per SM
 // unless the shared memory of the stage allows fewer; the streams (warps / half-warps) of this grid own fixed ranges.
 static int k1_grid_of(const Handle* H, int stage, int k1v, int nb) {
@@ -1249,6 +1254,15 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   std::vector<int> ppt(H->n_pose + 1, 0);
   H->h_bobs_cam.resize(H->nb); H->h_bobs_pose.resize(H->nb); H->h_bobs_board.resize(H->nb);
   H->h_bobs_ptr.assign(P->bobs_ptr, P->bobs_ptr + H->nb + 1);
+  {
+    long long p32 = 0, p16 = 0;      // Jacobian passes: one observation per warp / two per warp (a pair's passes = the longer half's)
+    for (int b = 0; b < H->nb; ++b) {
+      const long long c = P->bobs_ptr[b + 1] - P->bobs_ptr[b];
+      if (c > 0) { p32 += (c + 31) / 32; if (b % 2 == 0) { const long long c2 = b + 1 < H->nb ? P->bobs_ptr[b + 2] - P->bobs_ptr[b + 1] : 0; p16 += (std::max(c, c2) + 15) / 16; } }
+      else if (b % 2 == 0 && b + 1 < H->nb) { p16 += (P->bobs_ptr[b + 2] - P->bobs_ptr[b + 1] + 15) / 16; }
+    }
+    H->k1_pair_saves = H->batched || 10 * p16 < 9 * p32;
+  }
   for (int b = 0; b < H->nb; ++b) {
     const int c = P->bobs_cam[b], o = P->bobs_pose[b], bd = P->bobs_board ? P->bobs_board[b] : 0;
     if (c < 0 || c >= P->n_cam || o < 0 || o >= P->n_pose || (b > 0 && o < P->bobs_pose[b - 1]) ||
