@@ -80,8 +80,10 @@ def golden_c4(frames):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons while the timed region runs: NVML (initialised before the
-    region starts, sampled every few steps from the timed loop on rank 0 - the timed region is ~100 ms, and `nvidia-smi -lms` needs longer than that
+    """SM clock and throttle reasons while the timed region runs: NVML polled from a thread (initialised before the
+    region starts, one sample every 25 ms on rank 0 only - an NVML query takes ~0.4 ms and contends with CUDA launches in the
+    driver: taken from the timed loop itself six samples cost 4.6 % of the step, and a 4 ms poll on all eight ranks 15 % - the
+    timed region is ~100 ms, and `nvidia-smi -lms` needs longer than that
     to produce its first line on an 8-GPU box); nvidia-smi as the fallback when the NVML binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -89,7 +91,7 @@ class ClockSampler:
 
     def __init__(self, gpu_index, uuid=None):
         self.idx = gpu_index
-        self.p = self.f = None
+        self.p = self.f = self.thread = None
         self.sm, self.reason_bits, self.mx = [], 0, None
         self.nvml = None
         try:
@@ -107,22 +109,23 @@ class ClockSampler:
         except Exception:
             self.nvml = None
 
-    def sample(self):
-        """One NVML sample from the calling thread (the timed loop calls this every few steps on rank 0: a polling thread
-        perturbed the N = 8 step - NVML queries and CUDA launches contend in the driver)."""
-        if self.nvml is None:
-            return
+    def _poll(self):
         n = self.nvml
         get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
-        try:
-            self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
-            self.reason_bits |= int(get_reasons(self.h))
-        except Exception:
-            pass
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                self.reason_bits |= int(get_reasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.025)
 
     def start(self):
         if self.nvml is not None:
-            self.inline = True
+            import threading
+            self.stop_flag = False
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
             return
         try:
             self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
@@ -132,7 +135,9 @@ class ClockSampler:
             self.p = None
 
     def stop(self):
-        if self.nvml is not None:
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
             reasons = sorted(name for bit, name in self.REASONS.items() if self.reason_bits & bit)
             return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx, "reasons": reasons,
                     "samples": len(self.sm), "source": "nvml"}
@@ -349,11 +354,8 @@ def main():
             sampler.start()
         h.timer_start()
         t0 = time.perf_counter()
-        every = max(1, steps // 6)
-        for k in range(steps):
+        for _ in range(steps):
             assert h.solve_step() == 1, "LM terminated inside the timed region"
-            if sampler is not None and k % every == every // 2:
-                sampler.sample()                  # SM clock / throttle reasons under load, from this thread (~50 us of host time)
         ms_dev = h.timer_stop()
         ms_wall = (time.perf_counter() - t0) * 1e3
         barrier()
