@@ -346,10 +346,14 @@ def main():
         h.solve_begin(p, options)                       # upload parameters + iteration 0 (untimed)
         for _ in range(warmup):
             assert h.solve_step() == 1
-        barrier()
+        # rank 0 only: eight processes polling NVML every few ms slowed the N = 8 step by 15 %. Created (NVML initialisation:
+        # tens of ms) BEFORE the barrier: everything between the barrier and timer_start delays this rank alone, and the
+        # other ranks - whose timers are already running - wait for it in the first exchange (the max over ranks then
+        # charges that delay to the timed region: 2.77 instead of 2.13 ms per step in one N = 8 run)
+        sampler = ClockSampler(local_rank, gpu_uuid) if (sample_clocks and rank == 0) else None
         h.reset_kernel_stats()
         l0 = h.kernel_launches()
-        sampler = ClockSampler(local_rank, gpu_uuid) if (sample_clocks and rank == 0) else None   # rank 0 only: eight processes polling NVML every few ms slowed the N = 8 step by 15 %
+        barrier()
         if sampler:
             sampler.start()
         h.timer_start()
