@@ -17,7 +17,8 @@ def last_line(path):
 
 
 @pytest.mark.parametrize("name,n", [("r01e_bench_n1.json", 1), ("r01e_bench_n2.json", 2), ("r01d_bench_n4.json", 4), ("r01d_bench_n8.json", 8),
-                                    ("r02b_bench_n1.json", 1), ("r02b_bench_n2.json", 2), ("r02b_bench_n4.json", 4), ("r02b_bench_n8.json", 8)])
+                                    ("r02b_bench_n1.json", 1), ("r02b_bench_n2.json", 2), ("r02b_bench_n4.json", 4), ("r02b_bench_n8.json", 8),
+                                    ("r02c_bench_n1.json", 1), ("r02c_bench_n2.json", 2), ("r02c_bench_n8.json", 8)])
 def test_committed_gpu_records(name, n):
     d = last_line(os.path.join(REPO, "profiles", name))
     for k in BASE + ["clocks", "gpu_launches", "e2e", "roofline", "cpu_baseline"]:
