@@ -182,6 +182,57 @@ MCBA_HD double ctx_entry_b(int e, const double* ctx, const double* po, const dou
   return M[i * 3 + 0] * D[0 * 3 + j] + M[i * 3 + 1] * D[1 * 3 + j] + M[i * 3 + 2] * D[2 * 3 + j];
 }
 
+// Cover of the upper triangle (in 4-column groups) by products rows {r0, r1} x columns {c0, c1}; own = which of the four
+// blocks (bit 2 * row_half + col_half) this product stores (a block may be computed twice in the small covers).
+template <int NG> struct RectCover;
+template <> struct RectCover<7> {   // Fano plane
+  static constexpr int NR = 7;
+  MCBA_HD static constexpr int r0(int i) { return i; }
+  MCBA_HD static constexpr int r1(int i) { return (i + 1) % 7; }
+  MCBA_HD static constexpr int c0(int i) { return i; }
+  MCBA_HD static constexpr int c1(int i) { return (i + 3) % 7; }
+  MCBA_HD static constexpr int own(int) { return 15; }
+};
+template <> struct RectCover<5> {   // (0,0)(0,2)(1,0)(1,2) | (3,3)(3,0)(4,3)(4,0) | (1,3)(1,4)(2,3)(2,4) | (1,1)(2,2) | (4,4)
+  static constexpr int NR = 5;
+  MCBA_HD static constexpr int r0(int i) { return i == 0 ? 0 : i == 1 ? 3 : i == 2 ? 1 : i == 3 ? 1 : 4; }
+  MCBA_HD static constexpr int r1(int i) { return i == 0 ? 1 : i == 1 ? 4 : i == 2 ? 2 : i == 3 ? 2 : 4; }
+  MCBA_HD static constexpr int c0(int i) { return i == 0 ? 0 : i == 1 ? 3 : i == 2 ? 3 : i == 3 ? 1 : 4; }
+  MCBA_HD static constexpr int c1(int i) { return i == 0 ? 2 : i == 1 ? 0 : i == 2 ? 4 : i == 3 ? 2 : 4; }
+  MCBA_HD static constexpr int own(int i) { return i < 3 ? 15 : i == 3 ? 9 : 1; }
+};
+template <> struct RectCover<4> {   // aligned 8x8 tiles: (0,0)(0,1)(1,1) | (0,2)(0,3)(1,2)(1,3) | (2,2)(2,3)(3,3)
+  static constexpr int NR = 3;
+  MCBA_HD static constexpr int r0(int i) { return i == 2 ? 2 : 0; }
+  MCBA_HD static constexpr int r1(int i) { return i == 2 ? 3 : 1; }
+  MCBA_HD static constexpr int c0(int i) { return i == 0 ? 0 : 2; }
+  MCBA_HD static constexpr int c1(int i) { return i == 0 ? 1 : 3; }
+  MCBA_HD static constexpr int own(int i) { return i == 1 ? 15 : 11; }   // not the mirrored (1,0) / (3,2)
+};
+
+// Record index (Cols<STAGE>::cidx) of entry h of the accumulator pair that lane `lane` holds for product r of the cover
+// (m8n8k4 accumulator layout: row lane / 4, columns 2 (lane % 4) + h; the lower half-warp's rows belong to the product's
+// first row group, the upper half-warp's to the second; columns 0-3 to its first column group, 4-7 to the second);
+// -1: nothing to store (mirrored half of a diagonal block, padding column, residual x residual, block owned elsewhere).
+template <int STAGE> MCBA_HD int k1_store_index(int r, int lane, int h) {
+  typedef Cols<STAGE> C;
+  typedef RectCover<(C::NC + 3) / 4> RCV;
+  const int g = lane >> 2, q = lane & 3, hi = lane >> 4, c4 = g & 3, ch = q >> 1;
+  int gr = 0, gc = 0, own = 0;
+  for (int rr = 0; rr < RCV::NR; ++rr)
+    if (rr == r) { gr = hi ? RCV::r1(rr) : RCV::r0(rr); gc = ch ? RCV::c1(rr) : RCV::c0(rr); own = RCV::own(rr); }
+  const int ea = 4 * gr + c4, eb = 4 * gc + ((2 * q + h) & 3);
+  if (!((own >> (2 * hi + ch)) & 1) || ea >= C::NC || eb >= C::NC || (gr == gc && ea > eb)) return -1;
+  return C::cidx(ea < eb ? ea : eb, ea < eb ? eb : ea);
+}
+// The 63 three-term products of the copy-free context: product e writes ctx[o] = sum_n ctx[m + n] * ctx[d + 3 n].
+// e < 9: Mco = Rc Ro; e < 36: No_k = Mc dRo_k; else Nb_k = Mco dRb_k (needs Mco: computed in an earlier round).
+MCBA_HD void ctx_raw_operands(int e, int& m, int& d, int& o) {
+  if (e < 9) { m = CtxRaw::RC + 3 * (e / 3); d = CtxRaw::RO + e % 3; o = CtxRaw::MCO + e; }
+  else if (e < 36) { const int f = e - 9, k = f / 9, i = (f % 9) / 3, j = f % 3; m = CtxRaw::MC + 3 * i; d = CtxRaw::PO + 9 + 9 * k + j; o = CtxRaw::NO + f; }
+  else { const int f = e - 36, k = f / 9, i = (f % 9) / 3, j = f % 3; m = CtxRaw::MCO + 3 * i; d = CtxRaw::PB + 9 + 9 * k + j; o = CtxRaw::NB + f; }
+}
+
 MCBA_HD void mat3_vec(const double* M, const double* x, double* y) {
   y[0] = M[0] * x[0] + M[1] * x[1] + M[2] * x[2];
   y[1] = M[3] * x[0] + M[4] * x[1] + M[5] * x[2];

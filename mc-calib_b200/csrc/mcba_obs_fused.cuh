@@ -29,34 +29,6 @@ namespace mcba {
 // Identity prep record (R = I, dR/dw_k = 0, t = 0) for blocks that are not refined.
 __device__ const double g_prep_identity[PREP + 1] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
 
-// Cover of the upper triangle (in 4-column groups) by products rows {r0, r1} x columns {c0, c1}; own = which of the four
-// blocks (bit 2 * row_half + col_half) this product stores (a block may be computed twice in the small covers).
-template <int NG> struct RectCover;
-template <> struct RectCover<7> {   // Fano plane
-  static constexpr int NR = 7;
-  __host__ __device__ static constexpr int r0(int i) { return i; }
-  __host__ __device__ static constexpr int r1(int i) { return (i + 1) % 7; }
-  __host__ __device__ static constexpr int c0(int i) { return i; }
-  __host__ __device__ static constexpr int c1(int i) { return (i + 3) % 7; }
-  __host__ __device__ static constexpr int own(int) { return 15; }
-};
-template <> struct RectCover<5> {   // (0,0)(0,2)(1,0)(1,2) | (3,3)(3,0)(4,3)(4,0) | (1,3)(1,4)(2,3)(2,4) | (1,1)(2,2) | (4,4)
-  static constexpr int NR = 5;
-  __host__ __device__ static constexpr int r0(int i) { return i == 0 ? 0 : i == 1 ? 3 : i == 2 ? 1 : i == 3 ? 1 : 4; }
-  __host__ __device__ static constexpr int r1(int i) { return i == 0 ? 1 : i == 1 ? 4 : i == 2 ? 2 : i == 3 ? 2 : 4; }
-  __host__ __device__ static constexpr int c0(int i) { return i == 0 ? 0 : i == 1 ? 3 : i == 2 ? 3 : i == 3 ? 1 : 4; }
-  __host__ __device__ static constexpr int c1(int i) { return i == 0 ? 2 : i == 1 ? 0 : i == 2 ? 4 : i == 3 ? 2 : 4; }
-  __host__ __device__ static constexpr int own(int i) { return i < 3 ? 15 : i == 3 ? 9 : 1; }
-};
-template <> struct RectCover<4> {   // aligned 8x8 tiles: (0,0)(0,1)(1,1) | (0,2)(0,3)(1,2)(1,3) | (2,2)(2,3)(3,3)
-  static constexpr int NR = 3;
-  __host__ __device__ static constexpr int r0(int i) { return i == 2 ? 2 : 0; }
-  __host__ __device__ static constexpr int r1(int i) { return i == 2 ? 3 : 1; }
-  __host__ __device__ static constexpr int c0(int i) { return i == 0 ? 0 : 2; }
-  __host__ __device__ static constexpr int c1(int i) { return i == 0 ? 1 : 3; }
-  __host__ __device__ static constexpr int own(int i) { return i == 1 ? 15 : 11; }   // not the mirrored (1,0) / (3,2)
-};
-
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(d), "l"(gsrc) : "memory");
@@ -108,22 +80,8 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, MINB) k_observations_fused(Obs
   // left to the compiler they are hoisted out of the board-observation loop and spilled (14 dependent local-memory
   // round trips per board observation in the epilogue, 30 % of the kernel: profiles/r02_ncu_k1_source_hotspots.txt)
   short2* sidx = reinterpret_cast<short2*>(smem + OBS_WARPS * SM::WARP_DOUBLES);
-  for (int r = warp; r < NR; r += OBS_WARPS) {
-    int gr = 0, gc = 0, own = 0;
-#pragma unroll
-    for (int rr = 0; rr < NR; ++rr)
-      if (rr == r) { gr = hi ? RCV::r1(rr) : RCV::r0(rr); gc = (q >> 1) ? RCV::c1(rr) : RCV::c0(rr); own = RCV::own(rr); }
-    short v[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int ea = 4 * gr + c4, eb = 4 * gc + ((2 * q + h) & 3);
-      const bool mine = (own >> (2 * hi + (q >> 1))) & 1;
-      int ci = -1;
-      if (mine && ea < C::NC && eb < C::NC && (gr != gc || ea <= eb)) ci = C::cidx(min(ea, eb), max(ea, eb));
-      v[h] = (short)ci;
-    }
-    sidx[r * 32 + lane] = make_short2(v[0], v[1]);
-  }
+  for (int r = warp; r < NR; r += OBS_WARPS)
+    sidx[r * 32 + lane] = make_short2((short)k1_store_index<STAGE>(r, lane, 0), (short)k1_store_index<STAGE>(r, lane, 1));
   __syncthreads();
   // work items: ACC: positions [it, it_end) of the pair-ordered list; otherwise board observations it, it + total_warps, ...
   int it, it_end, it_step;
@@ -138,13 +96,9 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, MINB) k_observations_fused(Obs
   };
   for (int e = lane; e < SM::TILE; e += 32) T[e] = 0.0;
   // lane-constant operands of the two rounds of context products: out = M[3 i + .] . D[. + j]
-  int m1, d1, o1, m2, d2, o2;
-  {
-    if (lane < 9) { m1 = CtxRaw::RC + 3 * (lane / 3); d1 = CtxRaw::RO + lane % 3; o1 = CtxRaw::MCO + lane; }
-    else { const int e = lane - 9, k = e / 9, i = (e % 9) / 3, j = e % 3; m1 = CtxRaw::MC + 3 * i; d1 = CtxRaw::PO + 9 + 9 * k + j; o1 = CtxRaw::NO + e; }
-    if (lane < 4) { const int e = 23 + lane, k = e / 9, i = (e % 9) / 3, j = e % 3; m2 = CtxRaw::MC + 3 * i; d2 = CtxRaw::PO + 9 + 9 * k + j; o2 = CtxRaw::NO + e; }
-    else { const int e = min(lane - 4, 26), k = e / 9, i = (e % 9) / 3, j = e % 3; m2 = CtxRaw::MCO + 3 * i; d2 = CtxRaw::PB + 9 + 9 * k + j; o2 = CtxRaw::NB + e; }
-  }
+  int m1, d1, o1, m2, d2, o2;   // products 0..31 in the first round (Mco and No[0..22]), 32..62 in the second (No[23..26], Nb)
+  ctx_raw_operands(lane, m1, d1, o1);
+  ctx_raw_operands(min(32 + lane, 62), m2, d2, o2);
   // flags of a board observation (ObsArgs::bobs_flags: bit 0 reference camera, bit 1 reference board, camera model
   // << 2): one word per board observation, so that nothing has to be looked up through the record
   auto issue_ctx = [&](const int4& r, int f, double* dst) {   // raw context of one board observation -> dst (asynchronous)
@@ -317,28 +271,11 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 3) k_observations_pair(ObsArgs
   double* T = cbuf + 2 * CTXP;
   short2* sidx = reinterpret_cast<short2*>(smem + OBS_WARPS * SM::WARP_DOUBLES);
   int* ctab = reinterpret_cast<int*>(sidx + NR * 32);
-  for (int r = warp; r < NR; r += OBS_WARPS) {
-    int gr = 0, gc = 0, own = 0;
-#pragma unroll
-    for (int rr = 0; rr < NR; ++rr)
-      if (rr == r) { gr = hi ? RCV::r1(rr) : RCV::r0(rr); gc = (q >> 1) ? RCV::c1(rr) : RCV::c0(rr); own = RCV::own(rr); }
-    short v[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int ea = 4 * gr + c4, eb = 4 * gc + ((2 * q + h) & 3);
-      const bool mine = (own >> (2 * hi + (q >> 1))) & 1;
-      int ci = -1;
-      if (mine && ea < C::NC && eb < C::NC && (gr != gc || ea <= eb)) ci = C::cidx(min(ea, eb), max(ea, eb));
-      v[h] = (short)ci;
-    }
-    sidx[r * 32 + lane] = make_short2(v[0], v[1]);
-  }
-  if (threadIdx.x < 64) {   // context products out = M[3 i + .] . D[. + j]: Mco (9), No (27), Nb (27, needs Mco: rounds 2, 3)
-    const int e = min((int)threadIdx.x, 62);
+  for (int r = warp; r < NR; r += OBS_WARPS)
+    sidx[r * 32 + lane] = make_short2((short)k1_store_index<STAGE>(r, lane, 0), (short)k1_store_index<STAGE>(r, lane, 1));
+  if (threadIdx.x < 64) {   // context products (ctx_raw_operands): Mco (9), No (27), Nb (27, needs Mco: rounds 2, 3)
     int m, d, o;
-    if (e < 9) { m = CtxRaw::RC + 3 * (e / 3); d = CtxRaw::RO + e % 3; o = CtxRaw::MCO + e; }
-    else if (e < 36) { const int f = e - 9, k = f / 9, i = (f % 9) / 3, j = f % 3; m = CtxRaw::MC + 3 * i; d = CtxRaw::PO + 9 + 9 * k + j; o = CtxRaw::NO + f; }
-    else { const int f = e - 36, k = f / 9, i = (f % 9) / 3, j = f % 3; m = CtxRaw::MCO + 3 * i; d = CtxRaw::PB + 9 + 9 * k + j; o = CtxRaw::NB + f; }
+    ctx_raw_operands(min((int)threadIdx.x, 62), m, d, o);
     ctab[threadIdx.x] = m | (d << 8) | (o << 16);
   }
   __syncthreads();

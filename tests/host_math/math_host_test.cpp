@@ -203,3 +203,79 @@ extern "C" int lmtest_replay(const mcba_options* opt, double cost0, double grad0
   *n_successful = s.num_successful; *n_unsuccessful = s.num_unsuccessful; *final_cost = s.x_cost;
   return n_rows;
 }
+
+// ---- fused observation kernels of round 2 (csrc/mcba_obs_fused.cuh): the two pieces that are plain arithmetic ----
+// Copy-free context (CtxRaw): raw prep records (or the identity record for a block that is not refined) + intrinsics as
+// the kernels copy them, the 63 products in the kernels' order, then obs_jacobian on that layout.
+template <int STAGE>
+static double run_raw(int model, int flags, const double* cam, const double* pose, const double* board,
+                      const double* intr, const double* xyz, const double* uv, double huber_a, double* r, double* J) {
+  typedef StageTraits<STAGE> T;
+  double pc[PREP], po[PREP], pb[PREP], ident[PREP] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, ctx[CtxRaw::SIZE] = {0};
+  const double zero6[6] = {0, 0, 0, 0, 0, 0};
+  prep_block(cam ? cam : zero6, pc);
+  prep_block(pose, po);
+  prep_block(board ? board : zero6, pb);
+  const bool act_c = T::CAM && !(flags & 1), act_b = T::BOARD && !(flags & 2);
+  for (int e = 0; e < PREP; ++e) {
+    ctx[CtxRaw::PC + e] = act_c ? pc[e] : ident[e];
+    ctx[CtxRaw::PO + e] = po[e];
+    ctx[CtxRaw::PB + e] = act_b ? pb[e] : ident[e];
+  }
+  for (int e = 0; e < 9; ++e) ctx[CtxRaw::IN + e] = intr[e];
+  for (int e = 0; e < 63; ++e) {          // Mco (e < 9) before the Nb products that read it, as in the kernels' rounds
+    int m, d, o;
+    ctx_raw_operands(e, m, d, o);
+    ctx[o] = ctx[m] * ctx[d] + ctx[m + 1] * ctx[d + 3] + ctx[m + 2] * ctx[d + 6];
+  }
+  ArraySink<STAGE> sink{J, r};
+  return obs_jacobian<STAGE, ArraySink<STAGE>, CtxRaw>(ctx, act_c, act_b, model, xyz, uv[0], uv[1], huber_a, sink);
+}
+extern "C" double mathtest_obs_raw(int stage, int model, int flags, const double* cam, const double* pose,
+                                   const double* board, const double* intr, const double* xyz, const double* uv,
+                                   double huber_a, double* r, double* J) {
+  switch (stage) {
+    case 1: return run_raw<1>(model, flags, cam, pose, board, intr, xyz, uv, huber_a, r, J);
+    case 2: return run_raw<2>(model, flags, cam, pose, board, intr, xyz, uv, huber_a, r, J);
+    case 3: return run_raw<3>(model, flags, cam, pose, board, intr, xyz, uv, huber_a, r, J);
+    case 4: return run_raw<4>(model, flags, cam, pose, board, intr, xyz, uv, huber_a, r, J);
+    case 5: return run_raw<5>(model, flags, cam, pose, board, intr, xyz, uv, huber_a, r, J);
+  }
+  return -1;
+}
+// Group-pair cover of the triangle: how many (product, lane, entry) triples of the DMMA accumulators land on each entry
+// of the compact record, plus, per product, the row / column groups; returns the record length (NCOMP).
+template <int STAGE> static int cover_counts(int* count, int* n_products, int* groups) {
+  typedef Cols<STAGE> C;
+  typedef RectCover<(C::NC + 3) / 4> RCV;
+  for (int i = 0; i < C::NCOMP; ++i) count[i] = 0;
+  for (int r = 0; r < RCV::NR; ++r) {
+    groups[4 * r] = RCV::r0(r); groups[4 * r + 1] = RCV::r1(r); groups[4 * r + 2] = RCV::c0(r); groups[4 * r + 3] = RCV::c1(r);
+    for (int lane = 0; lane < 32; ++lane)
+      for (int h = 0; h < 2; ++h) {
+        const int ci = k1_store_index<STAGE>(r, lane, h);
+        if (ci >= C::NCOMP) return -1;
+        if (ci >= 0) count[ci]++;
+      }
+  }
+  *n_products = RCV::NR;
+  return C::NCOMP;
+}
+extern "C" int mathtest_cover(int stage, int* count, int* n_products, int* groups) {
+  switch (stage) {
+    case 1: return cover_counts<1>(count, n_products, groups);
+    case 2: return cover_counts<2>(count, n_products, groups);
+    case 3: return cover_counts<3>(count, n_products, groups);
+    case 4: return cover_counts<4>(count, n_products, groups);
+    case 5: return cover_counts<5>(count, n_products, groups);
+  }
+  return -1;
+}
+// Which (column a, column b) of J~ a record entry holds (inverse of Cols<STAGE>::cidx), for the test's bookkeeping
+extern "C" int mathtest_cidx(int stage, int a, int b) {
+  switch (stage) {
+    case 1: return Cols<1>::cidx(a, b); case 2: return Cols<2>::cidx(a, b); case 3: return Cols<3>::cidx(a, b);
+    case 4: return Cols<4>::cidx(a, b); case 5: return Cols<5>::cidx(a, b);
+  }
+  return -2;
+}
