@@ -1220,6 +1220,8 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   Handle* H = new Handle();
   *handle = H;
   if (!P || P->n_obs < 0 || P->n_bobs < 0 || P->n_cam <= 0 || P->n_pose < 0) { H->err = "bad problem sizes"; return MCBA_ERR_INVALID; }
+  if (!P->cam_model || !P->bobs_ptr || (P->n_bobs > 0 && (!P->bobs_cam || !P->bobs_pose)) || (P->n_obs > 0 && (!P->u || !P->v || !P->pt_idx)) ||
+      (P->n_pts > 0 && !P->pts_xyz) || P->n_pts < 0) { H->err = "missing array in mcba_problem"; return MCBA_ERR_INVALID; }
   if (P->n_obs >= (int64_t)1 << 31 || P->n_bobs >= (int64_t)1 << 30) { H->err = "shard too large for 32-bit indices: split across handles"; return MCBA_ERR_INVALID; }
   if (P->cam_problem || P->n_problems > 1) {
     // batched independent problems: stage 1, one problem per camera, one board observation per e-block, camera-major
@@ -1248,6 +1250,8 @@ int mcba_create(void** handle, const mcba_problem* P, int device) {
   H->n_obs = P->n_obs; H->nb = (int)P->n_bobs; H->npad = ((P->n_obs + 31) / 32) * 32; H->n_obs_global = P->n_obs;
   mark("device + stream");
   // validate + pack the board-observation table (host, small)
+  for (int c = 0; c < P->n_cam; ++c)
+    if (P->cam_model[c] != 0 && P->cam_model[c] != 1) { H->err = "cam_model must be 0 (Brown) or 1 (Kannala)"; return MCBA_ERR_INVALID; }
   std::vector<int4> bobs(H->nb + 1);
   std::vector<int32_t>& bflags = H->h_bobs_flags;
   bflags.assign(H->nb + 1, 0);

@@ -261,6 +261,10 @@ def test_invalid_inputs_are_rejected():
         mcba.Handle(bad)
     with pytest.raises(mcba.McbaError):
         mcba.Handle(prob.with_stage(9))
+    bad = prob.with_stage(4)
+    bad.cam_model = prob.cam_model.copy(); bad.cam_model[1] = 7          # neither Brown nor Kannala
+    with pytest.raises(mcba.McbaError):
+        mcba.Handle(bad)
     h = mcba.Handle(prob)
     with pytest.raises(mcba.McbaError):
         h.solve_batched(init.copy())
