@@ -60,3 +60,23 @@ def test_reference_arm_runs_on_the_cpu():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
     assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["single_thread_value"] > 0
     assert d["config"]["frames"] == 12 and d["config"]["observations"] == d["cpu_baseline"]["observations_timed"]   # same config, same shard
+
+
+def test_committed_launch_list_holds_only_this_librarys_kernels():
+    """profiles/r02c_ncu_launches_bench_steps2.csv (ncu launch list of the bench command): every kernel that ran is one
+    of libmcba's own - no library kernel (cuBLAS, cuSOLVER, NCCL, torch) anywhere on the path - and the three
+    heavyweights of an LM iteration are there."""
+    import csv
+    import re
+    rows = list(csv.reader(open(os.path.join(REPO, "profiles", "r02c_ncu_launches_bench_steps2.csv"))))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    kn = rows[hi].index("Kernel Name")
+    names = {re.sub(r"\(.*", "", r[kn]).replace("void ", "").strip() for r in rows[hi + 1:] if len(r) > kn}
+    src = "".join(open(os.path.join(REPO, "mc-calib_b200", "csrc", f)).read()
+                  for f in os.listdir(os.path.join(REPO, "mc-calib_b200", "csrc")) if f.endswith((".cu", ".cuh")))
+    ours = set(re.findall(r"\b(k_[a-z0-9_]+)\s*\(", src))
+    assert len(names) >= 15
+    for n in names:
+        base = re.sub(r"<.*", "", n).replace("mcba::", "")
+        assert base in ours, n
+    assert {"k_syrk2", "k_chol_tiles", "k_observations_pair"} <= {re.sub(r"<.*", "", n).replace("mcba::", "") for n in names}
