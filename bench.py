@@ -44,7 +44,7 @@ FLOPS_PER_OBS = {4: 500 + 756, 5: 500 + 1620}                  # SURVEY.md §8(d
 FP64_PEAK_TFLOPS = 36.9    # measured on this pool's B200 with tools/peak_fp64.cu (DMMA m8n8k4), profiles/r01_peak_fp64.json
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the two K1 variants on the 6.18 M-observation
 # shard, from ncu --set full captures of this same command; NOT measured inside the run (ncu cannot run under the timer)
-NCU_TRAFFIC = {"fused": (77.5e6 + 367.3e6, "profiles/r02b_ncu_full_step_kernels.txt"),
+NCU_TRAFFIC = {"fused": (78.0e6 + 368.4e6, "profiles/r02c_ncu_full_step_kernels.txt"),
                "materialize": (77.6e6 + 2712.9e6, "profiles/r01c_ncu_full_materialize.txt")}
 METRIC = "LM bundle-adjustment throughput (full LM iteration: resid+Jac, normal equations, Schur, Cholesky, candidate cost)"
 
